@@ -1,0 +1,140 @@
+// mdb_comm.cu - multi-GPU plumbing: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+//
+// The reference is single-process and has no communication layer; the only exchange on
+// the path is the key-partitioned shuffle of join sides.  NCCL is resolved with dlopen
+// at mdbcu_comm_init time so the single-GPU path carries no link-time dependency on libnccl and a
+// process that already loaded torch's bundled libnccl.so.2 keeps using that copy.
+#include "mdb_common.cuh"
+
+#include <dlfcn.h>
+#include <string.h>
+
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+typedef int ncclDataType_t;
+#define NCCL_UINT8 1
+#define NCCL_UINT64 5
+
+struct NcclApi {
+	void *handle = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	ncclResult_t (*GroupStart)() = nullptr;
+	ncclResult_t (*GroupEnd)() = nullptr;
+	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi g_nccl;
+
+static int load_nccl(mdbcu_ctx *ctx)
+{
+	if (g_nccl.handle)
+		return MDBCU_OK;
+	const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+	void *h = nullptr;
+	for (int i = 0; names[i] && !h; i++)
+		h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+	if (!h)
+		return mdb_fail(ctx, MDBCU_ECUDA, "cannot load libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                                          \
+	do {                                                                                      \
+		*(void**)(&g_nccl.field) = dlsym(h, name);                                        \
+		if (!g_nccl.field)                                                                \
+			return mdb_fail(ctx, MDBCU_ECUDA, "libnccl is missing symbol %s", name);  \
+	} while (0)
+	SYM(GetUniqueId, "ncclGetUniqueId");
+	SYM(CommInitRank, "ncclCommInitRank");
+	SYM(CommDestroy, "ncclCommDestroy");
+	SYM(GroupStart, "ncclGroupStart");
+	SYM(GroupEnd, "ncclGroupEnd");
+	SYM(Send, "ncclSend");
+	SYM(Recv, "ncclRecv");
+	SYM(AllGather, "ncclAllGather");
+	SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+	g_nccl.handle = h;
+	return MDBCU_OK;
+}
+
+#define NCCL_TRY(ctx, call)                                                                       \
+	do {                                                                                      \
+		ncclResult_t _r = (call);                                                         \
+		if (_r != 0)                                                                      \
+			return mdb_fail((ctx), MDBCU_ECUDA, "%s failed: %s", #call, g_nccl.GetErrorString(_r)); \
+	} while (0)
+
+extern "C" int mdbcu_comm_unique_id(mdbcu_ctx *ctx, void *id128)
+{
+	if (!ctx || !id128)
+		return MDBCU_EERROR;
+	MDB_TRY(load_nccl(ctx));
+	ncclUniqueId id;
+	NCCL_TRY(ctx, g_nccl.GetUniqueId(&id));
+	memcpy(id128, &id, sizeof(id));
+	return MDBCU_OK;
+}
+
+extern "C" int mdbcu_comm_init(mdbcu_ctx *ctx, int rank, int world, const void *id128)
+{
+	if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world)
+		return ctx ? mdb_fail(ctx, MDBCU_EERROR, "mdbcu_comm_init: bad arguments") : MDBCU_EERROR;
+	cudaSetDevice(ctx->device);
+	MDB_TRY(load_nccl(ctx));
+	ncclUniqueId id;
+	memcpy(&id, id128, sizeof(id));
+	ncclComm_t comm = nullptr;
+	NCCL_TRY(ctx, g_nccl.CommInitRank(&comm, world, id, rank));
+	ctx->nccl_comm = comm;
+	ctx->rank = rank;
+	ctx->world = world;
+	return MDBCU_OK;
+}
+
+extern "C" int mdbcu_comm_world(mdbcu_ctx *ctx, int *rank, int *world)
+{
+	if (!ctx)
+		return MDBCU_EERROR;
+	if (rank)
+		*rank = ctx->rank;
+	if (world)
+		*world = ctx->world;
+	return MDBCU_OK;
+}
+
+void mdb_comm_destroy(mdbcu_ctx *ctx)
+{
+	if (ctx->nccl_comm && g_nccl.CommDestroy)
+		g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
+	ctx->nccl_comm = nullptr;
+}
+
+// byte-granular all-to-all: rank r receives send[send_off[r] .. send_off[r+1]) of every peer at recv_off[peer]
+int mdb_comm_alltoallv_bytes(mdbcu_ctx *ctx, const void *send, const uint64_t *send_off, void *recv, const uint64_t *recv_off)
+{
+	if (!ctx->nccl_comm)
+		return mdb_fail(ctx, MDBCU_EERROR, "distributed plan without mdbcu_comm_init");
+	ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+	NCCL_TRY(ctx, g_nccl.GroupStart());
+	for (int p = 0; p < ctx->world; p++) {
+		uint64_t sb = send_off[p + 1] - send_off[p], rb = recv_off[p + 1] - recv_off[p];
+		if (sb)
+			NCCL_TRY(ctx, g_nccl.Send((const char*)send + send_off[p], sb, NCCL_UINT8, p, comm, ctx->stream));
+		if (rb)
+			NCCL_TRY(ctx, g_nccl.Recv((char*)recv + recv_off[p], rb, NCCL_UINT8, p, comm, ctx->stream));
+	}
+	NCCL_TRY(ctx, g_nccl.GroupEnd());
+	return MDBCU_OK;
+}
+
+int mdb_comm_allgather_u64(mdbcu_ctx *ctx, const uint64_t *send, uint64_t *recv, size_t count)
+{
+	if (!ctx->nccl_comm)
+		return mdb_fail(ctx, MDBCU_EERROR, "distributed plan without mdbcu_comm_init");
+	NCCL_TRY(ctx, g_nccl.AllGather(send, recv, count, NCCL_UINT64, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+	return MDBCU_OK;
+}

@@ -1,0 +1,273 @@
+// mdb_common.cuh - shared declarations of libmidoridb_cuda.so (sm_100a only).
+//
+// Device mirror layout (SURVEY.md 8a "a1"): the reference keeps rows as an array-of-structs inside
+// 4 KiB pages (include/primitive/row.h:22-28, datablock.h:9-13).  The mirror is columnar: one
+// 8-byte-cell array per column plus a "present" bitmap (bit = row is live AND cell is not NULL) and one
+// "live" bitmap per table.  Device row id = page * rows_per_page + slot with
+// rows_per_page = floor(4095 / row_size) (row.c:38), so (page, slot) <-> row id is stable across DML.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "midoridb_cuda.h"
+
+#define MDB_WARP 32
+
+struct mdbcu_ctx {
+	int device = 0;
+	int num_sms = 0;
+	cudaStream_t stream = nullptr;
+	std::string err;
+	mdbcu_stats stats{};
+	uint64_t total_launches = 0;
+	// multi-GPU
+	int rank = 0, world = 1;
+	void *nccl_comm = nullptr;
+	// reusable scratch: pinned host word for small D2H reads
+	uint64_t *h_scalar = nullptr; // pinned, 64 entries
+	uint64_t *d_scalar = nullptr; // device, 64 entries
+};
+
+struct DevColumn {
+	int type = 0;
+	int width = 8;             // bytes in the reference row (column.c:255)
+	int row_off = 0;           // byte offset inside row->data
+	int64_t *data = nullptr;   // n_slots cells (double kept as raw bits)
+	uint32_t *present = nullptr; // bitmap, bit i = live && not NULL
+	bool has_nulls = false;
+	bool stats_ok = false;     // imin/imax valid (conservative bounds over present cells)
+	int64_t imin = 0, imax = 0;
+};
+
+struct mdbcu_table {
+	mdbcu_ctx *ctx = nullptr;
+	std::string name;
+	int ncols = 0;
+	size_t row_size = 0;       // 24 + sum(width)  (row.c:21)
+	size_t rows_per_page = 0;  // floor(4095/row_size)
+	uint64_t n_slots = 0;      // device rows in use (index space)
+	uint64_t cap = 0;          // allocated rows
+	uint64_t n_pages = 0;
+	bool paged = false;
+	bool all_live = true;      // every slot in [0, n_slots) is live
+	uint32_t *live = nullptr;  // bitmap
+	std::vector<DevColumn> cols;
+};
+
+struct ResultColumn {
+	int type = MDBCU_CT_INTEGER;
+	int64_t *cells = nullptr; // device
+	uint8_t *nulls = nullptr; // device byte flags (nullptr = no NULLs)
+};
+
+struct mdbcu_result {
+	mdbcu_ctx *ctx = nullptr;
+	uint64_t nrows = 0;
+	std::vector<ResultColumn> cols;
+	uint64_t *order_key = nullptr; // device; optional canonical-order key (reference row order)
+	bool owns = true;
+};
+
+// ---------------------------------------------------------------- error handling
+
+int mdb_fail(mdbcu_ctx *ctx, int code, const char *fmt, ...);
+void mdb_set_global_error(const char *msg);
+
+#define CUDA_TRY(ctx, call)                                                                  \
+	do {                                                                                 \
+		cudaError_t _e = (call);                                                     \
+		if (_e != cudaSuccess)                                                       \
+			return mdb_fail((ctx), MDBCU_ECUDA, "%s failed at %s:%d: %s", #call, \
+					__FILE__, __LINE__, cudaGetErrorString(_e));         \
+	} while (0)
+
+#define MDB_TRY(call)              \
+	do {                       \
+		int _rc = (call);  \
+		if (_rc != MDBCU_OK) \
+			return _rc; \
+	} while (0)
+
+// every kernel launch goes through this so `gpu_launches` is counted, not guessed
+#define MDB_LAUNCH(ctx, kernel, grid, block, smem, ...)                                  \
+	do {                                                                             \
+		kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);         \
+		(ctx)->stats.kernel_launches++;                                          \
+		(ctx)->total_launches++;                                                 \
+	} while (0)
+
+#define CUDA_CHECK_LAUNCH(ctx) CUDA_TRY(ctx, cudaGetLastError())
+
+// ---------------------------------------------------------------- memory (stream-ordered pool)
+
+template <typename T>
+static inline int mdb_alloc(mdbcu_ctx *ctx, T **out, size_t count)
+{
+	void *p = nullptr;
+	size_t bytes = (count ? count : 1) * sizeof(T);
+	cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+	if (e != cudaSuccess) {
+		*out = nullptr;
+		return mdb_fail(ctx, e == cudaErrorMemoryAllocation ? MDBCU_ENOMEM : MDBCU_ECUDA,
+				"device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+	}
+	*out = (T*)p;
+	return MDBCU_OK;
+}
+
+static inline void mdb_free(mdbcu_ctx *ctx, void *p)
+{
+	if (p)
+		cudaFreeAsync(p, ctx->stream);
+}
+
+// RAII holder for query temporaries
+struct DevTemp {
+	mdbcu_ctx *ctx;
+	std::vector<void*> ptrs;
+	explicit DevTemp(mdbcu_ctx *c) : ctx(c) {}
+	~DevTemp()
+	{
+		for (void *p : ptrs)
+			mdb_free(ctx, p);
+	}
+	template <typename T>
+	int alloc(T **out, size_t count)
+	{
+		int rc = mdb_alloc(ctx, out, count);
+		if (rc == MDBCU_OK)
+			ptrs.push_back(*out);
+		return rc;
+	}
+	// hand ownership of p to the caller
+	void release(void *p)
+	{
+		for (auto &q : ptrs)
+			if (q == p)
+				q = nullptr;
+	}
+};
+
+// ---------------------------------------------------------------- device helpers
+
+__host__ __device__ static inline uint64_t mdb_mix64(uint64_t x)
+{
+	x ^= x >> 33;
+	x *= 0xff51afd7ed558ccdULL;
+	x ^= x >> 33;
+	x *= 0xc4ceb9fe1a85ec53ULL;
+	x ^= x >> 33;
+	return x;
+}
+
+__device__ static inline bool mdb_bit(const uint32_t *bm, uint64_t i)
+{
+	return (bm[i >> 5] >> (i & 31)) & 1u;
+}
+
+// streaming 128-bit load: data read once, keep it out of L1
+__device__ static inline int4 mdb_ldg_stream(const int4 *p)
+{
+	int4 r;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];"
+			: "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+			: "l"(p));
+	return r;
+}
+
+__device__ static inline uint32_t mdb_ldg_stream_u32(const uint32_t *p)
+{
+	uint32_t r;
+	asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+	return r;
+}
+
+// order-preserving map double <-> int64 so MIN/MAX on doubles can use integer atomics
+__host__ __device__ static inline int64_t mdb_dbl_to_ordered(int64_t bits)
+{
+	return bits < 0 ? (int64_t)(~(uint64_t)bits ^ 0x8000000000000000ULL) : bits;
+}
+__host__ __device__ static inline int64_t mdb_ordered_to_dbl(int64_t o)
+{
+	return o < 0 ? (int64_t)(~((uint64_t)o ^ 0x8000000000000000ULL)) : o;
+}
+
+static inline size_t mdb_div_up(size_t a, size_t b)
+{
+	return (a + b - 1) / b;
+}
+
+static inline int mdb_col_width(int type)
+{
+	return type == MDBCU_CT_TINYINT ? 1 : 8; // table_calc_column_space, column.c:255-293
+}
+
+// ---------------------------------------------------------------- cross-file entry points
+
+// exclusive prefix sums (mdb_ops.cu); *_total are device pointers receiving the grand total
+int mdb_scan_u32_u64(mdbcu_ctx *ctx, const uint32_t *in, uint64_t *out, size_t n, uint64_t *d_total);
+int mdb_scan_u64_u64(mdbcu_ctx *ctx, const uint64_t *in, uint64_t *out, size_t n, uint64_t *d_total);
+// read one 64-bit device word (synchronises the stream)
+int mdb_read_u64(mdbcu_ctx *ctx, const uint64_t *d_ptr, uint64_t *out);
+
+int mdb_table_reserve(mdbcu_table *t, uint64_t rows);
+int mdb_result_alloc(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res, uint64_t nrows, bool with_order);
+int mdb_table_refresh_stats(mdbcu_table *t, int col);
+
+// physical paths (return MDBCU_EUNSUPPORTED when the plan does not fit so the caller can fall through)
+int mdb_select_general(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res);
+int mdb_select_scan_agg(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res);
+int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res);
+int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res);
+
+// multi-GPU exchange used by the radix join path (mdb_comm.cu)
+int mdb_comm_alltoallv_bytes(mdbcu_ctx *ctx, const void *send, const uint64_t *send_off, void *recv,
+		const uint64_t *recv_off);
+void mdb_comm_destroy(mdbcu_ctx *ctx);
+int mdb_comm_allgather_u64(mdbcu_ctx *ctx, const uint64_t *send, uint64_t *recv, size_t count);
+
+// phase clock: events are only recorded while the query runs; one synchronise at the end
+struct PhaseClock {
+	mdbcu_ctx *ctx;
+	std::vector<cudaEvent_t> ev;
+	std::vector<int> ph;
+	explicit PhaseClock(mdbcu_ctx *c) : ctx(c) {}
+	void begin(int phase)
+	{
+		cudaEvent_t e;
+		cudaEventCreate(&e);
+		cudaEventRecord(e, ctx->stream);
+		ev.push_back(e);
+		ph.push_back(phase);
+	}
+	// closes the last phase, waits for the stream and fills stats.phase_ms / total_ms
+	void finish()
+	{
+		if (ev.empty())
+			return;
+		begin(-1);
+		cudaEventSynchronize(ev.back());
+		for (size_t i = 0; i + 1 < ev.size(); i++) {
+			float ms = 0.f;
+			cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+			if (ph[i] >= 0 && ph[i] < 8)
+				ctx->stats.phase_ms[ph[i]] += ms;
+		}
+		float total = 0.f;
+		cudaEventElapsedTime(&total, ev.front(), ev.back());
+		ctx->stats.total_ms = total;
+		for (cudaEvent_t e : ev)
+			cudaEventDestroy(e);
+		ev.clear();
+		ph.clear();
+	}
+	~PhaseClock()
+	{
+		for (cudaEvent_t e : ev)
+			cudaEventDestroy(e);
+	}
+};

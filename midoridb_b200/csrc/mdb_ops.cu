@@ -1,0 +1,1242 @@
+// mdb_ops.cu - general physical operators of the SELECT path (any plan shape the ABI can express).
+//
+// The reference materialises early and interprets per row (src/engine/executor_select.c); here the same
+// stages run as data-parallel kernels over row-id tuples (late materialisation):
+//   proc_from_clause_table :1282            -> live-row scan (bitmap compaction)
+//   _join_nested_loop_tbl2tbl/_tbl2mat :1076,:1151 -> hash build (CSR multimap) + probe count/emit
+//   proc_where_clause :1435, eval_row_cond :1027    -> k_eval_pred (postfix program) + compaction
+//   proc_groupby_clause :1526, inc_count_cols :1501 -> k_group_update (open-addressing hash aggregate)
+//   handle_countonly_case :1590                     -> the same aggregate with a single constant group
+//   proc_select_clause :1369                        -> k_gather_out
+// The fused fast paths for the benchmark shapes live in mdb_fast.cu.
+#include "mdb_common.cuh"
+
+#include <string.h>
+#include <algorithm>
+#include <new>
+
+// =========================================================================================== scan
+
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+template <typename T>
+__device__ static inline T block_exclusive_scan(T v, T *total, T *smem /* 32 entries */)
+{
+	int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+	T incl = v;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		T n = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o)
+			incl += n;
+	}
+	if (lane == 31)
+		smem[warp] = incl;
+	__syncthreads();
+	if (warp == 0) {
+		T w = lane < nwarps ? smem[lane] : (T)0;
+		T wi = w;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			T n = __shfl_up_sync(0xffffffffu, wi, o);
+			if (lane >= o)
+				wi += n;
+		}
+		smem[lane] = wi - w; // exclusive warp offsets
+		if (lane == 31)
+			smem[32] = wi; // block total
+	}
+	__syncthreads();
+	T res = smem[warp] + incl - v;
+	if (total)
+		*total = smem[32];
+	__syncthreads();
+	return res;
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const TIn *__restrict__ in, size_t n, uint64_t *__restrict__ block_sums)
+{
+	__shared__ uint64_t sm[33];
+	size_t base = (size_t)blockIdx.x * SCAN_TILE;
+	uint64_t acc = 0;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; k++) {
+		size_t i = base + (size_t)k * SCAN_THREADS + threadIdx.x;
+		if (i < n)
+			acc += (uint64_t)in[i];
+	}
+	uint64_t total;
+	block_exclusive_scan<uint64_t>(acc, &total, sm);
+	if (threadIdx.x == 0)
+		block_sums[blockIdx.x] = total;
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const TIn *__restrict__ in, uint64_t *__restrict__ out, size_t n,
+		const uint64_t *__restrict__ block_offs, uint64_t *__restrict__ d_total)
+{
+	__shared__ uint64_t sm[33];
+	size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+	uint64_t v[SCAN_ITEMS];
+	uint64_t acc = 0;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; k++) {
+		size_t i = base + k;
+		v[k] = i < n ? (uint64_t)in[i] : 0;
+		acc += v[k];
+	}
+	uint64_t total;
+	uint64_t off = block_exclusive_scan<uint64_t>(acc, &total, sm) + (block_offs ? block_offs[blockIdx.x] : 0);
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; k++) {
+		size_t i = base + k;
+		if (i < n)
+			out[i] = off;
+		off += v[k];
+	}
+	if (d_total && blockIdx.x == gridDim.x - 1 && threadIdx.x == SCAN_THREADS - 1)
+		*d_total = off;
+}
+
+template <typename TIn>
+static int scan_impl(mdbcu_ctx *ctx, const TIn *in, uint64_t *out, size_t n, uint64_t *d_total)
+{
+	if (n == 0) {
+		if (d_total)
+			CUDA_TRY(ctx, cudaMemsetAsync(d_total, 0, sizeof(uint64_t), ctx->stream));
+		return MDBCU_OK;
+	}
+	size_t nblocks = mdb_div_up(n, SCAN_TILE);
+	if (nblocks == 1) {
+		MDB_LAUNCH(ctx, k_scan_apply<TIn>, 1, SCAN_THREADS, 0, in, out, n, (const uint64_t*)nullptr, d_total);
+		CUDA_CHECK_LAUNCH(ctx);
+		return MDBCU_OK;
+	}
+	DevTemp tmp(ctx);
+	uint64_t *sums, *offs;
+	MDB_TRY(tmp.alloc(&sums, nblocks));
+	MDB_TRY(tmp.alloc(&offs, nblocks));
+	MDB_LAUNCH(ctx, k_scan_reduce<TIn>, (unsigned)nblocks, SCAN_THREADS, 0, in, n, sums);
+	CUDA_CHECK_LAUNCH(ctx);
+	MDB_TRY(scan_impl<uint64_t>(ctx, sums, offs, nblocks, nullptr));
+	MDB_LAUNCH(ctx, k_scan_apply<TIn>, (unsigned)nblocks, SCAN_THREADS, 0, in, out, n, (const uint64_t*)offs, d_total);
+	CUDA_CHECK_LAUNCH(ctx);
+	return MDBCU_OK;
+}
+
+int mdb_scan_u32_u64(mdbcu_ctx *ctx, const uint32_t *in, uint64_t *out, size_t n, uint64_t *d_total)
+{
+	return scan_impl<uint32_t>(ctx, in, out, n, d_total);
+}
+
+int mdb_scan_u64_u64(mdbcu_ctx *ctx, const uint64_t *in, uint64_t *out, size_t n, uint64_t *d_total)
+{
+	return scan_impl<uint64_t>(ctx, in, out, n, d_total);
+}
+
+// =========================================================================================== tuples
+
+struct Tuples {
+	int ntab = 0;
+	uint64_t n = 0;
+	uint32_t *rid[MDBCU_MAX_TABLES] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+struct TuplesDev {
+	int ntab;
+	uint64_t n;
+	const uint32_t *rid[MDBCU_MAX_TABLES];
+};
+
+static TuplesDev to_dev(const Tuples &t)
+{
+	TuplesDev d;
+	d.ntab = t.ntab;
+	d.n = t.n;
+	for (int i = 0; i < MDBCU_MAX_TABLES; i++)
+		d.rid[i] = t.rid[i];
+	return d;
+}
+
+static void free_tuples(mdbcu_ctx *ctx, Tuples &t)
+{
+	for (int i = 0; i < MDBCU_MAX_TABLES; i++) {
+		mdb_free(ctx, t.rid[i]);
+		t.rid[i] = nullptr;
+	}
+	t.n = 0;
+}
+
+// ------------------------------------------------------------------------------- bitmap compaction
+// items flagged in `bits` (bit i <-> item i, i < n) are written in order to dst[k] = src[k] ? src[k][i] : i
+
+#define CMP_THREADS 256
+
+__global__ void __launch_bounds__(CMP_THREADS) k_compact_count(const uint32_t *__restrict__ bits, uint64_t n, uint32_t *__restrict__ block_counts)
+{
+	__shared__ uint32_t sm[33];
+	uint64_t words = (n + 31) / 32;
+	uint64_t w = (uint64_t)blockIdx.x * CMP_THREADS + threadIdx.x;
+	uint32_t c = 0;
+	if (w < words) {
+		uint32_t valid = (w == words - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
+		c = __popc(bits[w] & valid);
+	}
+	uint32_t total;
+	block_exclusive_scan<uint32_t>(c, &total, sm);
+	if (threadIdx.x == 0)
+		block_counts[blockIdx.x] = total;
+}
+
+struct CompactArrays {
+	int narr;
+	const uint32_t *src[MDBCU_MAX_TABLES];
+	uint32_t *dst[MDBCU_MAX_TABLES];
+};
+
+__global__ void __launch_bounds__(CMP_THREADS) k_compact_write(const uint32_t *__restrict__ bits, uint64_t n,
+		const uint64_t *__restrict__ block_offs, CompactArrays arr)
+{
+	__shared__ uint32_t sm[33];
+	uint64_t words = (n + 31) / 32;
+	uint64_t w = (uint64_t)blockIdx.x * CMP_THREADS + threadIdx.x;
+	uint32_t b = 0;
+	if (w < words) {
+		uint32_t valid = (w == words - 1 && (n & 31)) ? ((1u << (n & 31)) - 1u) : 0xffffffffu;
+		b = bits[w] & valid;
+	}
+	uint32_t off = block_exclusive_scan<uint32_t>(__popc(b), nullptr, sm);
+	uint64_t o = block_offs[blockIdx.x] + off;
+	while (b) {
+		int bit = __ffs(b) - 1;
+		b &= b - 1;
+		uint64_t i = w * 32 + bit;
+		for (int k = 0; k < arr.narr; k++)
+			arr.dst[k][o] = arr.src[k] ? arr.src[k][i] : (uint32_t)i;
+		o++;
+	}
+}
+
+// compacts `in` (or the identity when in == nullptr, ntab = 1) by `bits`; result arrays are freshly allocated
+static int compact_tuples(mdbcu_ctx *ctx, const uint32_t *bits, uint64_t n, const Tuples *in, int ntab, Tuples *out)
+{
+	out->ntab = ntab;
+	out->n = 0;
+	if (n == 0)
+		return MDBCU_OK;
+	DevTemp tmp(ctx);
+	uint64_t words = (n + 31) / 32;
+	size_t nblocks = mdb_div_up(words, CMP_THREADS);
+	uint32_t *counts;
+	uint64_t *offs, *d_total;
+	MDB_TRY(tmp.alloc(&counts, nblocks));
+	MDB_TRY(tmp.alloc(&offs, nblocks));
+	MDB_TRY(tmp.alloc(&d_total, 1));
+	MDB_LAUNCH(ctx, k_compact_count, (unsigned)nblocks, CMP_THREADS, 0, bits, n, counts);
+	CUDA_CHECK_LAUNCH(ctx);
+	MDB_TRY(mdb_scan_u32_u64(ctx, counts, offs, nblocks, d_total));
+	uint64_t total = 0;
+	MDB_TRY(mdb_read_u64(ctx, d_total, &total));
+	out->n = total;
+	if (total == 0)
+		return MDBCU_OK;
+	CompactArrays arr;
+	arr.narr = ntab;
+	for (int k = 0; k < MDBCU_MAX_TABLES; k++) {
+		arr.src[k] = nullptr;
+		arr.dst[k] = nullptr;
+	}
+	for (int k = 0; k < ntab; k++) {
+		int rc = mdb_alloc(ctx, &out->rid[k], total);
+		if (rc != MDBCU_OK) {
+			free_tuples(ctx, *out);
+			return rc;
+		}
+		arr.src[k] = in ? in->rid[k] : nullptr;
+		arr.dst[k] = out->rid[k];
+	}
+	MDB_LAUNCH(ctx, k_compact_write, (unsigned)nblocks, CMP_THREADS, 0, bits, n, (const uint64_t*)offs, arr);
+	CUDA_CHECK_LAUNCH(ctx);
+	return MDBCU_OK;
+}
+
+__global__ void k_iota(uint32_t *out, uint64_t n)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		out[i] = (uint32_t)i;
+}
+
+static int grid_for(mdbcu_ctx *ctx, uint64_t n, int threads)
+{
+	uint64_t g = mdb_div_up(n ? n : 1, threads);
+	return (int)std::min<uint64_t>(g, (uint64_t)ctx->num_sms * 16);
+}
+
+// FROM <table>: live rows in storage order (proc_from_clause_table, executor_select.c:1295-1306)
+static int scan_live(mdbcu_ctx *ctx, const mdbcu_table *t, Tuples *out)
+{
+	out->ntab = 1;
+	out->n = 0;
+	if (t->n_slots == 0)
+		return MDBCU_OK;
+	if (t->all_live) {
+		MDB_TRY(mdb_alloc(ctx, &out->rid[0], t->n_slots));
+		MDB_LAUNCH(ctx, k_iota, grid_for(ctx, t->n_slots, 256), 256, 0, out->rid[0], t->n_slots);
+		CUDA_CHECK_LAUNCH(ctx);
+		out->n = t->n_slots;
+		return MDBCU_OK;
+	}
+	return compact_tuples(ctx, t->live, t->n_slots, nullptr, 1, out);
+}
+
+// =========================================================================================== predicate
+
+struct DPredOp {
+	int32_t op, arg;
+	int32_t tbl, is_dbl;
+	const int64_t *data;
+	const uint32_t *present; // nullptr = every cell present
+	int64_t ival;
+	double dval;
+};
+
+struct DPredProgram {
+	int32_t n;
+	int32_t _pad;
+	DPredOp ops[MDBCU_MAX_PRED];
+};
+
+struct PVal {
+	int kind; // 0 int, 1 double, 2 null, 3 bool
+	int64_t i;
+};
+
+__device__ static inline bool pv_cmp(int cmp, PVal a, PVal b)
+{
+	if (a.kind == 2 || b.kind == 2)
+		return false; // executor_select.c:629-631
+	if (a.kind == 1 || b.kind == 1) {
+		double x = a.kind == 1 ? __longlong_as_double(a.i) : (double)a.i;
+		double y = b.kind == 1 ? __longlong_as_double(b.i) : (double)b.i;
+		switch (cmp) {
+		case 1: return x < y;
+		case 2: return x > y;
+		case 3: return x != y;
+		case 4: return x == y;
+		case 5: return x <= y;
+		case 6: return x >= y;
+		}
+		return false;
+	}
+	switch (cmp) {
+	case 1: return a.i < b.i;
+	case 2: return a.i > b.i;
+	case 3: return a.i != b.i;
+	case 4: return a.i == b.i;
+	case 5: return a.i <= b.i;
+	case 6: return a.i >= b.i;
+	}
+	return false;
+}
+
+#define PRED_STACK 24
+
+__device__ static bool eval_program(const DPredProgram *__restrict__ prog, const TuplesDev &ts, uint64_t i)
+{
+	PVal st[PRED_STACK];
+	int sp = 0;
+	for (int k = 0; k < prog->n; k++) {
+		const DPredOp &op = prog->ops[k];
+		PVal v;
+		v.kind = 3;
+		v.i = 0;
+		switch (op.op) {
+		case MDBCU_P_COL: {
+			uint32_t r = ts.rid[op.tbl][i];
+			if (op.present && !mdb_bit(op.present, r)) {
+				v.kind = 2;
+			} else {
+				v.kind = op.is_dbl ? 1 : 0;
+				v.i = op.data[r];
+			}
+			st[sp++] = v;
+			break;
+		}
+		case MDBCU_P_INT:
+			v.kind = 0; v.i = op.ival; st[sp++] = v;
+			break;
+		case MDBCU_P_DBL:
+			v.kind = 1; v.i = __double_as_longlong(op.dval); st[sp++] = v;
+			break;
+		case MDBCU_P_NULL:
+			v.kind = 2; st[sp++] = v;
+			break;
+		case MDBCU_P_BOOL:
+			v.kind = 3; v.i = op.ival != 0; st[sp++] = v;
+			break;
+		case MDBCU_P_CMP: {
+			PVal b = st[--sp], a = st[--sp];
+			v.i = pv_cmp(op.arg, a, b); st[sp++] = v;
+			break;
+		}
+		case MDBCU_P_AND: case MDBCU_P_OR: case MDBCU_P_XOR: {
+			PVal b = st[--sp], a = st[--sp];
+			bool x = a.i != 0, y = b.i != 0;
+			v.i = op.op == MDBCU_P_AND ? (x && y) : (op.op == MDBCU_P_OR ? (x || y) : (x != y));
+			st[sp++] = v;
+			break;
+		}
+		case MDBCU_P_ISNULL: case MDBCU_P_ISNOTNULL: {
+			PVal a = st[--sp];
+			v.i = (a.kind == 2) != (op.op == MDBCU_P_ISNOTNULL); st[sp++] = v;
+			break;
+		}
+		case MDBCU_P_IN: case MDBCU_P_NOTIN: {
+			int n = op.arg;
+			PVal probe = st[sp - n - 1];
+			bool any = false, all_diff = true;
+			for (int j = 0; j < n; j++) {
+				PVal e = st[sp - n + j];
+				any = any || pv_cmp(4, probe, e);
+				all_diff = all_diff && pv_cmp(3, probe, e);
+			}
+			sp -= n + 1;
+			v.i = op.op == MDBCU_P_IN ? any : all_diff; st[sp++] = v;
+			break;
+		}
+		}
+	}
+	return sp == 1 && st[0].i != 0;
+}
+
+__global__ void k_eval_pred(const DPredProgram *__restrict__ prog, TuplesDev ts, uint32_t *__restrict__ bits)
+{
+	// one aligned group of 32 tuples per warp iteration, so every ballot is exactly one bitmap word
+	uint64_t groups = (ts.n + 31) / 32;
+	uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	int lane = threadIdx.x & 31;
+	for (uint64_t g = warp; g < groups; g += nwarps) {
+		uint64_t i = g * 32 + lane;
+		bool keep = i < ts.n && eval_program(prog, ts, i);
+		uint32_t b = __ballot_sync(0xffffffffu, keep);
+		if (lane == 0)
+			bits[g] = b;
+	}
+}
+
+static int check_colref(mdbcu_ctx *ctx, const mdbcu_plan *plan, int tbl, int col, const char *what)
+{
+	if (tbl < 0 || tbl >= plan->n_tables || col < 0 || col >= plan->tables[tbl]->ncols)
+		return mdb_fail(ctx, MDBCU_EERROR, "%s references table %d column %d outside the plan", what, tbl, col);
+	if (plan->tables[tbl]->cols[col].type == MDBCU_CT_VARCHAR)
+		return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "%s uses a VARCHAR column (not mirrored on the device)", what);
+	return MDBCU_OK;
+}
+
+static bool col_all_present(const mdbcu_table *t, int col)
+{
+	return t->all_live && !t->cols[col].has_nulls;
+}
+
+static int build_pred(mdbcu_ctx *ctx, const mdbcu_plan *plan, DPredProgram *h)
+{
+	int depth = 0;
+	h->n = plan->n_pred;
+	h->_pad = 0;
+	if (plan->n_pred < 0 || plan->n_pred > MDBCU_MAX_PRED)
+		return mdb_fail(ctx, MDBCU_EERROR, "predicate program too long");
+	for (int k = 0; k < plan->n_pred; k++) {
+		const mdbcu_pred_op &s = plan->pred[k];
+		DPredOp &d = h->ops[k];
+		d.op = s.op;
+		d.arg = s.arg;
+		d.tbl = s.tbl;
+		d.is_dbl = 0;
+		d.data = nullptr;
+		d.present = nullptr;
+		d.ival = s.ival;
+		d.dval = s.dval;
+		switch (s.op) {
+		case MDBCU_P_COL: {
+			MDB_TRY(check_colref(ctx, plan, s.tbl, s.col, "WHERE"));
+			const mdbcu_table *t = plan->tables[s.tbl];
+			d.data = t->cols[s.col].data;
+			d.present = col_all_present(t, s.col) ? nullptr : t->cols[s.col].present;
+			d.is_dbl = t->cols[s.col].type == MDBCU_CT_DOUBLE;
+			depth++;
+			break;
+		}
+		case MDBCU_P_INT: case MDBCU_P_DBL: case MDBCU_P_NULL: case MDBCU_P_BOOL:
+			depth++;
+			break;
+		case MDBCU_P_CMP:
+			if (s.arg < 1 || s.arg > 6)
+				return mdb_fail(ctx, MDBCU_EERROR, "bad comparison code %d", s.arg);
+			/* fallthrough */
+		case MDBCU_P_AND: case MDBCU_P_OR: case MDBCU_P_XOR:
+			if (depth < 2)
+				return mdb_fail(ctx, MDBCU_EERROR, "malformed predicate program");
+			depth--;
+			break;
+		case MDBCU_P_ISNULL: case MDBCU_P_ISNOTNULL:
+			if (depth < 1)
+				return mdb_fail(ctx, MDBCU_EERROR, "malformed predicate program");
+			break;
+		case MDBCU_P_IN: case MDBCU_P_NOTIN:
+			if (s.arg < 1 || depth < s.arg + 1)
+				return mdb_fail(ctx, MDBCU_EERROR, "malformed predicate program");
+			depth -= s.arg;
+			break;
+		default:
+			return mdb_fail(ctx, MDBCU_EERROR, "unknown predicate op %d", s.op);
+		}
+		if (depth > PRED_STACK)
+			return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "predicate nests deeper than %d operands", PRED_STACK);
+	}
+	if (plan->n_pred && depth != 1)
+		return mdb_fail(ctx, MDBCU_EERROR, "malformed predicate program");
+	return MDBCU_OK;
+}
+
+static int filter_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, Tuples *ts)
+{
+	if (plan->n_pred == 0 || ts->n == 0)
+		return MDBCU_OK;
+	DPredProgram h;
+	MDB_TRY(build_pred(ctx, plan, &h));
+	DevTemp tmp(ctx);
+	DPredProgram *d_prog;
+	uint32_t *bits;
+	MDB_TRY(tmp.alloc(&d_prog, 1));
+	MDB_TRY(tmp.alloc(&bits, (ts->n + 31) / 32));
+	CUDA_TRY(ctx, cudaMemcpyAsync(d_prog, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+	MDB_LAUNCH(ctx, k_eval_pred, grid_for(ctx, ts->n, 256), 256, 0, (const DPredProgram*)d_prog, to_dev(*ts), bits);
+	CUDA_CHECK_LAUNCH(ctx);
+	Tuples out;
+	MDB_TRY(compact_tuples(ctx, bits, ts->n, ts, ts->ntab, &out));
+	free_tuples(ctx, *ts);
+	*ts = out;
+	return MDBCU_OK;
+}
+
+// =========================================================================================== hash join
+
+#define HT_EMPTY ((long long)0x8000000000000000LL) // INT64_MIN is the empty marker; that key value uses slot `cap`
+
+// normalise a key for equality hashing: -0.0 == +0.0 for doubles
+__device__ static inline long long norm_key(int64_t v, int is_dbl)
+{
+	if (is_dbl && v == (int64_t)0x8000000000000000LL)
+		return 0;
+	return v;
+}
+
+__device__ static inline bool key_is_nan(int64_t v)
+{
+	return (v & 0x7ff0000000000000LL) == 0x7ff0000000000000LL && (v & 0x000fffffffffffffLL) != 0;
+}
+
+__device__ static inline uint64_t ht_insert(long long *keys, uint64_t cap_mask, long long key)
+{
+	if (key == HT_EMPTY)
+		return cap_mask + 1;
+	uint64_t s = mdb_mix64((uint64_t)key) & cap_mask;
+	while (true) {
+		long long prev = keys[s];
+		if (prev == key)
+			return s;
+		if (prev == HT_EMPTY) {
+			prev = atomicCAS((unsigned long long*)&keys[s], (unsigned long long)HT_EMPTY, (unsigned long long)key);
+			if (prev == HT_EMPTY || prev == key)
+				return s;
+		}
+		s = (s + 1) & cap_mask;
+	}
+}
+
+__device__ static inline bool ht_find(const long long *keys, uint64_t cap_mask, long long key, uint64_t *slot)
+{
+	if (key == HT_EMPTY) {
+		*slot = cap_mask + 1;
+		return true; // the caller checks the count of the special slot
+	}
+	uint64_t s = mdb_mix64((uint64_t)key) & cap_mask;
+	while (true) {
+		long long prev = keys[s];
+		if (prev == key) {
+			*slot = s;
+			return true;
+		}
+		if (prev == HT_EMPTY)
+			return false;
+		s = (s + 1) & cap_mask;
+	}
+}
+
+__global__ void k_fill_i64(long long *p, uint64_t n, long long v)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		p[i] = v;
+}
+
+__global__ void k_join_build_count(const int64_t *__restrict__ data, const uint32_t *__restrict__ present, uint64_t n, int is_dbl,
+		long long *__restrict__ keys, uint64_t cap_mask, uint32_t *__restrict__ cnt)
+{
+	for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+		if (present && !mdb_bit(present, r))
+			continue; // NULL (or tombstoned) rows never match, executor_select.c:716-738
+		int64_t v = data[r];
+		if (is_dbl && key_is_nan(v))
+			continue;
+		uint64_t s = ht_insert(keys, cap_mask, norm_key(v, is_dbl));
+		atomicAdd(&cnt[s], 1u);
+	}
+}
+
+__global__ void k_join_build_fill(const int64_t *__restrict__ data, const uint32_t *__restrict__ present, uint64_t n, int is_dbl,
+		const long long *__restrict__ keys, uint64_t cap_mask, const uint64_t *__restrict__ off, uint32_t *__restrict__ fill,
+		uint32_t *__restrict__ rows)
+{
+	for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+		if (present && !mdb_bit(present, r))
+			continue;
+		int64_t v = data[r];
+		if (is_dbl && key_is_nan(v))
+			continue;
+		uint64_t s;
+		if (!ht_find(keys, cap_mask, norm_key(v, is_dbl), &s))
+			continue;
+		uint32_t pos = atomicAdd(&fill[s], 1u);
+		rows[off[s] + pos] = (uint32_t)r;
+	}
+}
+
+__global__ void k_join_probe_count(TuplesDev ts, int ltbl, const int64_t *__restrict__ data, const uint32_t *__restrict__ present,
+		int is_dbl, const long long *__restrict__ keys, uint64_t cap_mask, const uint32_t *__restrict__ cnt,
+		const uint64_t *__restrict__ row_off, uint32_t *__restrict__ matches, uint64_t *__restrict__ first_row)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < ts.n; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t r = ts.rid[ltbl][i];
+		uint32_t m = 0;
+		uint64_t s = 0;
+		if (!present || mdb_bit(present, r)) {
+			int64_t v = data[r];
+			if (!(is_dbl && key_is_nan(v)) && ht_find(keys, cap_mask, norm_key(v, is_dbl), &s))
+				m = cnt[s];
+		}
+		matches[i] = m;
+		first_row[i] = m ? row_off[s] : 0;
+	}
+}
+
+__global__ void k_join_probe_emit(TuplesDev ts, const uint32_t *__restrict__ matches, const uint64_t *__restrict__ first_row,
+		const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ rows, CompactArrays dst)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < ts.n; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t m = matches[i];
+		if (!m)
+			continue;
+		uint64_t o = out_off[i], ro = first_row[i];
+		for (uint32_t j = 0; j < m; j++) {
+			for (int k = 0; k < ts.ntab; k++)
+				dst.dst[k][o + j] = ts.rid[k][i];
+			dst.dst[ts.ntab][o + j] = rows[ro + j];
+		}
+	}
+}
+
+__global__ void k_cross_emit(TuplesDev ts, const uint32_t *__restrict__ right, uint64_t nright, CompactArrays dst)
+{
+	uint64_t total = ts.n * nright;
+	for (uint64_t o = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; o < total; o += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t i = o / nright, j = o - i * nright;
+		for (int k = 0; k < ts.ntab; k++)
+			dst.dst[k][o] = ts.rid[k][i];
+		dst.dst[ts.ntab][o] = right[j];
+	}
+}
+
+static int alloc_out_tuples(mdbcu_ctx *ctx, Tuples *out, int ntab, uint64_t n, CompactArrays *arr)
+{
+	if (n >= (1ull << 32))
+		return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "join produces %llu rows; the general path is limited to 2^32-1",
+				(unsigned long long)n);
+	out->ntab = ntab;
+	out->n = n;
+	arr->narr = ntab;
+	for (int k = 0; k < MDBCU_MAX_TABLES; k++) {
+		arr->src[k] = nullptr;
+		arr->dst[k] = nullptr;
+	}
+	for (int k = 0; k < ntab; k++) {
+		int rc = mdb_alloc(ctx, &out->rid[k], n);
+		if (rc != MDBCU_OK) {
+			free_tuples(ctx, *out);
+			return rc;
+		}
+		arr->dst[k] = out->rid[k];
+	}
+	return MDBCU_OK;
+}
+
+static int join_step(mdbcu_ctx *ctx, const mdbcu_plan *plan, int j, Tuples *ts)
+{
+	const mdbcu_join &jn = plan->joins[j];
+	const mdbcu_table *rt = plan->tables[j + 1];
+	Tuples out;
+	CompactArrays arr;
+
+	if (ts->ntab != j + 1)
+		return mdb_fail(ctx, MDBCU_EINTERNAL, "join order mismatch");
+
+	if (jn.cross) {
+		// comma list / ON 1=1: every pair (wrap_on_join_node, optimiser_select.c:395)
+		Tuples right;
+		MDB_TRY(scan_live(ctx, rt, &right));
+		uint64_t total = ts->n * right.n;
+		int rc = alloc_out_tuples(ctx, &out, ts->ntab + 1, total, &arr);
+		if (rc == MDBCU_OK && total) {
+			MDB_LAUNCH(ctx, k_cross_emit, grid_for(ctx, total, 256), 256, 0, to_dev(*ts), (const uint32_t*)right.rid[0],
+					right.n, arr);
+			cudaError_t e = cudaGetLastError();
+			if (e != cudaSuccess)
+				rc = mdb_fail(ctx, MDBCU_ECUDA, "k_cross_emit: %s", cudaGetErrorString(e));
+		}
+		free_tuples(ctx, right);
+		if (rc != MDBCU_OK)
+			return rc;
+		free_tuples(ctx, *ts);
+		*ts = out;
+		return MDBCU_OK;
+	}
+
+	MDB_TRY(check_colref(ctx, plan, jn.left.tbl, jn.left.col, "JOIN"));
+	MDB_TRY(check_colref(ctx, plan, jn.right.tbl, jn.right.col, "JOIN"));
+	if (jn.right.tbl != j + 1 || jn.left.tbl > j)
+		return mdb_fail(ctx, MDBCU_EERROR, "join %d must compare a column of tables[0..%d] with one of tables[%d]", j, j, j + 1);
+	const mdbcu_table *lt = plan->tables[jn.left.tbl];
+	const DevColumn &lc = lt->cols[jn.left.col], &rc_ = rt->cols[jn.right.col];
+	int l_dbl = lc.type == MDBCU_CT_DOUBLE, r_dbl = rc_.type == MDBCU_CT_DOUBLE;
+	if (l_dbl != r_dbl)
+		return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "join key types differ (INT vs DOUBLE)");
+
+	if (ts->n == 0 || rt->n_slots == 0) {
+		free_tuples(ctx, *ts);
+		ts->ntab = j + 2;
+		return MDBCU_OK;
+	}
+
+	DevTemp tmp(ctx);
+	uint64_t cap = 1024;
+	while (cap < rt->n_slots * 2)
+		cap <<= 1;
+	long long *keys;
+	uint32_t *cnt, *fill, *rows, *matches;
+	uint64_t *off, *out_off, *d_total, *first_row;
+	MDB_TRY(tmp.alloc(&keys, cap));
+	MDB_TRY(tmp.alloc(&cnt, cap + 2));
+	MDB_TRY(tmp.alloc(&fill, cap + 2));
+	MDB_TRY(tmp.alloc(&off, cap + 2));
+	MDB_TRY(tmp.alloc(&rows, rt->n_slots));
+	MDB_TRY(tmp.alloc(&matches, ts->n));
+	MDB_TRY(tmp.alloc(&first_row, ts->n));
+	MDB_TRY(tmp.alloc(&out_off, ts->n));
+	MDB_TRY(tmp.alloc(&d_total, 1));
+	MDB_LAUNCH(ctx, k_fill_i64, grid_for(ctx, cap, 256), 256, 0, keys, cap, HT_EMPTY);
+	CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, (cap + 2) * sizeof(uint32_t), ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(fill, 0, (cap + 2) * sizeof(uint32_t), ctx->stream));
+
+	const uint32_t *r_present = col_all_present(rt, jn.right.col) ? nullptr : rc_.present;
+	const uint32_t *l_present = col_all_present(lt, jn.left.col) ? nullptr : lc.present;
+	int gr = grid_for(ctx, rt->n_slots, 256);
+	MDB_LAUNCH(ctx, k_join_build_count, gr, 256, 0, (const int64_t*)rc_.data, r_present, rt->n_slots, r_dbl, keys, cap - 1, cnt);
+	CUDA_CHECK_LAUNCH(ctx);
+	MDB_TRY(mdb_scan_u32_u64(ctx, cnt, off, cap + 2, nullptr));
+	MDB_LAUNCH(ctx, k_join_build_fill, gr, 256, 0, (const int64_t*)rc_.data, r_present, rt->n_slots, r_dbl,
+			(const long long*)keys, cap - 1, (const uint64_t*)off, fill, rows);
+	CUDA_CHECK_LAUNCH(ctx);
+
+	int gp = grid_for(ctx, ts->n, 256);
+	MDB_LAUNCH(ctx, k_join_probe_count, gp, 256, 0, to_dev(*ts), jn.left.tbl, (const int64_t*)lc.data, l_present, l_dbl,
+			(const long long*)keys, cap - 1, (const uint32_t*)cnt, (const uint64_t*)off, matches, first_row);
+	CUDA_CHECK_LAUNCH(ctx);
+	MDB_TRY(mdb_scan_u32_u64(ctx, matches, out_off, ts->n, d_total));
+	uint64_t total = 0;
+	MDB_TRY(mdb_read_u64(ctx, d_total, &total));
+
+	MDB_TRY(alloc_out_tuples(ctx, &out, ts->ntab + 1, total, &arr));
+	if (total) {
+		MDB_LAUNCH(ctx, k_join_probe_emit, gp, 256, 0, to_dev(*ts), (const uint32_t*)matches, (const uint64_t*)first_row,
+				(const uint64_t*)out_off, (const uint32_t*)rows, arr);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) {
+			free_tuples(ctx, out);
+			return mdb_fail(ctx, MDBCU_ECUDA, "k_join_probe_emit: %s", cudaGetErrorString(e));
+		}
+	}
+	free_tuples(ctx, *ts);
+	*ts = out;
+	return MDBCU_OK;
+}
+
+// =========================================================================================== output / aggregation
+
+struct DOut {
+	int32_t kind;
+	int32_t tbl;
+	int32_t is_dbl;
+	int32_t key_idx; // >= 0: this plain column equals group key `key_idx` (no first-row lookup needed)
+	const int64_t *data;
+	const uint32_t *present;
+	long long *acc;           // per-slot accumulator (sum / min / max / count)
+	unsigned long long *nn;   // per-slot count of non-NULL inputs (or COUNT(*) rows)
+};
+
+struct DGroupSpec {
+	int32_t n_group;
+	int32_t n_out;
+	int32_t ntab;
+	int32_t pack_ok;         // order keys are available
+	int32_t pack_shift[MDBCU_MAX_TABLES];
+	struct {
+		int32_t tbl, is_dbl, mode; // mode 0: whole 64-bit key (single group column), 1: low 32 bits packed
+		int32_t _pad;
+		const int64_t *data;
+		const uint32_t *present;
+	} g[MDBCU_MAX_GROUP];
+	DOut out[MDBCU_MAX_OUT];
+};
+
+__device__ static inline unsigned long long pack_rids(const DGroupSpec *sp, const TuplesDev &ts, uint64_t i)
+{
+	unsigned long long k = 0;
+	for (int t = 0; t < sp->ntab; t++)
+		k |= (unsigned long long)ts.rid[t][i] << sp->pack_shift[t];
+	return k;
+}
+
+// slot layout: [0, cap) hashed keys, cap = key INT64_MIN, cap+1 = NULL group (NULLs collate equal, :1476-1482)
+__global__ void k_group_update(const DGroupSpec *__restrict__ sp, TuplesDev ts, long long *__restrict__ keys, uint64_t cap_mask,
+		unsigned long long *__restrict__ first_key, uint32_t *__restrict__ used)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < ts.n; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t slot;
+		if (sp->n_group == 0) {
+			slot = 0;
+		} else {
+			bool any_null = false;
+			long long key = 0;
+			for (int g = 0; g < sp->n_group; g++) {
+				uint32_t r = ts.rid[sp->g[g].tbl][i];
+				bool isnull = sp->g[g].present && !mdb_bit(sp->g[g].present, r);
+				long long v = isnull ? 0 : norm_key(sp->g[g].data[r], sp->g[g].is_dbl);
+				if (sp->g[g].mode == 0) {
+					key = v;
+					any_null = isnull;
+				} else {
+					// two int32-range columns packed into one 64-bit key; NULL is encoded out of band below
+					key = (long long)(((unsigned long long)key << 32) | ((unsigned long long)v & 0xffffffffull));
+					if (isnull)
+						any_null = true;
+				}
+			}
+			if (any_null) {
+				// the NULL group; composite keys containing NULLs are rejected on the host (build_group_spec)
+				slot = cap_mask + 2;
+			} else {
+				slot = ht_insert(keys, cap_mask, key);
+			}
+		}
+		used[slot] = 1;
+		if (sp->pack_ok)
+			atomicMin(&first_key[slot], pack_rids(sp, ts, i));
+		for (int o = 0; o < sp->n_out; o++) {
+			const DOut &out = sp->out[o];
+			if (out.kind == MDBCU_OUT_COLUMN)
+				continue;
+			if (out.kind == MDBCU_OUT_COUNT_STAR) {
+				atomicAdd(&out.nn[slot], 1ull);
+				continue;
+			}
+			uint32_t r = ts.rid[out.tbl][i];
+			if (out.present && !mdb_bit(out.present, r))
+				continue;
+			long long v = out.data[r];
+			atomicAdd(&out.nn[slot], 1ull);
+			switch (out.kind) {
+			case MDBCU_OUT_SUM: case MDBCU_OUT_AVG:
+				if (out.is_dbl)
+					atomicAdd((double*)&out.acc[slot], __longlong_as_double(v));
+				else
+					atomicAdd((unsigned long long*)&out.acc[slot], (unsigned long long)v);
+				break;
+			case MDBCU_OUT_MIN:
+				atomicMin(&out.acc[slot], out.is_dbl ? mdb_dbl_to_ordered(v) : v);
+				break;
+			case MDBCU_OUT_MAX:
+				atomicMax(&out.acc[slot], out.is_dbl ? mdb_dbl_to_ordered(v) : v);
+				break;
+			}
+		}
+	}
+}
+
+__global__ void k_flags_to_bits(const uint32_t *__restrict__ used, uint64_t n, uint32_t *__restrict__ bits)
+{
+	uint64_t groups = (n + 31) / 32;
+	uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+	int lane = threadIdx.x & 31;
+	for (uint64_t g = warp; g < groups; g += nwarps) {
+		uint64_t i = g * 32 + lane;
+		uint32_t b = __ballot_sync(0xffffffffu, i < n && used[i]);
+		if (lane == 0)
+			bits[g] = b;
+	}
+}
+
+struct DResultCols {
+	int64_t *cells[MDBCU_MAX_OUT];
+	uint8_t *nulls[MDBCU_MAX_OUT];
+};
+
+__device__ static inline void unpack_rids(const DGroupSpec *sp, unsigned long long k, uint32_t *rid)
+{
+	for (int t = 0; t < sp->ntab; t++) {
+		int hi = t == 0 ? 64 : sp->pack_shift[t - 1];
+		int width = hi - sp->pack_shift[t];
+		unsigned long long m = width >= 64 ? ~0ull : ((1ull << width) - 1ull);
+		rid[t] = (uint32_t)((k >> sp->pack_shift[t]) & m);
+	}
+}
+
+__global__ void k_group_emit(const DGroupSpec *__restrict__ sp, const uint32_t *__restrict__ slots, uint64_t ngroups,
+		const long long *__restrict__ keys, uint64_t cap_mask, const unsigned long long *__restrict__ first_key,
+		DResultCols res, unsigned long long *__restrict__ order_out)
+{
+	for (uint64_t gidx = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; gidx < ngroups; gidx += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t slot = slots[gidx];
+		uint32_t rid[MDBCU_MAX_TABLES] = {0, 0, 0, 0};
+		if (sp->pack_ok) {
+			unpack_rids(sp, first_key[slot], rid);
+			if (order_out)
+				order_out[gidx] = first_key[slot];
+		}
+		bool key_null = sp->n_group > 0 && slot == cap_mask + 2;
+		long long key = 0;
+		if (sp->n_group > 0 && !key_null)
+			key = slot == cap_mask + 1 ? HT_EMPTY : keys[slot];
+		for (int o = 0; o < sp->n_out; o++) {
+			const DOut &out = sp->out[o];
+			long long cell = 0;
+			bool isnull = false;
+			unsigned long long nn = out.nn ? out.nn[slot] : 0;
+			switch (out.kind) {
+			case MDBCU_OUT_COLUMN:
+				if (out.key_idx >= 0 && sp->g[out.key_idx].mode == 0) {
+					cell = key;
+					isnull = key_null;
+				} else {
+					uint32_t r = rid[out.tbl];
+					isnull = out.present && !mdb_bit(out.present, r);
+					cell = isnull ? 0 : out.data[r];
+				}
+				break;
+			case MDBCU_OUT_COUNT_STAR: case MDBCU_OUT_COUNT_COL:
+				cell = (long long)nn;
+				break;
+			case MDBCU_OUT_SUM:
+				isnull = nn == 0;
+				cell = out.acc[slot];
+				break;
+			case MDBCU_OUT_MIN: case MDBCU_OUT_MAX:
+				isnull = nn == 0;
+				cell = out.is_dbl ? mdb_ordered_to_dbl(out.acc[slot]) : out.acc[slot];
+				break;
+			case MDBCU_OUT_AVG:
+				isnull = nn == 0;
+				if (!isnull) {
+					double s = out.is_dbl ? __longlong_as_double(out.acc[slot]) : (double)out.acc[slot];
+					cell = __double_as_longlong(s / (double)nn);
+				}
+				break;
+			}
+			res.cells[o][gidx] = isnull ? 0 : cell;
+			res.nulls[o][gidx] = isnull;
+		}
+	}
+}
+
+__global__ void k_gather_out(const DGroupSpec *__restrict__ sp, TuplesDev ts, DResultCols res, unsigned long long *__restrict__ order_out)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < ts.n; i += (uint64_t)gridDim.x * blockDim.x) {
+		for (int o = 0; o < sp->n_out; o++) {
+			const DOut &out = sp->out[o];
+			uint32_t r = ts.rid[out.tbl][i];
+			bool isnull = out.present && !mdb_bit(out.present, r);
+			res.cells[o][i] = isnull ? 0 : out.data[r];
+			res.nulls[o][i] = isnull;
+		}
+		if (order_out)
+			order_out[i] = pack_rids(sp, ts, i);
+	}
+}
+
+static int out_result_type(const mdbcu_plan *plan, int o)
+{
+	const mdbcu_out &out = plan->out[o];
+	if (out.kind == MDBCU_OUT_COUNT_STAR || out.kind == MDBCU_OUT_COUNT_COL)
+		return MDBCU_CT_INTEGER;
+	if (out.kind == MDBCU_OUT_AVG)
+		return MDBCU_CT_DOUBLE;
+	int type = plan->tables[out.ref.tbl]->cols[out.ref.col].type;
+	if (out.kind == MDBCU_OUT_COLUMN)
+		return type;
+	return type == MDBCU_CT_DOUBLE ? MDBCU_CT_DOUBLE : MDBCU_CT_INTEGER;
+}
+
+int mdb_result_alloc(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res, uint64_t nrows, bool with_order)
+{
+	res->nrows = nrows;
+	res->cols.resize(plan->n_out);
+	for (int o = 0; o < plan->n_out; o++) {
+		res->cols[o].type = out_result_type(plan, o);
+		MDB_TRY(mdb_alloc(ctx, &res->cols[o].cells, nrows));
+		MDB_TRY(mdb_alloc(ctx, &res->cols[o].nulls, nrows));
+	}
+	if (with_order)
+		MDB_TRY(mdb_alloc(ctx, &res->order_key, nrows));
+	return MDBCU_OK;
+}
+
+static bool colref_eq(const mdbcu_colref &a, const mdbcu_colref &b)
+{
+	return a.tbl == b.tbl && a.col == b.col;
+}
+
+// fills everything of the spec except accumulator pointers
+static int build_group_spec(mdbcu_ctx *ctx, const mdbcu_plan *plan, int ntab, DGroupSpec *sp)
+{
+	memset(sp, 0, sizeof(*sp));
+	sp->n_group = plan->n_group;
+	sp->n_out = plan->n_out;
+	sp->ntab = ntab;
+
+	// order keys: row ids of all joined tables packed left-major = the reference's nested-loop row order
+	int bits_total = 0, bits[MDBCU_MAX_TABLES];
+	for (int t = 0; t < ntab; t++) {
+		uint64_t n = std::max<uint64_t>(plan->tables[t]->n_slots, 2);
+		bits[t] = 1;
+		while ((1ull << bits[t]) < n)
+			bits[t]++;
+		bits_total += bits[t];
+	}
+	sp->pack_ok = bits_total <= 64;
+	if (sp->pack_ok) {
+		int sh = 64;
+		for (int t = 0; t < ntab; t++) {
+			sh -= bits[t];
+			sp->pack_shift[t] = sh;
+		}
+		// put the last table at bit 0 so single-table keys are plain row ids
+		int slack = sp->pack_shift[ntab - 1];
+		for (int t = 0; t < ntab; t++)
+			sp->pack_shift[t] -= slack;
+	}
+
+	if (plan->n_group < 0 || plan->n_group > MDBCU_MAX_GROUP)
+		return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "GROUP BY supports at most %d columns", MDBCU_MAX_GROUP);
+	for (int g = 0; g < plan->n_group; g++) {
+		MDB_TRY(check_colref(ctx, plan, plan->group[g].tbl, plan->group[g].col, "GROUP BY"));
+		const mdbcu_table *t = plan->tables[plan->group[g].tbl];
+		const DevColumn &c = t->cols[plan->group[g].col];
+		sp->g[g].tbl = plan->group[g].tbl;
+		sp->g[g].is_dbl = c.type == MDBCU_CT_DOUBLE;
+		sp->g[g].data = c.data;
+		sp->g[g].present = col_all_present(t, plan->group[g].col) ? nullptr : c.present;
+		sp->g[g].mode = plan->n_group == 1 ? 0 : 1;
+		if (plan->n_group > 1) {
+			// composite keys are packed 2 x 32 bits: the reference's own integer domain is int32
+			if (c.type == MDBCU_CT_DOUBLE || !c.stats_ok || (c.imin <= c.imax && (c.imin < INT32_MIN || c.imax > INT32_MAX)))
+				return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "composite GROUP BY needs INT columns within int32 range");
+			if (c.has_nulls)
+				return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "composite GROUP BY over columns containing NULLs");
+		}
+	}
+
+	for (int o = 0; o < plan->n_out; o++) {
+		const mdbcu_out &po = plan->out[o];
+		DOut &d = sp->out[o];
+		d.kind = po.kind;
+		d.key_idx = -1;
+		if (po.kind < MDBCU_OUT_COLUMN || po.kind > MDBCU_OUT_AVG)
+			return mdb_fail(ctx, MDBCU_EERROR, "unknown output kind %d", po.kind);
+		if (po.kind == MDBCU_OUT_COUNT_STAR)
+			continue;
+		MDB_TRY(check_colref(ctx, plan, po.ref.tbl, po.ref.col, "SELECT list"));
+		const mdbcu_table *t = plan->tables[po.ref.tbl];
+		const DevColumn &c = t->cols[po.ref.col];
+		d.tbl = po.ref.tbl;
+		d.is_dbl = c.type == MDBCU_CT_DOUBLE;
+		d.data = c.data;
+		d.present = col_all_present(t, po.ref.col) ? nullptr : c.present;
+		if (po.kind == MDBCU_OUT_COLUMN) {
+			for (int g = 0; g < plan->n_group; g++)
+				if (colref_eq(po.ref, plan->group[g]))
+					d.key_idx = g;
+		}
+	}
+	return MDBCU_OK;
+}
+
+__global__ void k_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+		p[i] = v;
+}
+
+static bool plan_has_aggregate(const mdbcu_plan *plan)
+{
+	for (int o = 0; o < plan->n_out; o++)
+		if (plan->out[o].kind != MDBCU_OUT_COLUMN)
+			return true;
+	return false;
+}
+
+static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples &ts, mdbcu_result *res)
+{
+	DGroupSpec sp;
+	MDB_TRY(build_group_spec(ctx, plan, ts.ntab, &sp));
+
+	bool need_first = false;
+	for (int o = 0; o < plan->n_out; o++)
+		if (sp.out[o].kind == MDBCU_OUT_COLUMN && !(sp.out[o].key_idx >= 0 && sp.g[sp.out[o].key_idx].mode == 0))
+			need_first = true;
+	if (need_first && !sp.pack_ok)
+		return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "plain columns under GROUP BY need row ids that pack into 64 bits");
+
+	if (ts.n == 0)
+		return mdb_result_alloc(ctx, plan, res, 0, false); // no qualifying row: no result row (executor keeps zero rows)
+
+	uint64_t cap = 1024;
+	if (plan->n_group > 0)
+		while (cap < ts.n * 2)
+			cap <<= 1;
+	uint64_t nslots = cap + 3;
+
+	DevTemp tmp(ctx);
+	long long *keys;
+	unsigned long long *first_key;
+	uint32_t *used, *bits;
+	DGroupSpec *d_sp;
+	MDB_TRY(tmp.alloc(&keys, cap));
+	MDB_TRY(tmp.alloc(&first_key, nslots));
+	MDB_TRY(tmp.alloc(&used, nslots));
+	MDB_TRY(tmp.alloc(&bits, (nslots + 31) / 32));
+	MDB_TRY(tmp.alloc(&d_sp, 1));
+	MDB_LAUNCH(ctx, k_fill_i64, grid_for(ctx, cap, 256), 256, 0, keys, cap, HT_EMPTY);
+	MDB_LAUNCH(ctx, k_fill_u64, grid_for(ctx, nslots, 256), 256, 0, first_key, nslots, ~0ull);
+	CUDA_TRY(ctx, cudaMemsetAsync(used, 0, nslots * sizeof(uint32_t), ctx->stream));
+
+	for (int o = 0; o < plan->n_out; o++) {
+		DOut &d = sp.out[o];
+		if (d.kind == MDBCU_OUT_COLUMN)
+			continue;
+		MDB_TRY(tmp.alloc(&d.nn, nslots));
+		CUDA_TRY(ctx, cudaMemsetAsync(d.nn, 0, nslots * sizeof(unsigned long long), ctx->stream));
+		if (d.kind == MDBCU_OUT_COUNT_STAR || d.kind == MDBCU_OUT_COUNT_COL)
+			continue;
+		MDB_TRY(tmp.alloc(&d.acc, nslots));
+		long long init = 0;
+		if (d.kind == MDBCU_OUT_MIN)
+			init = INT64_MAX;
+		else if (d.kind == MDBCU_OUT_MAX)
+			init = INT64_MIN;
+		MDB_LAUNCH(ctx, k_fill_i64, grid_for(ctx, nslots, 256), 256, 0, d.acc, nslots, init);
+	}
+	CUDA_TRY(ctx, cudaMemcpyAsync(d_sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, ctx->stream));
+
+	MDB_LAUNCH(ctx, k_group_update, grid_for(ctx, ts.n, 256), 256, 0, (const DGroupSpec*)d_sp, to_dev(ts), keys, cap - 1,
+			first_key, used);
+	CUDA_CHECK_LAUNCH(ctx);
+	MDB_LAUNCH(ctx, k_flags_to_bits, grid_for(ctx, nslots, 256), 256, 0, (const uint32_t*)used, nslots, bits);
+	CUDA_CHECK_LAUNCH(ctx);
+
+	Tuples slots;
+	MDB_TRY(compact_tuples(ctx, bits, nslots, nullptr, 1, &slots));
+	int rc = mdb_result_alloc(ctx, plan, res, slots.n, sp.pack_ok != 0);
+	if (rc == MDBCU_OK && slots.n) {
+		DResultCols rcols;
+		memset(&rcols, 0, sizeof(rcols));
+		for (int o = 0; o < plan->n_out; o++) {
+			rcols.cells[o] = res->cols[o].cells;
+			rcols.nulls[o] = res->cols[o].nulls;
+		}
+		MDB_LAUNCH(ctx, k_group_emit, grid_for(ctx, slots.n, 256), 256, 0, (const DGroupSpec*)d_sp,
+				(const uint32_t*)slots.rid[0], slots.n, (const long long*)keys, cap - 1,
+				(const unsigned long long*)first_key, rcols, (unsigned long long*)res->order_key);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess)
+			rc = mdb_fail(ctx, MDBCU_ECUDA, "k_group_emit: %s", cudaGetErrorString(e));
+	}
+	free_tuples(ctx, slots);
+	return rc;
+}
+
+static int project_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples &ts, mdbcu_result *res)
+{
+	DGroupSpec sp;
+	MDB_TRY(build_group_spec(ctx, plan, ts.ntab, &sp));
+	MDB_TRY(mdb_result_alloc(ctx, plan, res, ts.n, sp.pack_ok != 0));
+	if (ts.n == 0)
+		return MDBCU_OK;
+	DevTemp tmp(ctx);
+	DGroupSpec *d_sp;
+	MDB_TRY(tmp.alloc(&d_sp, 1));
+	CUDA_TRY(ctx, cudaMemcpyAsync(d_sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, ctx->stream));
+	DResultCols rcols;
+	memset(&rcols, 0, sizeof(rcols));
+	for (int o = 0; o < plan->n_out; o++) {
+		rcols.cells[o] = res->cols[o].cells;
+		rcols.nulls[o] = res->cols[o].nulls;
+	}
+	MDB_LAUNCH(ctx, k_gather_out, grid_for(ctx, ts.n, 256), 256, 0, (const DGroupSpec*)d_sp, to_dev(ts), rcols,
+			(unsigned long long*)res->order_key);
+	CUDA_CHECK_LAUNCH(ctx);
+	return MDBCU_OK;
+}
+
+// =========================================================================================== driver
+
+int mdb_select_general(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res)
+{
+	Tuples ts;
+	PhaseClock clock(ctx);
+	int rc;
+
+	ctx->stats.path = MDBCU_PATH_GENERAL;
+	clock.begin(0);
+	rc = scan_live(ctx, plan->tables[0], &ts);
+	for (int j = 0; rc == MDBCU_OK && j < plan->n_joins; j++) {
+		clock.begin(j == 0 ? 2 : 3);
+		rc = join_step(ctx, plan, j, &ts);
+	}
+	if (rc == MDBCU_OK) {
+		clock.begin(0);
+		rc = filter_tuples(ctx, plan, &ts);
+	}
+	if (rc == MDBCU_OK) {
+		if (plan->n_group > 0 || plan_has_aggregate(plan)) {
+			clock.begin(4);
+			rc = aggregate_tuples(ctx, plan, ts, res);
+		} else {
+			clock.begin(5);
+			rc = project_tuples(ctx, plan, ts, res);
+		}
+	}
+	free_tuples(ctx, ts);
+	clock.finish();
+	return rc;
+}

@@ -1,0 +1,300 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI (libmidoridb_cuda.so), against
+  * the reference's known answers (tests/golden/reference_select.json),
+  * the CPU oracle on seeded random inputs (bit-exact for ints, 1e-9 relative for DOUBLE SUM/AVG),
+  * size-independent properties at larger sizes.
+Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+from midoridb_b200 import capi
+from midoridb_b200.capi import (CT_DOUBLE, CT_INTEGER, CT_TINYINT, OUT_AVG, OUT_COLUMN, OUT_COUNT_COL, OUT_COUNT_STAR, OUT_MAX,
+                                OUT_MIN, OUT_SUM, PLAN_NO_FASTPATH)
+from oracle import oracle
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+CASES = helpers.load_golden()
+I, D = CT_INTEGER, CT_DOUBLE
+
+
+@pytest.fixture(scope="module")
+def be():
+    b = capi.Backend(0)
+    yield b
+    b.close()
+
+
+def both_tables(be, types, columns, nulls=None, paged=False):
+    """the same data in a device table and an oracle table"""
+    g = be.create_table("t", types)
+    o = oracle.OracleTable(types)
+    if paged:
+        cells = np.stack([c.view(np.int64) if c.dtype == np.float64 else c for c in columns], axis=1)
+        nl = None if nulls is None else np.stack([np.zeros(len(columns[0]), np.uint8) if x is None else x for x in nulls], axis=1)
+        pages = capi.pack_pages(types, cells, nl)
+        g.append_pages(pages)
+        o.append_pages(pages)
+    else:
+        g.append_columns(columns, nulls)
+        o.append_columns(columns, nulls)
+    return g, o
+
+
+def run_both(be, gt, ot, flags=0, **kw):
+    gp = capi.make_plan(gt, flags=flags, **kw)
+    op = capi.make_plan(ot, **kw)
+    res = be.select(gp)
+    grows = res.rows()
+    pages = res.fetch_pages()
+    res.free()
+    _, cells, nulls = oracle.select(op)
+    return grows, oracle.rows_of(cells, nulls), pages, be.stats()
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_cuda_matches_reference_golden(be, case):
+    tables = []
+    for tbl in case["tables"]:
+        types, pages = helpers.golden_pages(tbl)
+        t = be.create_table(tbl["name"], types)
+        t.append_pages(pages)
+        tables.append(t)
+    plan = helpers.plan_from_dict(tables, case["plan"])
+    res = be.select(plan)
+    got = [helpers.norm_row(r) for r in res.rows()]
+    want = [helpers.norm_row(r) for r in case["rows"]]
+    # small results come back in the reference's own row order
+    assert got == want
+    # and the page images decode to the same rows through the reference's row format
+    cells, nulls = capi.unpack_pages(res.fetch_pages(), res.ncols)
+    types = res.types
+    dec = []
+    for r in range(cells.shape[0]):
+        dec.append(tuple(None if nulls[r, c] else (float(cells[r, c].view(np.float64)) if types[c] == D else int(cells[r, c]))
+                         for c in range(res.ncols)))
+    assert dec == want
+    res.free()
+    for t in tables:
+        t.drop()
+
+
+def test_unpack_roundtrip_and_tombstones(be):
+    rng = np.random.default_rng(3)
+    n = 1000
+    types = [I, D, CT_TINYINT, I]
+    cells = np.stack([rng.integers(-2**50, 2**50, n), rng.random(n).view(np.int64), rng.integers(0, 2, n),
+                      rng.integers(0, 100, n)], axis=1).astype(np.int64)
+    nulls = (rng.random((n, 4)) < 0.15).astype(np.uint8)
+    deleted = (rng.random(n) < 0.1).astype(np.uint8)
+    pages = capi.pack_pages(types, cells, nulls, deleted)
+    t = be.create_table("T", types)
+    t.append_pages(pages[:3])
+    t.append_pages(pages[3:])  # second append continues at a page boundary
+    rs = capi.row_size_of(types)
+    rpp = 4095 // rs
+    assert t.slots == pages.shape[0] * rpp
+    assert t.live_rows() == int((deleted == 0).sum())
+    for c in range(4):
+        got, valid = t.read_column(c, 0, n)
+        want_valid = ((deleted == 0) & (nulls[:, c] == 0)).astype(np.uint8)
+        assert np.array_equal(valid, want_valid)
+        assert np.array_equal(got.view(np.int64)[want_valid == 1], cells[want_valid == 1, c])
+    # tombstone through the (page, slot) API, like executor_delete.c:430
+    victims = np.flatnonzero(deleted == 0)[:50]
+    t.tombstone(victims // rpp, victims % rpp)
+    assert t.live_rows() == int((deleted == 0).sum()) - 50
+    t.drop()
+
+
+@pytest.mark.parametrize("seed", range(4))
+@pytest.mark.parametrize("flags", [0, PLAN_NO_FASTPATH])
+def test_readme_query_random(be, seed, flags):
+    """README query on random keys with duplicates and NULLs, general operators and auto-selected path"""
+    rng = np.random.default_rng(200 + seed)
+    na, nb, dom = [(50, 80, 20), (5000, 7000, 900), (40000, 30000, 100000), (3000, 3000, 3000)][seed]
+    a, b = rng.integers(-dom // 2, dom // 2, na), rng.integers(-dom // 2, dom // 2, nb)
+    an, bn = (rng.random(na) < 0.05).astype(np.uint8), (rng.random(nb) < 0.05).astype(np.uint8)
+    ga, oa = both_tables(be, [I], [a], [an], paged=(seed % 2 == 0))
+    gb, ob = both_tables(be, [I], [b], [bn], paged=(seed % 2 == 0))
+    grows, orows, pages, st = run_both(be, [ga, gb], [oa, ob], flags=flags, joins=[((0, 0), (1, 0))], group=[(0, 0)],
+                                       out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)])
+    assert grows == orows  # same rows in the same (reference) order
+    assert st.kernel_launches > 0
+    for t in (ga, gb):
+        t.drop()
+
+
+def test_general_operators_random(be):
+    """joins (2- and 3-way), WHERE programs, every aggregate, NULLs: CUDA general path == oracle"""
+    rng = np.random.default_rng(11)
+    n = 20000
+    a_cols = [rng.integers(0, 500, n), (rng.random(n) * 100).round(3)]
+    a_nulls = [None, (rng.random(n) < 0.1).astype(np.uint8)]
+    b_cols = [rng.integers(0, 500, 3000), rng.integers(-1000, 1000, 3000)]
+    b_nulls = [(rng.random(3000) < 0.05).astype(np.uint8), (rng.random(3000) < 0.1).astype(np.uint8)]
+    c_cols = [rng.permutation(500)[:400].astype(np.int64), rng.integers(0, 50, 400)]
+    ga, oa = both_tables(be, [I, D], a_cols, a_nulls)
+    gb, ob = both_tables(be, [I, I], b_cols, b_nulls, paged=True)
+    gc, oc = both_tables(be, [I, I], c_cols)
+
+    # GROUP BY with every aggregate
+    grows, orows, _, _ = run_both(be, [ga], [oa], group=[(0, 0)],
+                                  out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,), (OUT_COUNT_COL, 0, 1), (OUT_SUM, 0, 1),
+                                       (OUT_MIN, 0, 1), (OUT_MAX, 0, 1), (OUT_AVG, 0, 1)])
+    assert helpers.canon_close(grows, orows, rel=1e-9)
+
+    # 3-way join + WHERE + GROUP BY SUM/AVG (config 4 shape)
+    kw = dict(joins=[((0, 0), (1, 0)), ((0, 0), (2, 0))],
+              pred=[("col", 0, 1), ("dbl", 25.0), ("cmp", 6), ("col", 1, 1), ("int", 500), ("cmp", 1), ("and",)],
+              group=[(0, 0)], out=[(OUT_COLUMN, 0, 0), (OUT_SUM, 0, 1), (OUT_AVG, 2, 1), (OUT_COUNT_STAR,)])
+    grows, orows, _, _ = run_both(be, [ga, gb, gc], [oa, ob, oc], **kw)
+    assert len(orows) > 10
+    assert helpers.canon_close(grows, orows, rel=1e-9)
+
+    # plain 2-way join with projection, OR/XOR/IN/NOT IN/IS NULL programs; row order must equal the oracle's
+    preds = [
+        [("col", 1, 1), ("int", 0), ("cmp", 1), ("col", 0, 0), ("int", 400), ("cmp", 6), ("or",)],
+        [("col", 1, 1), ("int", 0), ("cmp", 2), ("col", 0, 1), ("dbl", 50.0), ("cmp", 2), ("xor",)],
+        [("col", 0, 0), ("int", 3), ("int", 5), ("int", 8), ("int", 13), ("in", 4)],
+        [("col", 0, 0), ("int", 3), ("int", 5), ("notin", 2), ("col", 1, 1), ("isnull",), ("and",)],
+        [("col", 0, 1), ("isnotnull",), ("col", 0, 0), ("col", 1, 1), ("cmp", 3), ("and",)],
+    ]
+    for pred in preds:
+        grows, orows, pages, _ = run_both(be, [ga, gb], [oa, ob], joins=[((0, 0), (1, 0))], pred=pred,
+                                          out=[(OUT_COLUMN, 0, 0), (OUT_COLUMN, 0, 1), (OUT_COLUMN, 1, 1)])
+        assert len(orows) > 0
+        assert [helpers.norm_row(r) for r in grows] == [helpers.norm_row(r) for r in orows]
+
+    # aggregates without GROUP BY over a join; and the empty case (no row, like the reference)
+    grows, orows, _, _ = run_both(be, [ga, gb], [oa, ob], joins=[((0, 0), (1, 0))],
+                                  out=[(OUT_COUNT_STAR,), (OUT_SUM, 1, 1), (OUT_MIN, 0, 1), (OUT_MAX, 0, 1), (OUT_AVG, 1, 1)])
+    assert helpers.canon_close(grows, orows, rel=1e-9)
+    grows, orows, pages, _ = run_both(be, [ga], [oa], pred=[("col", 0, 0), ("int", 10**6), ("cmp", 2)], out=[(OUT_COUNT_STAR,)])
+    assert grows == orows == []
+    assert pages.shape[0] == 1 and pages[0, 0] == 1  # one page of empty slots, never zero pages
+    # cross join (comma list)
+    gs, os_ = both_tables(be, [I], [np.arange(7, dtype=np.int64)])
+    grows, orows, _, _ = run_both(be, [gs, gc], [os_, oc], joins=["cross"], out=[(OUT_COLUMN, 0, 0), (OUT_COLUMN, 1, 1)])
+    assert [helpers.norm_row(r) for r in grows] == [helpers.norm_row(r) for r in orows]
+    for t in (ga, gb, gc, gs):
+        t.drop()
+
+
+@pytest.mark.parametrize("sel", [0.01, 0.5, 1.0])
+def test_scan_filter_aggregate_fastpath(be, sel):
+    """config 2 shape: SELECT COUNT(*), SUM(v) ... WHERE k >= lo AND k <= hi - fused kernel vs oracle"""
+    rng = np.random.default_rng(21)
+    n = 300001  # odd on purpose: exercises the scalar tail
+    k = rng.integers(0, 2**31, n)
+    v = rng.random(n)
+    vn = (rng.random(n) < 0.02).astype(np.uint8)
+    m = rng.integers(-2**40, 2**40, n)
+    g, o = both_tables(be, [I, D, I], [k, v, m], [None, vn, None])
+    lo = 2**29
+    hi = lo + int(sel * 2**31) - 1
+    pred = [("col", 0, 0), ("int", lo), ("cmp", 6), ("col", 0, 0), ("int", hi), ("cmp", 5), ("and",)]
+    out = [(OUT_COUNT_STAR,), (OUT_SUM, 0, 1), (OUT_COUNT_COL, 0, 1), (OUT_AVG, 0, 1), (OUT_MIN, 0, 2), (OUT_MAX, 0, 2), (OUT_SUM, 0, 2)]
+    grows, orows, _, st = run_both(be, [g], [o], pred=pred, out=out)
+    assert st.path == capi.PATH_SCAN_AGG
+    assert len(grows) == 1
+    assert helpers.rows_close(grows, [helpers.norm_row(r) for r in orows], rel=1e-9)
+    # integer aggregates are bit-exact
+    assert grows[0][0] == orows[0][0] and grows[0][4:] == tuple(orows[0][4:])
+    # same answer from the general operators
+    g2, _, _, st2 = run_both(be, [g], [o], flags=PLAN_NO_FASTPATH, pred=pred, out=out)
+    assert st2.path == capi.PATH_GENERAL
+    assert helpers.rows_close(g2, grows, rel=1e-9)
+    # double range predicate, yoda form
+    pred = [("dbl", 0.25), ("col", 0, 1), ("cmp", 5), ("col", 0, 1), ("dbl", 0.75), ("cmp", 1), ("and",)]
+    grows, orows, _, st = run_both(be, [g], [o], pred=pred, out=[(OUT_COUNT_STAR,), (OUT_MIN, 0, 1), (OUT_MAX, 0, 1)])
+    assert st.path == capi.PATH_SCAN_AGG
+    assert grows == [helpers.norm_row(r) for r in orows]
+    g.drop()
+
+
+@pytest.mark.parametrize("shape", ["uniform", "sparse_overlap", "nulls_paged"])
+def test_radix_joincount_fastpath(be, shape):
+    """README query at 2^20-2^21 rows: radix path == oracle, bit-exact after canonical ordering"""
+    rng = np.random.default_rng(31)
+    if shape == "uniform":
+        na = nb = 1 << 20
+        a, b = rng.integers(0, 1 << 20, na), rng.integers(0, 1 << 20, nb)
+        an = bn = None
+    elif shape == "sparse_overlap":
+        na, nb = 700000, 900001
+        a = rng.integers(-5_000_000, 40_000_000, na)
+        b = rng.integers(30_000_000, 90_000_000, nb)
+        an = bn = None
+    else:
+        na, nb = 600000, 500000
+        a, b = rng.integers(1000, 300000, na), rng.integers(0, 250000, nb)
+        an, bn = (rng.random(na) < 0.03).astype(np.uint8), (rng.random(nb) < 0.03).astype(np.uint8)
+    paged = shape == "nulls_paged"
+    ga, oa = both_tables(be, [I], [a], None if an is None else [an], paged=paged)
+    gb, ob = both_tables(be, [I], [b], None if bn is None else [bn], paged=paged)
+    kw = dict(joins=[((0, 0), (1, 0))], group=[(1, 0)], out=[(OUT_COUNT_STAR,), (OUT_COLUMN, 0, 0), (OUT_COLUMN, 1, 0)])
+    grows, orows, _, st = run_both(be, [ga, gb], [oa, ob], **kw)
+    assert st.path == capi.PATH_RADIX_JOINCOUNT
+    assert helpers.canon(grows) == helpers.canon(orows)
+    # independent cross-check of the invariant: sum of counts == join cardinality
+    ua, ca = np.unique(a[an == 0] if an is not None else a, return_counts=True)
+    ub, cb = np.unique(b[bn == 0] if bn is not None else b, return_counts=True)
+    common, ia, ib = np.intersect1d(ua, ub, return_indices=True)
+    assert sum(r[0] for r in grows) == int((ca[ia] * cb[ib]).sum())
+    assert len(grows) == common.size
+    for t in (ga, gb):
+        t.drop()
+
+
+def test_radix_joincount_heavy_key_falls_back(be):
+    """more than 255 equal keys wrap a byte counter: detected by the checksum, redone by the general operators"""
+    rng = np.random.default_rng(41)
+    n = 1 << 20
+    a = rng.integers(0, 1 << 20, n)
+    b = rng.integers(0, 1 << 20, n)
+    a[:5000] = 777  # heavy hitter
+    b[:300] = 777
+    ga, oa = both_tables(be, [I], [a])
+    gb, ob = both_tables(be, [I], [b])
+    grows, orows, _, st = run_both(be, [ga, gb], [oa, ob], joins=[((0, 0), (1, 0))], group=[(0, 0)],
+                                   out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)])
+    assert st.path == capi.PATH_GENERAL
+    assert helpers.canon(grows) == helpers.canon(orows)
+    for t in (ga, gb):
+        t.drop()
+
+
+def test_generate_is_sharding_invariant_and_join_properties(be):
+    """device-side generator: any sharding of (seed, global index) gives the same table; at 2^24 x 2^24 the
+    radix path satisfies the domain invariants (groups <= min side, keys sorted-unique, sum(count) == |A join B|)"""
+    spec = capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=(1 << 24) - 1, seed=3)
+    whole = be.create_table("w", [I])
+    whole.generate(1 << 16, [spec])
+    parts = be.create_table("p", [I])
+    parts.generate(1 << 15, [spec], row_offset=0)
+    parts.generate(1 << 15, [spec], row_offset=1 << 15)
+    w, _ = whole.read_column(0)
+    p, _ = parts.read_column(0)
+    assert np.array_equal(w, p)
+    assert w.min() >= 0 and w.max() < (1 << 24)
+    whole.drop()
+    parts.drop()
+
+    n = 1 << 24
+    ta, tb = be.create_table("A", [I]), be.create_table("B", [I])
+    ta.generate(n, [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=n - 1, seed=1)])
+    tb.generate(n, [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=n - 1, seed=2)])
+    plan = capi.make_plan([ta, tb], joins=[((0, 0), (1, 0))], group=[(0, 0)], out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)])
+    res = be.select(plan)
+    assert be.stats().path == capi.PATH_RADIX_JOINCOUNT
+    (keys, cnts), _ = res.fetch_columns()
+    res.free()
+    a, _ = ta.read_column(0)
+    b, _ = tb.read_column(0)
+    ca, cb = np.bincount(a, minlength=n), np.bincount(b, minlength=n)
+    want_keys = np.flatnonzero((ca > 0) & (cb > 0))
+    order = np.argsort(keys)
+    assert np.array_equal(keys[order], want_keys)
+    assert np.array_equal(cnts[order], (ca * cb)[want_keys])
+    ta.drop()
+    tb.drop()
