@@ -228,6 +228,13 @@ struct mdbcu_stats {
 #define MDBCU_PATH_DIRECT_STAR    3 /* small build side, direct-addressed probe + grouped MIN/MAX/SUM/COUNT */
 int mdbcu_get_stats(mdbcu_ctx *ctx, struct mdbcu_stats *out);
 
+/* CUDA events on the context's own stream (the stream every kernel of this library is launched on), so a
+ * harness can time a region of calls on the device: record slot a, run, record slot b, read the elapsed time.
+ * MDBCU_EVENT_SLOTS slots. */
+#define MDBCU_EVENT_SLOTS 8
+int mdbcu_event_record(mdbcu_ctx *ctx, int slot);
+int mdbcu_event_elapsed_ms(mdbcu_ctx *ctx, int slot_start, int slot_stop, double *ms);
+
 /* ------------------------------------------------------------------ multi-GPU (one process per GPU) */
 
 /* 128-byte NCCL unique id, created on rank 0 and distributed by the host program (torch.distributed,

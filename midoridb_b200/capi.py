@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "mdbcu_select",
     "mdbcu_result_rows", "mdbcu_result_cols", "mdbcu_result_col_type", "mdbcu_result_fetch_columns",
     "mdbcu_result_page_count", "mdbcu_result_row_size", "mdbcu_result_fetch_pages", "mdbcu_result_free",
-    "mdbcu_get_stats", "mdbcu_comm_unique_id", "mdbcu_comm_init", "mdbcu_comm_world", "mdbcu_version",
+    "mdbcu_get_stats", "mdbcu_event_record", "mdbcu_event_elapsed_ms", "mdbcu_comm_unique_id", "mdbcu_comm_init", "mdbcu_comm_world", "mdbcu_version",
 ]
 
 
@@ -128,6 +128,8 @@ def load_library():
     L.mdbcu_result_free.argtypes = [vp]
     L.mdbcu_result_free.restype = None
     L.mdbcu_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.mdbcu_event_record.argtypes = [vp, C.c_int]
+    L.mdbcu_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.mdbcu_comm_unique_id.argtypes = [vp, vp]
     L.mdbcu_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.mdbcu_comm_world.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -346,6 +348,14 @@ class Backend:
         s = Stats()
         self._check(self.L.mdbcu_get_stats(self.ctx, C.byref(s)))
         return s
+
+    def event_record(self, slot):
+        self._check(self.L.mdbcu_event_record(self.ctx, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_double()
+        self._check(self.L.mdbcu_event_elapsed_ms(self.ctx, a, b, C.byref(ms)))
+        return ms.value
 
     def comm_unique_id(self):
         buf = (C.c_ubyte * 128)()

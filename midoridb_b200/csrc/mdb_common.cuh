@@ -30,6 +30,7 @@ struct mdbcu_ctx {
 	// reusable scratch: pinned host word for small D2H reads
 	uint64_t *h_scalar = nullptr; // pinned, 64 entries
 	uint64_t *d_scalar = nullptr; // device, 64 entries
+	cudaEvent_t user_events[MDBCU_EVENT_SLOTS] = {};
 };
 
 struct DevColumn {

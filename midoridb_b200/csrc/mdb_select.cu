@@ -114,6 +114,30 @@ extern "C" int mdbcu_get_stats(mdbcu_ctx *ctx, struct mdbcu_stats *out)
 	return MDBCU_OK;
 }
 
+extern "C" int mdbcu_event_record(mdbcu_ctx *ctx, int slot)
+{
+	if (!ctx || slot < 0 || slot >= MDBCU_EVENT_SLOTS)
+		return MDBCU_EERROR;
+	cudaSetDevice(ctx->device);
+	if (!ctx->user_events[slot])
+		CUDA_TRY(ctx, cudaEventCreate(&ctx->user_events[slot]));
+	CUDA_TRY(ctx, cudaEventRecord(ctx->user_events[slot], ctx->stream));
+	return MDBCU_OK;
+}
+
+extern "C" int mdbcu_event_elapsed_ms(mdbcu_ctx *ctx, int a, int b, double *ms)
+{
+	if (!ctx || !ms || a < 0 || b < 0 || a >= MDBCU_EVENT_SLOTS || b >= MDBCU_EVENT_SLOTS || !ctx->user_events[a] ||
+			!ctx->user_events[b])
+		return MDBCU_EERROR;
+	cudaSetDevice(ctx->device);
+	float f = 0.f;
+	CUDA_TRY(ctx, cudaEventSynchronize(ctx->user_events[b]));
+	CUDA_TRY(ctx, cudaEventElapsedTime(&f, ctx->user_events[a], ctx->user_events[b]));
+	*ms = f;
+	return MDBCU_OK;
+}
+
 // ------------------------------------------------------------------------------------------ results
 
 extern "C" uint64_t mdbcu_result_rows(const mdbcu_result *r)
