@@ -62,6 +62,10 @@ void mdbcu_shutdown(mdbcu_ctx *ctx);
 /* message of the last failure on this context (or of a failed mdbcu_init when ctx == NULL) */
 const char *mdbcu_last_error(mdbcu_ctx *ctx);
 int mdbcu_device_sync(mdbcu_ctx *ctx);
+/* page-locked host memory for page images / result buffers (full PCIe speed for the copies below);
+ * plain malloc'd memory is accepted everywhere too, just slower */
+void *mdbcu_host_alloc(mdbcu_ctx *ctx, size_t bytes);
+void mdbcu_host_free(mdbcu_ctx *ctx, void *p);
 
 /* ------------------------------------------------------------------ device mirror of row storage */
 

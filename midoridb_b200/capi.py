@@ -26,7 +26,7 @@ GEN_UNIFORM_INT, GEN_UNIFORM_DBL, GEN_PERMUTATION, GEN_ZIPF, GEN_SEQUENCE = rang
 PATH_GENERAL, PATH_SCAN_AGG, PATH_RADIX_JOINCOUNT, PATH_DIRECT_STAR = range(4)
 
 EXPORTED_SYMBOLS = [
-    "mdbcu_init", "mdbcu_shutdown", "mdbcu_last_error", "mdbcu_device_sync",
+    "mdbcu_init", "mdbcu_shutdown", "mdbcu_last_error", "mdbcu_device_sync", "mdbcu_host_alloc", "mdbcu_host_free",
     "mdbcu_table_create", "mdbcu_table_drop", "mdbcu_table_append_pages", "mdbcu_table_append_page_ptrs",
     "mdbcu_table_reload_pages", "mdbcu_table_tombstone", "mdbcu_table_append_columns", "mdbcu_table_generate",
     "mdbcu_table_slots", "mdbcu_table_live_rows", "mdbcu_table_read_column",
@@ -100,6 +100,10 @@ def load_library():
     L.mdbcu_last_error.argtypes = [vp]
     L.mdbcu_last_error.restype = C.c_char_p
     L.mdbcu_device_sync.argtypes = [vp]
+    L.mdbcu_host_alloc.argtypes = [vp, sz]
+    L.mdbcu_host_alloc.restype = vp
+    L.mdbcu_host_free.argtypes = [vp, vp]
+    L.mdbcu_host_free.restype = None
     L.mdbcu_table_create.argtypes = [vp, C.c_char_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(vp)]
     L.mdbcu_table_drop.argtypes = [vp]
     L.mdbcu_table_drop.restype = None
@@ -283,10 +287,23 @@ class Result:
         self.backend._check(self.backend.L.mdbcu_result_fetch_columns(self.handle, cp, npn))
         return cells, nulls
 
-    def fetch_pages(self):
+    def fetch_columns_into(self, cell_ptrs, null_ptrs=None):
+        """copy result columns into caller-owned buffers (raw addresses, e.g. page-locked memory)"""
+        cp = (C.c_void_p * max(self.ncols, 1))(*cell_ptrs)
+        npn = None if null_ptrs is None else (C.c_void_p * max(self.ncols, 1))(*null_ptrs)
+        self.backend._check(self.backend.L.mdbcu_result_fetch_columns(self.handle, cp, npn))
+
+    def page_count(self):
+        return self.backend.L.mdbcu_result_page_count(self.handle)
+
+    def fetch_pages(self, out=None):
         L = self.backend.L
         n = L.mdbcu_result_page_count(self.handle)
-        pages = np.zeros((n, PAGE_SIZE), dtype=np.uint8)
+        if out is None:
+            pages = np.zeros((n, PAGE_SIZE), dtype=np.uint8)
+        else:
+            assert out.size >= n * PAGE_SIZE
+            pages = out.reshape(-1)[:n * PAGE_SIZE].reshape(n, PAGE_SIZE)
         self.backend._check(L.mdbcu_result_fetch_pages(self.handle, pages.ctypes.data, n))
         return pages
 
@@ -348,6 +365,21 @@ class Backend:
         s = Stats()
         self._check(self.L.mdbcu_get_stats(self.ctx, C.byref(s)))
         return s
+
+    def host_array(self, nbytes):
+        """uint8 numpy array over page-locked host memory (freed with host_free(arr))"""
+        p = self.L.mdbcu_host_alloc(self.ctx, nbytes)
+        if not p:
+            raise MdbError(ENOMEM, (self.L.mdbcu_last_error(self.ctx) or b"").decode())
+        arr = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(p))
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[arr.ctypes.data] = p
+        return arr
+
+    def host_free(self, arr):
+        p = getattr(self, "_pinned", {}).pop(arr.ctypes.data, None)
+        if p:
+            self.L.mdbcu_host_free(self.ctx, p)
 
     def event_record(self, slot):
         self._check(self.L.mdbcu_event_record(self.ctx, slot))

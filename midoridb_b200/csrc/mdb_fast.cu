@@ -549,577 +549,6 @@ int mdb_select_scan_agg(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *re
 	return MDBCU_OK;
 }
 
-// ===================================================================================== radix join + count
-
-#define RJ_MAX_PART 4096           // partitions per pass (12 radix bits)
-#define RJ_MAX_SHIFT 16            // remainder bits: 2-byte remainders, 64 KiB byte-counter histogram per side
-#define RJ_CAP 20                  // staging slots per partition (flush at 16 = one 32-byte sector)
-#define RJ_FLUSH 16
-#define RJ_CHUNK 256               // remainders per chunk (512 bytes = one warp-wide 128-bit load)
-#define RJ_BLOCKS_PER_CHUNK (RJ_CHUNK / RJ_FLUSH)
-#define RJ_P1_THREADS 512
-#define RJ_P1_LOADS 8              // 128-bit loads (2 keys each) per thread per round
-#define RJ_P1_TILE (RJ_P1_THREADS * RJ_P1_LOADS * 2)
-#define RJ_P2_THREADS 1024
-#define RJ_NONE 0xffffffffu
-
-struct RJSide {
-	const int64_t *keys;
-	const uint32_t *present;
-	uint64_t n;
-	// chunk pool
-	uint16_t *pool;            // pool_chunks * RJ_CHUNK remainders
-	uint32_t pool_chunks;
-	uint32_t *pool_next;       // allocation cursor
-	uint16_t *chunk_part;      // partition of each chunk
-	uint16_t *chunk_entries;   // valid remainders in each chunk
-	uint32_t *dir_cnt;         // chunks per partition (RJ_MAX_PART + 1)
-	uint32_t *dir;             // chunk ids grouped by partition
-	uint64_t *dir_off;         // exclusive offsets into dir (RJ_MAX_PART + 1)
-	uint32_t *dir_fill;
-};
-
-struct RJParams {
-	long long kmin;
-	unsigned long long range;  // keys in [kmin, kmin + range) can match
-	int shift;                 // remainder bits
-	int nparts;
-	uint32_t *error_flag;      // bit 0: chunk pool exhausted, bit 1: byte counter overflow
-};
-
-// shared memory layout of pass 1 (dynamic)
-struct RJP1Smem {
-	uint16_t stage[RJ_MAX_PART * RJ_CAP]; // 160 KiB
-	uint32_t fill[RJ_MAX_PART];
-	uint32_t chunk_id[RJ_MAX_PART];
-	uint16_t worklist[RJ_MAX_PART];
-	uint8_t chunk_blocks[RJ_MAX_PART];
-	uint32_t wl_count;
-};
-
-__device__ static inline uint32_t rj_new_chunk(const RJSide &s, const RJParams &pr, RJP1Smem *sm, uint32_t p)
-{
-	uint32_t old = sm->chunk_id[p];
-	uint32_t cid = atomicAdd(s.pool_next, 1u);
-	if (cid >= s.pool_chunks) {
-		atomicOr(pr.error_flag, 1u);
-		return RJ_NONE;
-	}
-	if (old != RJ_NONE)
-		s.chunk_entries[old] = RJ_CHUNK; // retired chunks are always full
-	s.chunk_part[cid] = (uint16_t)p;
-	atomicAdd(&s.dir_cnt[p], 1u);
-	sm->chunk_id[p] = cid;
-	sm->chunk_blocks[p] = 0;
-	return cid;
-}
-
-// Pass 1.  One persistent CTA per SM.  Keys are streamed with 128-bit loads (double-buffered in
-// registers); each key is reduced to (partition, 16-bit remainder) and appended to the partition's
-// staging slots in shared memory with one shared-memory atomic.  A partition whose 16th slot fills
-// is queued and flushed as ONE aligned 32-byte sector into the CTA's current 512-byte chunk of that
-// partition, so DRAM only ever sees full-sector writes.
-__global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition(RJSide s, RJParams pr)
-{
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	RJP1Smem *sm = reinterpret_cast<RJP1Smem*>(smem_raw);
-	const int tid = threadIdx.x;
-
-	for (int p = tid; p < RJ_MAX_PART; p += RJ_P1_THREADS) {
-		sm->fill[p] = 0;
-		sm->chunk_id[p] = RJ_NONE;
-		sm->chunk_blocks[p] = 0;
-	}
-	if (tid == 0)
-		sm->wl_count = 0;
-	__syncthreads();
-
-	const uint64_t ntiles = (s.n + RJ_P1_TILE - 1) / RJ_P1_TILE;
-	const int4 *src = reinterpret_cast<const int4*>(s.keys);
-	const uint64_t npairs = s.n / 2;
-
-	int4 cur[RJ_P1_LOADS], nxt[RJ_P1_LOADS];
-	auto load_tile = [&](uint64_t tile, int4 *dst) {
-		uint64_t base_pair = tile * (RJ_P1_TILE / 2);
-#pragma unroll
-		for (int j = 0; j < RJ_P1_LOADS; j++) {
-			uint64_t pi = base_pair + (uint64_t)j * RJ_P1_THREADS + tid;
-			if (pi < npairs) {
-				dst[j] = mdb_ldg_stream(src + pi);
-			} else if (pi == npairs && (s.n & 1)) {
-				long long last = s.keys[s.n - 1];
-				dst[j] = make_int4((int)(unsigned)(unsigned long long)last, (int)(unsigned)((unsigned long long)last >> 32), 0, 0);
-			} else {
-				dst[j] = make_int4(0, 0, 0, 0);
-			}
-		}
-	};
-
-	uint64_t tile = blockIdx.x;
-	if (tile < ntiles)
-		load_tile(tile, cur);
-
-	for (; tile < ntiles; tile += gridDim.x) {
-		uint64_t next_tile = tile + gridDim.x;
-		if (next_tile < ntiles)
-			load_tile(next_tile, nxt);
-
-		// decode this round's keys into (partition << 16 | remainder), RJ_NONE = nothing to insert
-		uint32_t item[RJ_P1_LOADS * 2];
-		uint64_t base_pair = tile * (RJ_P1_TILE / 2);
-#pragma unroll
-		for (int j = 0; j < RJ_P1_LOADS; j++) {
-			uint64_t pi = base_pair + (uint64_t)j * RJ_P1_THREADS + tid;
-			uint32_t pw = 0xffffffffu;
-			if (s.present && pi * 2 < s.n)
-				pw = s.present[pi >> 4];
-			int bit = (int)((pi & 15) * 2);
-#pragma unroll
-			for (int h = 0; h < 2; h++) {
-				uint64_t row = pi * 2 + h;
-				long long key = h == 0 ? (long long)(((unsigned long long)(unsigned)cur[j].y << 32) | (unsigned)cur[j].x)
-						       : (long long)(((unsigned long long)(unsigned)cur[j].w << 32) | (unsigned)cur[j].z);
-				unsigned long long d = (unsigned long long)key - (unsigned long long)pr.kmin;
-				bool ok = row < s.n && ((pw >> (bit + h)) & 1) && d < pr.range;
-				item[j * 2 + h] = ok ? (uint32_t)(((d >> pr.shift) << 16) | (d & ((1ull << pr.shift) - 1))) : RJ_NONE;
-			}
-		}
-
-		bool pending;
-		do {
-			pending = false;
-#pragma unroll
-			for (int k = 0; k < RJ_P1_LOADS * 2; k++) {
-				uint32_t it = item[k];
-				if (it == RJ_NONE)
-					continue;
-				uint32_t p = it >> 16;
-				uint32_t pos = atomicAdd(&sm->fill[p], 1u);
-				if (pos < RJ_CAP) {
-					sm->stage[p * RJ_CAP + pos] = (uint16_t)it;
-					item[k] = RJ_NONE;
-					if (pos == RJ_FLUSH - 1)
-						sm->worklist[atomicAdd(&sm->wl_count, 1u)] = (uint16_t)p;
-				} else {
-					pending = true; // staging full: retry after this round's flush
-				}
-			}
-			pending = __syncthreads_or(pending);
-			uint32_t nwl = sm->wl_count;
-			__syncthreads();
-			if (tid == 0)
-				sm->wl_count = 0;
-			// flush: one lane per queued partition moves its first 16 remainders (one 32-byte sector)
-			for (uint32_t w = tid; w < nwl; w += RJ_P1_THREADS) {
-				uint32_t p = sm->worklist[w];
-				uint32_t f = min(sm->fill[p], (uint32_t)RJ_CAP);
-				uint32_t cid = sm->chunk_id[p];
-				if (cid == RJ_NONE || sm->chunk_blocks[p] == RJ_BLOCKS_PER_CHUNK)
-					cid = rj_new_chunk(s, pr, sm, p);
-				const uint2 *st = reinterpret_cast<const uint2*>(&sm->stage[p * RJ_CAP]); // 40-byte rows: 8-byte aligned
-				uint2 a = st[0], b = st[1], c = st[2], d = st[3], e = st[4];
-				if (cid != RJ_NONE) {
-					uint32_t blk = sm->chunk_blocks[p];
-					int4 *dst = reinterpret_cast<int4*>(s.pool + (size_t)cid * RJ_CHUNK + blk * RJ_FLUSH);
-					dst[0] = make_int4((int)a.x, (int)a.y, (int)b.x, (int)b.y);
-					dst[1] = make_int4((int)c.x, (int)c.y, (int)d.x, (int)d.y);
-					sm->chunk_blocks[p] = (uint8_t)(blk + 1);
-				}
-				// keep the (at most 4) remainders behind the flushed sector
-				reinterpret_cast<uint2*>(&sm->stage[p * RJ_CAP])[0] = e;
-				sm->fill[p] = f - RJ_FLUSH;
-			}
-			__syncthreads();
-		} while (pending);
-
-#pragma unroll
-		for (int j = 0; j < RJ_P1_LOADS; j++)
-			cur[j] = nxt[j];
-	}
-
-	// drain: every partition's partial sector goes out, chunk entry counts are finalised
-	__syncthreads();
-	for (int p = tid; p < pr.nparts; p += RJ_P1_THREADS) {
-		uint32_t f = sm->fill[p];
-		uint32_t cid = sm->chunk_id[p];
-		if (f > 0) {
-			if (cid == RJ_NONE || sm->chunk_blocks[p] == RJ_BLOCKS_PER_CHUNK)
-				cid = rj_new_chunk(s, pr, sm, p);
-			if (cid != RJ_NONE) {
-				uint32_t blk = sm->chunk_blocks[p];
-				uint16_t *dst = s.pool + (size_t)cid * RJ_CHUNK + blk * RJ_FLUSH;
-				for (uint32_t i = 0; i < f; i++)
-					dst[i] = sm->stage[p * RJ_CAP + i];
-				s.chunk_entries[cid] = (uint16_t)(blk * RJ_FLUSH + f);
-			}
-		} else if (cid != RJ_NONE) {
-			s.chunk_entries[cid] = (uint16_t)(sm->chunk_blocks[p] * RJ_FLUSH);
-		}
-	}
-}
-
-// group chunk ids by partition (counting sort; counts were accumulated in pass 1)
-__global__ void k_radix_dir_scan(RJSide s, int nparts)
-{
-	// single block, nparts <= 4096
-	__shared__ uint64_t warp_tot[33];
-	uint64_t carry = 0;
-	for (int base = 0; base < nparts + 1; base += blockDim.x) {
-		int i = base + threadIdx.x;
-		uint64_t v = i < nparts ? s.dir_cnt[i] : 0;
-		uint64_t incl = v;
-		int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-		for (int o = 1; o < 32; o <<= 1) {
-			uint64_t n = __shfl_up_sync(0xffffffffu, incl, o);
-			if (lane >= o)
-				incl += n;
-		}
-		if (lane == 31)
-			warp_tot[warp] = incl;
-		__syncthreads();
-		if (warp == 0) {
-			uint64_t w = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0, wi = w;
-			for (int o = 1; o < 32; o <<= 1) {
-				uint64_t n = __shfl_up_sync(0xffffffffu, wi, o);
-				if (lane >= o)
-					wi += n;
-			}
-			warp_tot[lane] = wi - w;
-			if (lane == 31)
-				warp_tot[32] = wi;
-		}
-		__syncthreads();
-		if (i < nparts + 1)
-			s.dir_off[i] = carry + warp_tot[warp] + incl - v;
-		carry += warp_tot[32];
-		__syncthreads();
-	}
-}
-
-__global__ void k_radix_dir_fill(RJSide s)
-{
-	uint32_t nchunks = min(*s.pool_next, s.pool_chunks);
-	for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += gridDim.x * blockDim.x) {
-		uint32_t p = s.chunk_part[c];
-		uint32_t pos = atomicAdd(&s.dir_fill[p], 1u);
-		s.dir[s.dir_off[p] + pos] = c;
-	}
-}
-
-struct RJOut {
-	int nout;
-	int is_count[4];
-	int64_t *cells[4];
-	unsigned long long *cursor;
-	uint64_t cap;
-};
-
-__device__ static inline void rj_histogram(const RJSide &s, uint32_t p, uint32_t *cnt, uint32_t *total_smem)
-{
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = RJ_P2_THREADS / 32;
-	const uint64_t c0 = s.dir_off[p], c1 = s.dir_off[p + 1];
-	uint32_t seen = 0;
-	constexpr int MLP = 4; // chunks in flight per warp
-	for (uint64_t c = c0 + (uint64_t)warp * MLP; c < c1; c += (uint64_t)nwarps * MLP) {
-		int4 v[MLP];
-		uint32_t ne[MLP];
-#pragma unroll
-		for (int u = 0; u < MLP; u++) {
-			ne[u] = 0;
-			if (c + u < c1) {
-				uint32_t cid = s.dir[c + u];
-				ne[u] = s.chunk_entries[cid];
-				v[u] = mdb_ldg_stream(reinterpret_cast<const int4*>(s.pool + (size_t)cid * RJ_CHUNK) + lane);
-			}
-		}
-#pragma unroll
-		for (int u = 0; u < MLP; u++) {
-			if (!ne[u])
-				continue;
-			uint32_t w[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
-#pragma unroll
-			for (int j = 0; j < 8; j++) {
-				uint32_t idx = lane * 8 + j;
-				if (idx < ne[u]) {
-					uint32_t rem = (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu;
-					atomicAdd(&cnt[rem >> 2], 1u << ((rem & 3) * 8));
-				}
-			}
-			if (lane == 0)
-				seen += ne[u];
-		}
-	}
-	if (lane == 0 && seen)
-		atomicAdd(total_smem, seen);
-}
-
-// Pass 2.  Persistent CTAs take partitions from an atomic counter.  Both sides of a partition are
-// histogrammed into byte counters in shared memory (4 keys per 32-bit word, shared-memory atomics),
-// the byte sums are checked against the number of remainders (a wrapped byte counter changes the sum),
-// and every key present on both sides is emitted with count cntA * cntB.
-__global__ void __launch_bounds__(RJ_P2_THREADS, 1)
-k_radix_joincount(RJSide a, RJSide b, RJParams pr, RJOut out, uint32_t *__restrict__ part_counter)
-{
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	const int D = 1 << pr.shift;
-	const int words = D >= 4 ? D / 4 : 1;
-	uint32_t *cntA = reinterpret_cast<uint32_t*>(smem_raw);
-	uint32_t *cntB = cntA + words;
-	__shared__ uint32_t s_part, s_totA, s_totB, s_sumA, s_sumB;
-	__shared__ uint32_t s_scan[33];
-	__shared__ unsigned long long s_base;
-	const int tid = threadIdx.x;
-
-	while (true) {
-		if (tid == 0) {
-			s_part = atomicAdd(part_counter, 1u);
-			s_totA = s_totB = s_sumA = s_sumB = 0;
-		}
-		__syncthreads();
-		const uint32_t p = s_part;
-		if (p >= (uint32_t)pr.nparts)
-			break;
-
-		for (int w = tid; w < words * 2; w += RJ_P2_THREADS)
-			cntA[w] = 0; // cntB follows cntA
-		__syncthreads();
-		rj_histogram(a, p, cntA, &s_totA);
-		rj_histogram(b, p, cntB, &s_totB);
-		__syncthreads();
-
-		// byte-sum check + count matches
-		uint32_t sumA = 0, sumB = 0, matches = 0;
-		for (int w = tid; w < words; w += RJ_P2_THREADS) {
-			uint32_t x = cntA[w], y = cntB[w];
-			sumA = __dp4a(x, 0x01010101u, sumA);
-			sumB = __dp4a(y, 0x01010101u, sumB);
-			uint32_t m = __vcmpne4(x, 0) & __vcmpne4(y, 0);
-			matches += __popc(m) >> 3;
-		}
-		for (int o = 16; o > 0; o >>= 1) {
-			sumA += __shfl_xor_sync(0xffffffffu, sumA, o);
-			sumB += __shfl_xor_sync(0xffffffffu, sumB, o);
-		}
-		if ((tid & 31) == 0) {
-			atomicAdd(&s_sumA, sumA);
-			atomicAdd(&s_sumB, sumB);
-		}
-		// block exclusive scan of match counts
-		uint32_t incl = matches;
-		int lane = tid & 31, warp = tid >> 5;
-		for (int o = 1; o < 32; o <<= 1) {
-			uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-			if (lane >= o)
-				incl += n;
-		}
-		if (lane == 31)
-			s_scan[warp] = incl;
-		__syncthreads();
-		if (warp == 0) {
-			uint32_t w = s_scan[lane], wi = w;
-			for (int o = 1; o < 32; o <<= 1) {
-				uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
-				if (lane >= o)
-					wi += n;
-			}
-			s_scan[lane] = wi - w;
-			if (lane == 31) {
-				s_scan[32] = wi;
-				s_base = wi ? atomicAdd(out.cursor, (unsigned long long)wi) : 0ull;
-				if (s_sumA != s_totA || s_sumB != s_totB)
-					atomicOr(pr.error_flag, 2u); // a byte counter wrapped (>255 equal keys): host falls back
-			}
-		}
-		__syncthreads();
-		unsigned long long pos = s_base + s_scan[warp] + incl - matches;
-		if (matches && pos + matches <= out.cap) {
-			long long key_base = pr.kmin + (long long)((unsigned long long)p << pr.shift);
-			for (int w = tid; w < words; w += RJ_P2_THREADS) {
-				uint32_t x = cntA[w], y = cntB[w];
-				uint32_t m = __vcmpne4(x, 0) & __vcmpne4(y, 0);
-				while (m) {
-					int byte = (__ffs(m) - 1) >> 3;
-					m &= ~(0xffu << (byte * 8));
-					long long key = key_base + (long long)w * 4 + byte;
-					long long cnt = (long long)((x >> (byte * 8)) & 0xff) * (long long)((y >> (byte * 8)) & 0xff);
-#pragma unroll
-					for (int o = 0; o < 4; o++)
-						if (o < out.nout)
-							out.cells[o][pos] = out.is_count[o] ? cnt : key;
-					pos++;
-				}
-			}
-		}
-		__syncthreads();
-	}
-}
-
-static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_table *t, int col, int grid)
-{
-	memset(s, 0, sizeof(*s));
-	s->keys = t->cols[col].data;
-	s->present = col_all_present(t, col) ? nullptr : t->cols[col].present;
-	s->n = t->n_slots;
-	uint64_t chunks = t->n_slots / RJ_CHUNK + (uint64_t)grid * RJ_MAX_PART + 1024;
-	if (chunks >= 0xfffffff0ull)
-		return MDBCU_EUNSUPPORTED;
-	s->pool_chunks = (uint32_t)chunks;
-	MDB_TRY(tmp.alloc(&s->pool, chunks * RJ_CHUNK));
-	MDB_TRY(tmp.alloc(&s->pool_next, 1));
-	MDB_TRY(tmp.alloc(&s->chunk_part, chunks));
-	MDB_TRY(tmp.alloc(&s->chunk_entries, chunks));
-	MDB_TRY(tmp.alloc(&s->dir_cnt, RJ_MAX_PART + 1));
-	MDB_TRY(tmp.alloc(&s->dir_fill, RJ_MAX_PART + 1));
-	MDB_TRY(tmp.alloc(&s->dir_off, RJ_MAX_PART + 2));
-	MDB_TRY(tmp.alloc(&s->dir, chunks));
-	CUDA_TRY(ctx, cudaMemsetAsync(s->pool_next, 0, sizeof(uint32_t), ctx->stream));
-	CUDA_TRY(ctx, cudaMemsetAsync(s->dir_cnt, 0, (RJ_MAX_PART + 1) * sizeof(uint32_t), ctx->stream));
-	CUDA_TRY(ctx, cudaMemsetAsync(s->dir_fill, 0, (RJ_MAX_PART + 1) * sizeof(uint32_t), ctx->stream));
-	return MDBCU_OK;
-}
-
-int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res)
-{
-	if (plan->n_tables != 2 || plan->n_joins != 1 || plan->joins[0].cross || plan->n_pred != 0 || plan->n_group != 1 ||
-			plan->n_out < 1 || plan->n_out > 4)
-		return MDBCU_EUNSUPPORTED;
-	if (plan->flags & MDBCU_PLAN_DISTRIBUTED)
-		return MDBCU_EUNSUPPORTED; // the exchange variant lives in mdb_comm.cu (round 2)
-	const mdbcu_join &jn = plan->joins[0];
-	if (jn.left.tbl != 0 || jn.right.tbl != 1)
-		return MDBCU_EUNSUPPORTED;
-	const mdbcu_table *ta = plan->tables[0], *tb = plan->tables[1];
-	if (jn.left.col < 0 || jn.left.col >= ta->ncols || jn.right.col < 0 || jn.right.col >= tb->ncols)
-		return MDBCU_EUNSUPPORTED;
-	const DevColumn &ca = ta->cols[jn.left.col], &cb = tb->cols[jn.right.col];
-	auto intlike = [](int type) { return type == MDBCU_CT_INTEGER || type == MDBCU_CT_DATE || type == MDBCU_CT_DATETIME; };
-	if (!intlike(ca.type) || !intlike(cb.type) || !ca.stats_ok || !cb.stats_ok)
-		return MDBCU_EUNSUPPORTED;
-	auto is_key = [&](const mdbcu_colref &r) {
-		return (r.tbl == 0 && r.col == jn.left.col) || (r.tbl == 1 && r.col == jn.right.col);
-	};
-	if (!is_key(plan->group[0]))
-		return MDBCU_EUNSUPPORTED;
-	for (int o = 0; o < plan->n_out; o++) {
-		if (plan->out[o].kind == MDBCU_OUT_COUNT_STAR)
-			continue;
-		if (plan->out[o].kind != MDBCU_OUT_COLUMN || !is_key(plan->out[o].ref))
-			return MDBCU_EUNSUPPORTED;
-	}
-	if (ta->n_slots + tb->n_slots < (1ull << 20))
-		return MDBCU_EUNSUPPORTED; // small inputs: general operators (they also return the reference's row order)
-
-	// only keys inside both columns' [min, max] can ever match
-	long long kmin = std::max(ca.imin, cb.imin), kmax = std::min(ca.imax, cb.imax);
-	if (ca.imin > ca.imax || cb.imin > cb.imax || kmin > kmax) {
-		ctx->stats.path = MDBCU_PATH_RADIX_JOINCOUNT;
-		return mdb_result_alloc(ctx, plan, res, 0, false);
-	}
-	unsigned long long range = (unsigned long long)kmax - (unsigned long long)kmin + 1ull;
-	if (range == 0 || range > ((unsigned long long)RJ_MAX_PART << RJ_MAX_SHIFT) || range < 4096)
-		return MDBCU_EUNSUPPORTED;
-	int bits = 0;
-	while ((1ull << bits) < range)
-		bits++;
-	int shift = std::max(0, bits - 12);
-	int nparts = (int)((range + (1ull << shift) - 1) >> shift);
-
-	ctx->stats.path = MDBCU_PATH_RADIX_JOINCOUNT;
-	PhaseClock clock(ctx);
-	DevTemp tmp(ctx);
-	const int grid1 = ctx->num_sms;
-	RJSide sa, sb;
-	RJParams pr;
-	MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1));
-	MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1));
-	pr.kmin = kmin;
-	pr.range = range;
-	pr.shift = shift;
-	pr.nparts = nparts;
-	uint32_t *d_flags; // [0] error flag, [1] partition counter
-	unsigned long long *d_cursor;
-	MDB_TRY(tmp.alloc(&d_flags, 2));
-	MDB_TRY(tmp.alloc(&d_cursor, 1));
-	CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint32_t), ctx->stream));
-	CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
-	pr.error_flag = d_flags;
-
-	uint64_t cap_groups = std::min<uint64_t>(std::min<uint64_t>(ta->n_slots, tb->n_slots), range);
-	MDB_TRY(mdb_result_alloc(ctx, plan, res, 0, false));
-	RJOut out;
-	memset(&out, 0, sizeof(out));
-	out.nout = plan->n_out;
-	out.cursor = d_cursor;
-	out.cap = cap_groups;
-	for (int o = 0; o < plan->n_out; o++) {
-		mdb_free(ctx, res->cols[o].cells);
-		mdb_free(ctx, res->cols[o].nulls);
-		res->cols[o].nulls = nullptr; // NULL keys never join (executor_select.c:716-738): no NULL cells in this result
-		res->cols[o].cells = nullptr;
-		MDB_TRY(mdb_alloc(ctx, &res->cols[o].cells, cap_groups));
-		out.cells[o] = res->cols[o].cells;
-		out.is_count[o] = plan->out[o].kind == MDBCU_OUT_COUNT_STAR;
-	}
-
-	static bool attr_done = false;
-	size_t smem1 = sizeof(RJP1Smem);
-	size_t smem2 = 2 * (size_t)std::max(1, (1 << shift) / 4) * sizeof(uint32_t);
-	if (!attr_done) {
-		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
-		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_joincount, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
-		attr_done = true;
-	}
-
-	cudaEvent_t k0, k1;
-	cudaEventCreate(&k0);
-	cudaEventCreate(&k1);
-	clock.begin(1);
-	cudaEventRecord(k0, ctx->stream);
-	MDB_LAUNCH(ctx, k_radix_partition, grid1, RJ_P1_THREADS, smem1, sa, pr);
-	MDB_LAUNCH(ctx, k_radix_partition, grid1, RJ_P1_THREADS, smem1, sb, pr);
-	cudaEventRecord(k1, ctx->stream);
-	clock.begin(7);
-	MDB_LAUNCH(ctx, k_radix_dir_scan, 1, 1024, 0, sa, nparts);
-	MDB_LAUNCH(ctx, k_radix_dir_scan, 1, 1024, 0, sb, nparts);
-	MDB_LAUNCH(ctx, k_radix_dir_fill, ctx->num_sms * 4, 256, 0, sa);
-	MDB_LAUNCH(ctx, k_radix_dir_fill, ctx->num_sms * 4, 256, 0, sb);
-	clock.begin(2);
-	cudaEvent_t k2, k3;
-	cudaEventCreate(&k2);
-	cudaEventCreate(&k3);
-	cudaEventRecord(k2, ctx->stream);
-	MDB_LAUNCH(ctx, k_radix_joincount, std::min(nparts, ctx->num_sms), RJ_P2_THREADS, smem2, sa, sb, pr, out, d_flags + 1);
-	cudaEventRecord(k3, ctx->stream);
-	cudaError_t e = cudaGetLastError();
-	clock.finish();
-	float ms1 = 0.f, ms2 = 0.f;
-	cudaEventElapsedTime(&ms1, k0, k1);
-	cudaEventElapsedTime(&ms2, k2, k3);
-	cudaEventDestroy(k0);
-	cudaEventDestroy(k1);
-	cudaEventDestroy(k2);
-	cudaEventDestroy(k3);
-	if (e != cudaSuccess)
-		return mdb_fail(ctx, MDBCU_ECUDA, "radix join launch failed: %s", cudaGetErrorString(e));
-
-	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar, d_cursor, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar + 1, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-	uint64_t ngroups = ctx->h_scalar[0];
-	uint32_t flags = (uint32_t)(ctx->h_scalar[1] & 0xffffffffu);
-	if (flags || ngroups > cap_groups) {
-		// more than 255 equal keys in one partition (or pool exhaustion): redo with the general operators
-		return MDBCU_EUNSUPPORTED;
-	}
-	res->nrows = ngroups;
-
-	// compulsory traffic: every key once in, every (key, count) group once out
-	ctx->stats.algorithmic_bytes = 8ull * (ta->n_slots + tb->n_slots) + 8ull * plan->n_out * ngroups;
-	ctx->stats.dominant_ms = ms1 + ms2;
-	ctx->stats.dominant_bytes = ctx->stats.algorithmic_bytes;
-	return MDBCU_OK;
-}
-
 // ===================================================================================== small-build star join
 
 int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res)

@@ -1,0 +1,510 @@
+// mdb_radix.cu - radix-partitioned join + GROUP BY join key + COUNT(*)   (the README query; BASELINE configs 1 and 3)
+//
+//   SELECT k, COUNT(*) FROM A INNER JOIN B ON A.k = B.k GROUP BY k
+//
+// replaces _join_nested_loop_tbl2tbl (src/engine/executor_select.c:1076) + proc_groupby_clause (:1526):
+// result(k) = cntA[k] * cntB[k]; no candidate pair and no joined row is ever materialised.
+//
+//   pass 1  k_radix_partition   streams the 8-byte keys ONCE, writes 2-byte remainders into per-partition
+//                               512-byte chunks (partition = high bits of key - kmin, <= 4096 partitions);
+//   (dir)   k_radix_dir_*       counting sort of chunk ids by partition (a few microseconds);
+//   pass 2  k_radix_joincount   per partition: both sides' remainders -> packed 4- or 8-bit counters in shared
+//                               memory, checksum against the number of remainders, multiply, emit groups.
+//
+// Algorithmic bytes: 8|A| + 8|B| in, 16 G out.  Extra traffic of this design: 2 bytes per key
+// written + read back (the remainders).  HBM-bound integer work; no tensor cores (nothing here is a contraction).
+#include "mdb_common.cuh"
+
+#include <string.h>
+#include <algorithm>
+
+#define RJ_MAX_PART 4096           // partitions (12 radix bits)
+#define RJ_MAX_SHIFT 16            // remainder bits: 2-byte remainders
+#define RJ_CAP 20                  // staging slots per partition in shared memory
+#define RJ_FLUSH 16                // a partition is flushed when 16 remainders (= one 32-byte sector) are staged
+#define RJ_CHUNK 256               // remainders per chunk (512 bytes = one warp-wide 128-bit load)
+#define RJ_BLOCKS_PER_CHUNK (RJ_CHUNK / RJ_FLUSH)
+#define RJ_P1_THREADS 1024
+#define RJ_P1_LOADS 4              // 128-bit loads (2 keys each) per thread per round
+#define RJ_P1_TILE (RJ_P1_THREADS * RJ_P1_LOADS * 2)
+#define RJ_OVF_CAP 1024            // keys per round that may find their staging row full and wait one round
+#define RJ_NONE 0xffffffffu
+
+#define RJ_ERR_POOL 1u             // chunk pool exhausted
+#define RJ_ERR_COUNTER 2u          // a packed counter wrapped (too many equal keys for the counter width)
+#define RJ_ERR_SKEW 4u             // more than RJ_OVF_CAP keys per round hit full staging rows
+
+static bool col_all_present(const mdbcu_table *t, int col)
+{
+	return t->all_live && !t->cols[col].has_nulls;
+}
+
+struct RJDesc {
+	uint32_t cid;
+	uint32_t ne;
+};
+
+struct RJSide {
+	const int64_t *keys;
+	const uint32_t *present;
+	uint64_t n;
+	uint16_t *pool;            // pool_chunks * RJ_CHUNK remainders
+	uint32_t pool_chunks;
+	uint32_t *pool_next;       // allocation cursor
+	uint16_t *chunk_part;      // partition of each chunk
+	uint16_t *chunk_entries;   // valid remainders in each chunk
+	uint32_t *dir_cnt;         // chunks per partition
+	RJDesc *dir;               // (chunk id, entries) grouped by partition
+	uint64_t *dir_off;         // exclusive offsets into dir
+	uint32_t *dir_fill;
+};
+
+struct RJParams {
+	long long kmin;
+	unsigned long long range;  // keys in [kmin, kmin + range) can match
+	int shift;                 // remainder bits
+	uint32_t mask;             // (1 << shift) - 1
+	int nparts;
+	uint32_t *error_flag;
+};
+
+struct RJP1Smem {
+	uint16_t stage[RJ_MAX_PART * RJ_CAP];     // 160 KiB: 20 two-byte slots per partition
+	uint32_t fill[RJ_MAX_PART];               // slots handed out this round (may overshoot RJ_CAP)
+	uint32_t chunk[RJ_MAX_PART];              // current chunk of this CTA: chunk id * 32 + sectors used, or RJ_NONE
+	uint16_t worklist[2][RJ_MAX_PART];        // partitions whose 16th slot filled this round
+	uint32_t ovf[2][RJ_OVF_CAP];              // (partition << 16 | remainder) waiting for the next round
+	uint32_t wl_count[2];
+	uint32_t ovf_count[2];
+};
+
+__device__ static inline uint32_t rj_new_chunk(const RJSide &s, const RJParams &pr, RJP1Smem *sm, uint32_t p)
+{
+	uint32_t old = sm->chunk[p];
+	uint32_t cid = atomicAdd(s.pool_next, 1u);
+	if (cid >= s.pool_chunks) {
+		atomicOr(pr.error_flag, RJ_ERR_POOL);
+		return RJ_NONE;
+	}
+	if (old != RJ_NONE)
+		s.chunk_entries[old >> 5] = RJ_CHUNK; // a chunk is only replaced when all its sectors are written
+	s.chunk_part[cid] = (uint16_t)p;
+	atomicAdd(&s.dir_cnt[p], 1u);
+	sm->chunk[p] = cid << 5;
+	return cid;
+}
+
+__device__ static inline void rj_insert(RJP1Smem *sm, const RJParams &pr, uint32_t item, int par)
+{
+	uint32_t p = item >> 16;
+	uint32_t pos = atomicAdd(&sm->fill[p], 1u);
+	if (pos < RJ_CAP) {
+		sm->stage[p * RJ_CAP + pos] = (uint16_t)item;
+		if (pos == RJ_FLUSH - 1)
+			sm->worklist[par][atomicAdd(&sm->wl_count[par], 1u)] = (uint16_t)p;
+	} else {
+		// staging row full until this round's flush: park the key for one round
+		uint32_t o = atomicAdd(&sm->ovf_count[par], 1u);
+		if (o < RJ_OVF_CAP)
+			sm->ovf[par][o] = item;
+		else
+			atomicOr(pr.error_flag, RJ_ERR_SKEW);
+	}
+}
+
+template <bool HAS_PRESENT>
+__device__ static inline void rj_round(const RJSide &s, const RJParams &pr, RJP1Smem *sm, const int4 *buf, uint64_t tile,
+		bool have_keys, int par)
+{
+	const int tid = threadIdx.x;
+
+	// keys parked by the previous round go first (their rows were flushed since)
+	uint32_t novf = min(sm->ovf_count[par ^ 1], (uint32_t)RJ_OVF_CAP);
+	for (uint32_t i = tid; i < novf; i += RJ_P1_THREADS)
+		rj_insert(sm, pr, sm->ovf[par ^ 1][i], par);
+
+	if (have_keys) {
+		const uint64_t base_pair = tile * (RJ_P1_TILE / 2);
+		uint32_t item[RJ_P1_LOADS * 2], pos[RJ_P1_LOADS * 2];
+#pragma unroll
+		for (int j = 0; j < RJ_P1_LOADS; j++) {
+			const uint64_t pi = base_pair + (uint64_t)j * RJ_P1_THREADS + tid;
+			uint32_t pw = 0xffffffffu;
+			if (HAS_PRESENT)
+				pw = (pi * 2 < s.n) ? (s.present[pi >> 4] >> ((pi & 15) * 2)) : 0u;
+			const unsigned long long k0 = ((unsigned long long)(unsigned)buf[j].y << 32) | (unsigned)buf[j].x;
+			const unsigned long long k1 = ((unsigned long long)(unsigned)buf[j].w << 32) | (unsigned)buf[j].z;
+			const unsigned long long d0 = k0 - (unsigned long long)pr.kmin, d1 = k1 - (unsigned long long)pr.kmin;
+			bool ok0 = d0 < pr.range && pi * 2 < s.n, ok1 = d1 < pr.range && pi * 2 + 1 < s.n;
+			if (HAS_PRESENT) {
+				ok0 = ok0 && (pw & 1u);
+				ok1 = ok1 && (pw & 2u);
+			}
+			item[2 * j] = ok0 ? ((((uint32_t)d0 >> pr.shift) << 16) | ((uint32_t)d0 & pr.mask)) : RJ_NONE;
+			item[2 * j + 1] = ok1 ? ((((uint32_t)d1 >> pr.shift) << 16) | ((uint32_t)d1 & pr.mask)) : RJ_NONE;
+		}
+		// all slot requests of this thread are issued back to back (independent shared-memory atomics) ...
+#pragma unroll
+		for (int k = 0; k < RJ_P1_LOADS * 2; k++)
+			pos[k] = item[k] != RJ_NONE ? atomicAdd(&sm->fill[item[k] >> 16], 1u) : RJ_NONE;
+		// ... and only then consumed
+#pragma unroll
+		for (int k = 0; k < RJ_P1_LOADS * 2; k++) {
+			if (pos[k] < RJ_CAP) {
+				const uint32_t p = item[k] >> 16;
+				sm->stage[p * RJ_CAP + pos[k]] = (uint16_t)item[k];
+				if (pos[k] == RJ_FLUSH - 1)
+					sm->worklist[par][atomicAdd(&sm->wl_count[par], 1u)] = (uint16_t)p;
+			} else if (item[k] != RJ_NONE) {
+				const uint32_t o = atomicAdd(&sm->ovf_count[par], 1u);
+				if (o < RJ_OVF_CAP)
+					sm->ovf[par][o] = item[k];
+				else
+					atomicOr(pr.error_flag, RJ_ERR_SKEW);
+			}
+		}
+	}
+	__syncthreads();
+
+	const uint32_t nwl = sm->wl_count[par];
+	if (tid == 0) {
+		// the other parity's lists were consumed (worklist: last round's flush; parked keys: above)
+		sm->wl_count[par ^ 1] = 0;
+		sm->ovf_count[par ^ 1] = 0;
+	}
+	// flush: one lane per queued partition writes its first 16 remainders as ONE aligned 32-byte sector
+	for (uint32_t w = tid; w < nwl; w += RJ_P1_THREADS) {
+		const uint32_t p = sm->worklist[par][w];
+		const uint32_t f = min(sm->fill[p], (uint32_t)RJ_CAP);
+		uint32_t ch = sm->chunk[p];
+		if (ch == RJ_NONE || (ch & 31u) == RJ_BLOCKS_PER_CHUNK) {
+			rj_new_chunk(s, pr, sm, p);
+			ch = sm->chunk[p];
+		}
+		uint2 *row = reinterpret_cast<uint2*>(&sm->stage[p * RJ_CAP]); // 40-byte rows are 8-byte aligned
+		const uint2 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4];
+		if (ch != RJ_NONE && (ch & 31u) < RJ_BLOCKS_PER_CHUNK) {
+			int4 *dst = reinterpret_cast<int4*>(s.pool + (size_t)(ch >> 5) * RJ_CHUNK + (ch & 31u) * RJ_FLUSH);
+			dst[0] = make_int4((int)a.x, (int)a.y, (int)b.x, (int)b.y);
+			dst[1] = make_int4((int)c.x, (int)c.y, (int)d.x, (int)d.y);
+			sm->chunk[p] = ch + 1;
+		}
+		row[0] = e; // keep the (at most 4) remainders behind the flushed sector
+		sm->fill[p] = f - RJ_FLUSH;
+	}
+	__syncthreads();
+}
+
+template <bool HAS_PRESENT>
+__device__ static inline void rj_load_tile(const RJSide &s, uint64_t tile, int4 *dst)
+{
+	const int4 *src = reinterpret_cast<const int4*>(s.keys);
+	const uint64_t npairs = s.n / 2;
+	const uint64_t base_pair = tile * (RJ_P1_TILE / 2);
+	// pull the tile this CTA will load two rounds from now into L2 (one 128-byte line per thread)
+	const uint64_t pf_first = (tile + 2ull * gridDim.x) * RJ_P1_TILE + (uint64_t)threadIdx.x * 16;
+	if (threadIdx.x < RJ_P1_TILE / 16 && pf_first + 16 <= s.n)
+		asm volatile("prefetch.global.L2 [%0];" ::"l"(s.keys + pf_first));
+	if (base_pair + RJ_P1_TILE / 2 <= npairs) {
+#pragma unroll
+		for (int j = 0; j < RJ_P1_LOADS; j++)
+			dst[j] = mdb_ldg_stream(src + base_pair + (uint64_t)j * RJ_P1_THREADS + threadIdx.x);
+	} else {
+#pragma unroll
+		for (int j = 0; j < RJ_P1_LOADS; j++) {
+			const uint64_t pi = base_pair + (uint64_t)j * RJ_P1_THREADS + threadIdx.x;
+			if (pi < npairs) {
+				dst[j] = mdb_ldg_stream(src + pi);
+			} else if (pi == npairs && (s.n & 1)) {
+				const unsigned long long last = (unsigned long long)s.keys[s.n - 1];
+				dst[j] = make_int4((int)(unsigned)last, (int)(unsigned)(last >> 32), 0, 0);
+			} else {
+				dst[j] = make_int4(0, 0, 0, 0);
+			}
+		}
+	}
+}
+
+// Pass 1.  One persistent 1024-thread CTA per SM.  Keys are streamed with 128-bit loads, double-buffered in
+// registers (ping-pong, no copies).  Each key costs one shared-memory atomic (slot in its partition's staging
+// row) and one 2-byte shared store.  The thread that fills slot 16 of a row queues the partition; after the
+// round's barrier one lane per queued partition writes 16 remainders as one aligned 32-byte sector into the
+// CTA's current 512-byte chunk of that partition: DRAM only sees full-sector writes, 2 bytes per key.
+template <bool HAS_PRESENT>
+__global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition(RJSide s, RJParams pr)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	RJP1Smem *sm = reinterpret_cast<RJP1Smem*>(smem_raw);
+	const int tid = threadIdx.x;
+
+	for (int p = tid; p < RJ_MAX_PART; p += RJ_P1_THREADS) {
+		sm->fill[p] = 0;
+		sm->chunk[p] = RJ_NONE;
+	}
+	if (tid < 2) {
+		sm->wl_count[tid] = 0;
+		sm->ovf_count[tid] = 0;
+	}
+	__syncthreads();
+
+	const uint64_t ntiles = (s.n + RJ_P1_TILE - 1) / RJ_P1_TILE;
+	int4 buf_a[RJ_P1_LOADS], buf_b[RJ_P1_LOADS];
+	uint64_t tile = blockIdx.x;
+	int par = 0;
+	if (tile < ntiles)
+		rj_load_tile<HAS_PRESENT>(s, tile, buf_a);
+	while (tile < ntiles) {
+		uint64_t next = tile + gridDim.x;
+		if (next < ntiles)
+			rj_load_tile<HAS_PRESENT>(s, next, buf_b);
+		rj_round<HAS_PRESENT>(s, pr, sm, buf_a, tile, true, par);
+		par ^= 1;
+		tile = next;
+		if (tile >= ntiles)
+			break;
+		next = tile + gridDim.x;
+		if (next < ntiles)
+			rj_load_tile<HAS_PRESENT>(s, next, buf_a);
+		rj_round<HAS_PRESENT>(s, pr, sm, buf_b, tile, true, par);
+		par ^= 1;
+		tile = next;
+	}
+	// keys still parked by the last round(s)
+	while (sm->ovf_count[par ^ 1] != 0) { // block-uniform: written before the last barrier
+		rj_round<HAS_PRESENT>(s, pr, sm, buf_a, 0, false, par);
+		par ^= 1;
+	}
+
+	// drain: every partition's partial sector goes out, chunk entry counts are finalised
+	for (int p = tid; p < pr.nparts; p += RJ_P1_THREADS) {
+		const uint32_t f = min(sm->fill[p], (uint32_t)RJ_CAP);
+		uint32_t ch = sm->chunk[p];
+		if (f > 0) {
+			if (ch == RJ_NONE || (ch & 31u) == RJ_BLOCKS_PER_CHUNK) {
+				rj_new_chunk(s, pr, sm, p);
+				ch = sm->chunk[p];
+			}
+			if (ch != RJ_NONE && (ch & 31u) < RJ_BLOCKS_PER_CHUNK) {
+				uint16_t *dst = s.pool + (size_t)(ch >> 5) * RJ_CHUNK + (ch & 31u) * RJ_FLUSH;
+				for (uint32_t i = 0; i < f; i++)
+					dst[i] = sm->stage[p * RJ_CAP + i];
+				s.chunk_entries[ch >> 5] = (uint16_t)((ch & 31u) * RJ_FLUSH + f);
+			}
+		} else if (ch != RJ_NONE) {
+			s.chunk_entries[ch >> 5] = (uint16_t)((ch & 31u) * RJ_FLUSH);
+		}
+	}
+}
+
+// exclusive scan of the per-partition chunk counts (single block, nparts <= 4096)
+__global__ void k_radix_dir_scan(RJSide s, int nparts)
+{
+	__shared__ uint64_t warp_tot[33];
+	uint64_t carry = 0;
+	for (int base = 0; base < nparts + 1; base += blockDim.x) {
+		int i = base + threadIdx.x;
+		uint64_t v = i < nparts ? s.dir_cnt[i] : 0;
+		uint64_t incl = v;
+		int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+		for (int o = 1; o < 32; o <<= 1) {
+			uint64_t n = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o)
+				incl += n;
+		}
+		if (lane == 31)
+			warp_tot[warp] = incl;
+		__syncthreads();
+		if (warp == 0) {
+			uint64_t w = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0, wi = w;
+			for (int o = 1; o < 32; o <<= 1) {
+				uint64_t n = __shfl_up_sync(0xffffffffu, wi, o);
+				if (lane >= o)
+					wi += n;
+			}
+			warp_tot[lane] = wi - w;
+			if (lane == 31)
+				warp_tot[32] = wi;
+		}
+		__syncthreads();
+		if (i < nparts + 1)
+			s.dir_off[i] = carry + warp_tot[warp] + incl - v;
+		carry += warp_tot[32];
+		__syncthreads();
+	}
+}
+
+#include "mdb_radix_pass2.cuh"
+
+static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_table *t, int col, int grid)
+{
+	memset(s, 0, sizeof(*s));
+	s->keys = t->cols[col].data;
+	s->present = col_all_present(t, col) ? nullptr : t->cols[col].present;
+	s->n = t->n_slots;
+	uint64_t chunks = t->n_slots / RJ_CHUNK + (uint64_t)grid * RJ_MAX_PART + 1024;
+	if (chunks >= (1ull << 27))
+		return MDBCU_EUNSUPPORTED;
+	s->pool_chunks = (uint32_t)chunks;
+	MDB_TRY(tmp.alloc(&s->pool, chunks * RJ_CHUNK));
+	MDB_TRY(tmp.alloc(&s->pool_next, 1));
+	MDB_TRY(tmp.alloc(&s->chunk_part, chunks));
+	MDB_TRY(tmp.alloc(&s->chunk_entries, chunks));
+	MDB_TRY(tmp.alloc(&s->dir_cnt, RJ_MAX_PART + 1));
+	MDB_TRY(tmp.alloc(&s->dir_fill, RJ_MAX_PART + 1));
+	MDB_TRY(tmp.alloc(&s->dir_off, RJ_MAX_PART + 2));
+	MDB_TRY(tmp.alloc(&s->dir, chunks));
+	CUDA_TRY(ctx, cudaMemsetAsync(s->pool_next, 0, sizeof(uint32_t), ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(s->dir_cnt, 0, (RJ_MAX_PART + 1) * sizeof(uint32_t), ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(s->dir_fill, 0, (RJ_MAX_PART + 1) * sizeof(uint32_t), ctx->stream));
+	return MDBCU_OK;
+}
+
+static void launch_partition(mdbcu_ctx *ctx, int grid, const RJSide &s, const RJParams &pr)
+{
+	if (s.present)
+		MDB_LAUNCH(ctx, k_radix_partition<true>, grid, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
+	else
+		MDB_LAUNCH(ctx, k_radix_partition<false>, grid, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
+}
+
+int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res)
+{
+	if (plan->n_tables != 2 || plan->n_joins != 1 || plan->joins[0].cross || plan->n_pred != 0 || plan->n_group != 1 ||
+			plan->n_out < 1 || plan->n_out > 4)
+		return MDBCU_EUNSUPPORTED;
+	if (plan->flags & MDBCU_PLAN_DISTRIBUTED)
+		return MDBCU_EUNSUPPORTED;
+	const mdbcu_join &jn = plan->joins[0];
+	if (jn.left.tbl != 0 || jn.right.tbl != 1)
+		return MDBCU_EUNSUPPORTED;
+	const mdbcu_table *ta = plan->tables[0], *tb = plan->tables[1];
+	if (jn.left.col < 0 || jn.left.col >= ta->ncols || jn.right.col < 0 || jn.right.col >= tb->ncols)
+		return MDBCU_EUNSUPPORTED;
+	const DevColumn &ca = ta->cols[jn.left.col], &cb = tb->cols[jn.right.col];
+	auto intlike = [](int type) { return type == MDBCU_CT_INTEGER || type == MDBCU_CT_DATE || type == MDBCU_CT_DATETIME; };
+	if (!intlike(ca.type) || !intlike(cb.type) || !ca.stats_ok || !cb.stats_ok)
+		return MDBCU_EUNSUPPORTED;
+	auto is_key = [&](const mdbcu_colref &r) {
+		return (r.tbl == 0 && r.col == jn.left.col) || (r.tbl == 1 && r.col == jn.right.col);
+	};
+	if (!is_key(plan->group[0]))
+		return MDBCU_EUNSUPPORTED;
+	for (int o = 0; o < plan->n_out; o++) {
+		if (plan->out[o].kind == MDBCU_OUT_COUNT_STAR)
+			continue;
+		if (plan->out[o].kind != MDBCU_OUT_COLUMN || !is_key(plan->out[o].ref))
+			return MDBCU_EUNSUPPORTED;
+	}
+	if (ta->n_slots + tb->n_slots < (1ull << 20))
+		return MDBCU_EUNSUPPORTED; // small inputs: general operators (they also return the reference's row order)
+
+	// only keys inside both columns' [min, max] (zone-map statistics kept by the mirror) can ever match
+	long long kmin = std::max(ca.imin, cb.imin), kmax = std::min(ca.imax, cb.imax);
+	if (ca.imin > ca.imax || cb.imin > cb.imax || kmin > kmax) {
+		ctx->stats.path = MDBCU_PATH_RADIX_JOINCOUNT;
+		return mdb_result_alloc(ctx, plan, res, 0, false);
+	}
+	unsigned long long range = (unsigned long long)kmax - (unsigned long long)kmin + 1ull;
+	if (range == 0 || range > ((unsigned long long)RJ_MAX_PART << RJ_MAX_SHIFT) || range < 4096)
+		return MDBCU_EUNSUPPORTED;
+	int bits = 0;
+	while ((1ull << bits) < range)
+		bits++;
+	int shift = std::max(0, bits - 12);
+	int nparts = (int)((range + (1ull << shift) - 1) >> shift);
+
+	ctx->stats.path = MDBCU_PATH_RADIX_JOINCOUNT;
+	PhaseClock clock(ctx);
+	DevTemp tmp(ctx);
+	const int grid1 = ctx->num_sms;
+	RJSide sa, sb;
+	RJParams pr;
+	MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1));
+	MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1));
+	pr.kmin = kmin;
+	pr.range = range;
+	pr.shift = shift;
+	pr.mask = (1u << shift) - 1u;
+	pr.nparts = nparts;
+	uint32_t *d_flags; // [0] error flags, [1] partition counter
+	unsigned long long *d_cursor;
+	MDB_TRY(tmp.alloc(&d_flags, 2));
+	MDB_TRY(tmp.alloc(&d_cursor, 1));
+	CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint32_t), ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
+	pr.error_flag = d_flags;
+
+	uint64_t cap_groups = std::min<uint64_t>(std::min<uint64_t>(ta->n_slots, tb->n_slots), range);
+	MDB_TRY(mdb_result_alloc(ctx, plan, res, 0, false));
+	RJOut out;
+	memset(&out, 0, sizeof(out));
+	out.nout = plan->n_out;
+	out.cursor = d_cursor;
+	out.cap = cap_groups;
+	for (int o = 0; o < plan->n_out; o++) {
+		mdb_free(ctx, res->cols[o].cells);
+		mdb_free(ctx, res->cols[o].nulls);
+		res->cols[o].nulls = nullptr; // NULL keys never join (executor_select.c:716-738): no NULL cells in this result
+		res->cols[o].cells = nullptr;
+		MDB_TRY(mdb_alloc(ctx, &res->cols[o].cells, cap_groups));
+		out.cells[o] = res->cols[o].cells;
+		out.is_count[o] = plan->out[o].kind == MDBCU_OUT_COUNT_STAR;
+	}
+
+	static bool attr_done = false;
+	if (!attr_done) {
+		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
+		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 2 * RJ_DESC_CAP * (int)sizeof(RJDesc)));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 + 2 * RJ_DESC_CAP * (int)sizeof(RJDesc)));
+		attr_done = true;
+	}
+
+	clock.begin(1);
+	launch_partition(ctx, grid1, sa, pr);
+	launch_partition(ctx, grid1, sb, pr);
+	clock.begin(7);
+	MDB_LAUNCH(ctx, k_radix_dir_scan, 1, 1024, 0, sa, nparts);
+	MDB_LAUNCH(ctx, k_radix_dir_scan, 1, 1024, 0, sb, nparts);
+	MDB_LAUNCH(ctx, k_radix_dir_fill, ctx->num_sms * 4, 256, 0, sa);
+	MDB_LAUNCH(ctx, k_radix_dir_fill, ctx->num_sms * 4, 256, 0, sb);
+	clock.begin(2);
+
+	// 4-bit counters (two CTAs per SM) when keys are mostly unique per side, 8-bit otherwise; a wrapped
+	// counter is detected by the checksum and the pass is repeated one width up before giving up
+	const uint64_t D = 1ull << shift;
+	bool try4 = std::max(ta->n_slots, tb->n_slots) <= 2 * range;
+	uint64_t ngroups = 0;
+	uint32_t flags = 0;
+	for (int attempt = try4 ? 0 : 1; attempt < 2; attempt++) {
+		const int bitsw = attempt == 0 ? 4 : 8;
+		const size_t smem2 = 2 * (size_t)std::max<uint64_t>(1, D * bitsw / 32) * sizeof(uint32_t) + 2 * RJ_DESC_CAP * sizeof(RJDesc);
+		const int grid2 = std::min(nparts, ctx->num_sms * (bitsw == 4 ? 2 : 1));
+		if (bitsw == 4)
+			MDB_LAUNCH(ctx, (k_radix_joincount<4, 512>), grid2, 512, smem2, sa, sb, pr, out, d_flags + 1);
+		else
+			MDB_LAUNCH(ctx, (k_radix_joincount<8, 1024>), grid2, 1024, smem2, sa, sb, pr, out, d_flags + 1);
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess)
+			return mdb_fail(ctx, MDBCU_ECUDA, "radix join launch failed: %s", cudaGetErrorString(e));
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar, d_cursor, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar + 1, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+		ngroups = ctx->h_scalar[0];
+		flags = (uint32_t)(ctx->h_scalar[1] & 0xffffffffu);
+		if (flags != RJ_ERR_COUNTER || attempt == 1)
+			break;
+		// a 4-bit counter wrapped: repeat pass 2 with 8-bit counters (the partitioned remainders are still valid)
+		CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint32_t), ctx->stream));
+		CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
+	}
+	clock.finish();
+	if (flags || ngroups > cap_groups)
+		return MDBCU_EUNSUPPORTED; // heavy duplicates / skew / pool exhaustion: the general operators redo the query
+	res->nrows = ngroups;
+
+	ctx->stats.algorithmic_bytes = 8ull * (ta->n_slots + tb->n_slots) + 8ull * plan->n_out * ngroups;
+	ctx->stats.dominant_ms = ctx->stats.phase_ms[1] + ctx->stats.phase_ms[2];
+	ctx->stats.dominant_bytes = ctx->stats.algorithmic_bytes;
+	return MDBCU_OK;
+}

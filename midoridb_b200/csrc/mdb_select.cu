@@ -114,6 +114,28 @@ extern "C" int mdbcu_get_stats(mdbcu_ctx *ctx, struct mdbcu_stats *out)
 	return MDBCU_OK;
 }
 
+extern "C" void *mdbcu_host_alloc(mdbcu_ctx *ctx, size_t bytes)
+{
+	void *p = nullptr;
+	if (!ctx)
+		return nullptr;
+	cudaSetDevice(ctx->device);
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+		cudaGetLastError();
+		mdb_fail(ctx, MDBCU_ENOMEM, "cannot page-lock %zu bytes of host memory", bytes);
+		return nullptr;
+	}
+	return p;
+}
+
+extern "C" void mdbcu_host_free(mdbcu_ctx *ctx, void *p)
+{
+	if (ctx && p) {
+		cudaSetDevice(ctx->device);
+		cudaFreeHost(p);
+	}
+}
+
 extern "C" int mdbcu_event_record(mdbcu_ctx *ctx, int slot)
 {
 	if (!ctx || slot < 0 || slot >= MDBCU_EVENT_SLOTS)
