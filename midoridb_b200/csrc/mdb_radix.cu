@@ -27,7 +27,7 @@
 #define RJ_P1_THREADS 1024
 #define RJ_P1_LOADS 4              // 128-bit loads (2 keys each) per thread per round
 #define RJ_P1_TILE (RJ_P1_THREADS * RJ_P1_LOADS * 2)
-#define RJ_OVF_CAP 1024            // keys per round that may find their staging row full and wait one round
+#define RJ_OVF_CAP 1536            // keys per round that may find their staging row full and wait one round
 #define RJ_NONE 0xffffffffu
 
 #define RJ_ERR_POOL 1u             // chunk pool exhausted
@@ -48,6 +48,7 @@ struct RJSide {
 	const int64_t *keys;
 	const uint32_t *present;
 	uint64_t n;
+	int all_in_range;          // every key of the column lies in [kmin, kmin + range): no per-key range test
 	uint16_t *pool;            // pool_chunks * RJ_CHUNK remainders
 	uint32_t pool_chunks;
 	uint32_t *pool_next;       // allocation cursor
@@ -76,67 +77,153 @@ struct RJP1Smem {
 	uint32_t ovf[2][RJ_OVF_CAP];              // (partition << 16 | remainder) waiting for the next round
 	uint32_t wl_count[2];
 	uint32_t ovf_count[2];
+	uint32_t local_next, local_end;           // chunk ids reserved by this CTA (refilled in bulk by thread 0)
 };
 
-__device__ static inline uint32_t rj_new_chunk(const RJSide &s, const RJParams &pr, RJP1Smem *sm, uint32_t p)
+static_assert(sizeof(RJP1Smem) <= 227 * 1024, "pass-1 shared memory exceeds the 227 KiB a CTA can opt into");
+
+// plain shared-memory atomic: kept in PTX so the compiler does not expand it into warp-aggregation code
+__device__ __forceinline__ uint32_t rj_smem_inc(uint32_t *p)
 {
-	uint32_t old = sm->chunk[p];
-	uint32_t cid = atomicAdd(s.pool_next, 1u);
+	uint32_t old;
+	asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+	return old;
+}
+
+__device__ __forceinline__ void rj_global_red_inc(uint32_t *p)
+{
+	asm volatile("red.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+}
+
+// chunk ids come from the CTA's reserved range (one shared-memory atomic); thread 0 tops the range up with ONE
+// global atomic per RJ_ID_BATCH chunks while the other threads insert keys, so no flush ever waits on L2
+#define RJ_ID_BATCH 8192
+#define RJ_ID_LOW 2048
+
+__device__ static inline void rj_new_chunk(const RJSide &s, const RJParams &pr, RJP1Smem *sm, uint32_t p)
+{
+	const uint32_t old = sm->chunk[p];
+	uint32_t cid = rj_smem_inc(&sm->local_next);
+	if (cid >= sm->local_end)
+		cid = atomicAdd(s.pool_next, 1u); // reserve ran dry inside one round (extreme skew)
 	if (cid >= s.pool_chunks) {
 		atomicOr(pr.error_flag, RJ_ERR_POOL);
-		return RJ_NONE;
+		return;
 	}
 	if (old != RJ_NONE)
 		s.chunk_entries[old >> 5] = RJ_CHUNK; // a chunk is only replaced when all its sectors are written
 	s.chunk_part[cid] = (uint16_t)p;
-	atomicAdd(&s.dir_cnt[p], 1u);
+	rj_global_red_inc(&s.dir_cnt[p]);
 	sm->chunk[p] = cid << 5;
-	return cid;
+}
+
+__device__ static inline void rj_refill_ids(const RJSide &s, RJP1Smem *sm)
+{
+	// thread 0 only, during the insert phase (no flush lane is allocating then)
+	if (sm->local_end - min(sm->local_next, sm->local_end) < RJ_ID_LOW) {
+		const uint32_t base = atomicAdd(s.pool_next, (uint32_t)RJ_ID_BATCH);
+		sm->local_next = base;
+		sm->local_end = base + RJ_ID_BATCH; // ids left in the old range stay unused (chunk_part 0xffff)
+	}
+}
+
+__device__ static inline void rj_park(RJP1Smem *sm, const RJParams &pr, uint32_t item, int par)
+{
+	// staging row full until this round's flush: the key waits one round
+	const uint32_t o = rj_smem_inc(&sm->ovf_count[par]);
+	if (o < RJ_OVF_CAP)
+		sm->ovf[par][o] = item;
+	else
+		atomicOr(pr.error_flag, RJ_ERR_SKEW);
 }
 
 __device__ static inline void rj_insert(RJP1Smem *sm, const RJParams &pr, uint32_t item, int par)
 {
-	uint32_t p = item >> 16;
-	uint32_t pos = atomicAdd(&sm->fill[p], 1u);
+	const uint32_t p = item >> 16;
+	const uint32_t pos = rj_smem_inc(&sm->fill[p]);
 	if (pos < RJ_CAP) {
 		sm->stage[p * RJ_CAP + pos] = (uint16_t)item;
 		if (pos == RJ_FLUSH - 1)
-			sm->worklist[par][atomicAdd(&sm->wl_count[par], 1u)] = (uint16_t)p;
+			sm->worklist[par][rj_smem_inc(&sm->wl_count[par])] = (uint16_t)p;
 	} else {
-		// staging row full until this round's flush: park the key for one round
-		uint32_t o = atomicAdd(&sm->ovf_count[par], 1u);
-		if (o < RJ_OVF_CAP)
-			sm->ovf[par][o] = item;
-		else
-			atomicOr(pr.error_flag, RJ_ERR_SKEW);
+		rj_park(sm, pr, item, par);
 	}
 }
 
-template <bool HAS_PRESENT>
-__device__ static inline void rj_round(const RJSide &s, const RJParams &pr, RJP1Smem *sm, const int4 *buf, uint64_t tile,
-		bool have_keys, int par)
+__device__ static inline void rj_round_begin(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par)
 {
 	const int tid = threadIdx.x;
-
+	if (tid == 0)
+		rj_refill_ids(s, sm);
 	// keys parked by the previous round go first (their rows were flushed since)
-	uint32_t novf = min(sm->ovf_count[par ^ 1], (uint32_t)RJ_OVF_CAP);
+	const uint32_t novf = min(sm->ovf_count[par ^ 1], (uint32_t)RJ_OVF_CAP);
 	for (uint32_t i = tid; i < novf; i += RJ_P1_THREADS)
 		rj_insert(sm, pr, sm->ovf[par ^ 1][i], par);
+}
 
-	if (have_keys) {
+// Hot loop of pass 1 for the common case: a complete tile of a column without NULLs/tombstones whose
+// [min, max] lies inside the partitioned key range, so no per-key validity test is needed and all arithmetic
+// is 32-bit.  Per key: subtract, shift, one shared-memory atomic (slot), one 2-byte shared store; the rare
+// events (row completed a sector -> queue it; row full -> park the key) are predicated, never branched on.
+__device__ static inline void rj_insert_tile_fast(const RJParams &pr, RJP1Smem *sm, const int4 *buf, int par)
+{
+	constexpr int NK = RJ_P1_LOADS * 2;
+	uint32_t d[NK], pos[NK], widx[NK];
+	const uint32_t kmin_lo = (uint32_t)(unsigned long long)pr.kmin;
+#pragma unroll
+	for (int j = 0; j < RJ_P1_LOADS; j++) {
+		d[2 * j] = (uint32_t)buf[j].x - kmin_lo;     // low words: key - kmin < 2^32 is guaranteed by the caller
+		d[2 * j + 1] = (uint32_t)buf[j].z - kmin_lo;
+	}
+#pragma unroll
+	for (int k = 0; k < NK; k++)
+		pos[k] = rj_smem_inc(&sm->fill[d[k] >> pr.shift]);
+#pragma unroll
+	for (int k = 0; k < NK; k++) {
+		widx[k] = 0;
+		if (pos[k] == RJ_FLUSH - 1)
+			widx[k] = rj_smem_inc(&sm->wl_count[par]);
+	}
+	uint32_t park_mask = 0;
+#pragma unroll
+	for (int k = 0; k < NK; k++) {
+		const uint32_t p = d[k] >> pr.shift;
+		if (pos[k] < RJ_CAP)
+			sm->stage[p * RJ_CAP + pos[k]] = (uint16_t)(d[k] & pr.mask);
+		if (pos[k] == RJ_FLUSH - 1)
+			sm->worklist[par][widx[k]] = (uint16_t)p;
+		park_mask |= pos[k] >= RJ_CAP ? (1u << k) : 0u;
+	}
+	if (park_mask) {
+#pragma unroll
+		for (int k = 0; k < NK; k++)
+			if (park_mask & (1u << k))
+				rj_park(sm, pr, ((d[k] >> pr.shift) << 16) | (d[k] & pr.mask), par);
+	}
+}
+
+// generic insert phase.  FULL: every row of the tile exists (no bounds checks)
+template <bool HAS_PRESENT, bool FULL>
+__device__ static inline void rj_insert_tile(const RJSide &s, const RJParams &pr, RJP1Smem *sm, const int4 *buf, uint64_t tile,
+		int par)
+{
+	const int tid = threadIdx.x;
+	{
 		const uint64_t base_pair = tile * (RJ_P1_TILE / 2);
 		uint32_t item[RJ_P1_LOADS * 2], pos[RJ_P1_LOADS * 2];
 #pragma unroll
 		for (int j = 0; j < RJ_P1_LOADS; j++) {
 			const uint64_t pi = base_pair + (uint64_t)j * RJ_P1_THREADS + tid;
-			uint32_t pw = 0xffffffffu;
-			if (HAS_PRESENT)
-				pw = (pi * 2 < s.n) ? (s.present[pi >> 4] >> ((pi & 15) * 2)) : 0u;
 			const unsigned long long k0 = ((unsigned long long)(unsigned)buf[j].y << 32) | (unsigned)buf[j].x;
 			const unsigned long long k1 = ((unsigned long long)(unsigned)buf[j].w << 32) | (unsigned)buf[j].z;
 			const unsigned long long d0 = k0 - (unsigned long long)pr.kmin, d1 = k1 - (unsigned long long)pr.kmin;
-			bool ok0 = d0 < pr.range && pi * 2 < s.n, ok1 = d1 < pr.range && pi * 2 + 1 < s.n;
+			bool ok0 = d0 < pr.range, ok1 = d1 < pr.range;
+			if (!FULL) {
+				ok0 = ok0 && pi * 2 < s.n;
+				ok1 = ok1 && pi * 2 + 1 < s.n;
+			}
 			if (HAS_PRESENT) {
+				const uint32_t pw = (FULL || pi * 2 < s.n) ? (s.present[pi >> 4] >> ((pi & 15) * 2)) : 0u;
 				ok0 = ok0 && (pw & 1u);
 				ok1 = ok1 && (pw & 2u);
 			}
@@ -146,24 +233,35 @@ __device__ static inline void rj_round(const RJSide &s, const RJParams &pr, RJP1
 		// all slot requests of this thread are issued back to back (independent shared-memory atomics) ...
 #pragma unroll
 		for (int k = 0; k < RJ_P1_LOADS * 2; k++)
-			pos[k] = item[k] != RJ_NONE ? atomicAdd(&sm->fill[item[k] >> 16], 1u) : RJ_NONE;
-		// ... and only then consumed
+			pos[k] = item[k] != RJ_NONE ? rj_smem_inc(&sm->fill[item[k] >> 16]) : RJ_NONE;
+		// ... then consumed; the two rare events (row just completed a sector / row full) are only recorded here
+		uint32_t queue_mask = 0, park_mask = 0;
 #pragma unroll
 		for (int k = 0; k < RJ_P1_LOADS * 2; k++) {
-			if (pos[k] < RJ_CAP) {
-				const uint32_t p = item[k] >> 16;
-				sm->stage[p * RJ_CAP + pos[k]] = (uint16_t)item[k];
-				if (pos[k] == RJ_FLUSH - 1)
-					sm->worklist[par][atomicAdd(&sm->wl_count[par], 1u)] = (uint16_t)p;
-			} else if (item[k] != RJ_NONE) {
-				const uint32_t o = atomicAdd(&sm->ovf_count[par], 1u);
-				if (o < RJ_OVF_CAP)
-					sm->ovf[par][o] = item[k];
-				else
-					atomicOr(pr.error_flag, RJ_ERR_SKEW);
-			}
+			if (pos[k] < RJ_CAP)
+				sm->stage[(item[k] >> 16) * RJ_CAP + pos[k]] = (uint16_t)item[k];
+			queue_mask |= (pos[k] == RJ_FLUSH - 1) ? (1u << k) : 0u;
+			park_mask |= (pos[k] >= RJ_CAP && item[k] != RJ_NONE) ? (1u << k) : 0u;
+		}
+		if (queue_mask) {
+#pragma unroll
+			for (int k = 0; k < RJ_P1_LOADS * 2; k++)
+				if (queue_mask & (1u << k))
+					sm->worklist[par][rj_smem_inc(&sm->wl_count[par])] = (uint16_t)(item[k] >> 16);
+		}
+		if (park_mask) {
+#pragma unroll
+			for (int k = 0; k < RJ_P1_LOADS * 2; k++)
+				if (park_mask & (1u << k))
+					rj_park(sm, pr, item[k], par);
 		}
 	}
+}
+
+// barrier, flush the queued rows, barrier
+__device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par)
+{
+	const int tid = threadIdx.x;
 	__syncthreads();
 
 	const uint32_t nwl = sm->wl_count[par];
@@ -225,58 +323,10 @@ __device__ static inline void rj_load_tile(const RJSide &s, uint64_t tile, int4 
 	}
 }
 
-// Pass 1.  One persistent 1024-thread CTA per SM.  Keys are streamed with 128-bit loads, double-buffered in
-// registers (ping-pong, no copies).  Each key costs one shared-memory atomic (slot in its partition's staging
-// row) and one 2-byte shared store.  The thread that fills slot 16 of a row queues the partition; after the
-// round's barrier one lane per queued partition writes 16 remainders as one aligned 32-byte sector into the
-// CTA's current 512-byte chunk of that partition: DRAM only sees full-sector writes, 2 bytes per key.
-template <bool HAS_PRESENT>
-__global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition(RJSide s, RJParams pr)
+// every partition's partial sector goes out, chunk entry counts are finalised
+__device__ static inline void rj_drain(const RJSide &s, const RJParams &pr, RJP1Smem *sm)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	RJP1Smem *sm = reinterpret_cast<RJP1Smem*>(smem_raw);
-	const int tid = threadIdx.x;
-
-	for (int p = tid; p < RJ_MAX_PART; p += RJ_P1_THREADS) {
-		sm->fill[p] = 0;
-		sm->chunk[p] = RJ_NONE;
-	}
-	if (tid < 2) {
-		sm->wl_count[tid] = 0;
-		sm->ovf_count[tid] = 0;
-	}
-	__syncthreads();
-
-	const uint64_t ntiles = (s.n + RJ_P1_TILE - 1) / RJ_P1_TILE;
-	int4 buf_a[RJ_P1_LOADS], buf_b[RJ_P1_LOADS];
-	uint64_t tile = blockIdx.x;
-	int par = 0;
-	if (tile < ntiles)
-		rj_load_tile<HAS_PRESENT>(s, tile, buf_a);
-	while (tile < ntiles) {
-		uint64_t next = tile + gridDim.x;
-		if (next < ntiles)
-			rj_load_tile<HAS_PRESENT>(s, next, buf_b);
-		rj_round<HAS_PRESENT>(s, pr, sm, buf_a, tile, true, par);
-		par ^= 1;
-		tile = next;
-		if (tile >= ntiles)
-			break;
-		next = tile + gridDim.x;
-		if (next < ntiles)
-			rj_load_tile<HAS_PRESENT>(s, next, buf_a);
-		rj_round<HAS_PRESENT>(s, pr, sm, buf_b, tile, true, par);
-		par ^= 1;
-		tile = next;
-	}
-	// keys still parked by the last round(s)
-	while (sm->ovf_count[par ^ 1] != 0) { // block-uniform: written before the last barrier
-		rj_round<HAS_PRESENT>(s, pr, sm, buf_a, 0, false, par);
-		par ^= 1;
-	}
-
-	// drain: every partition's partial sector goes out, chunk entry counts are finalised
-	for (int p = tid; p < pr.nparts; p += RJ_P1_THREADS) {
+	for (int p = threadIdx.x; p < pr.nparts; p += RJ_P1_THREADS) {
 		const uint32_t f = min(sm->fill[p], (uint32_t)RJ_CAP);
 		uint32_t ch = sm->chunk[p];
 		if (f > 0) {
@@ -294,6 +344,135 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition(RJSide s, 
 			s.chunk_entries[ch >> 5] = (uint16_t)((ch & 31u) * RJ_FLUSH);
 		}
 	}
+}
+
+__device__ static inline void rj_smem_init(RJP1Smem *sm)
+{
+	const int tid = threadIdx.x;
+	for (int p = tid; p < RJ_MAX_PART; p += RJ_P1_THREADS) {
+		sm->fill[p] = 0;
+		sm->chunk[p] = RJ_NONE;
+	}
+	if (tid < 2) {
+		sm->ovf_count[tid] = 0;
+		sm->wl_count[tid] = 0;
+	}
+	if (tid == 0)
+		sm->local_next = sm->local_end = 0;
+	__syncthreads();
+}
+
+// Pass 1, lean variant: column without NULLs/tombstones whose [min, max] lies inside the partitioned range.
+// Complete tiles run the branch-free 32-bit hot loop; the ragged tail (< one tile) is inserted key by key by CTA 0.
+__global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSide s, RJParams pr)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	RJP1Smem *sm = reinterpret_cast<RJP1Smem*>(smem_raw);
+	rj_smem_init(sm);
+
+	const uint64_t nfull = s.n / RJ_P1_TILE;
+	const int4 *src = reinterpret_cast<const int4*>(s.keys);
+	int4 buf_a[RJ_P1_LOADS], buf_b[RJ_P1_LOADS];
+	int par = 0;
+	auto load = [&](uint64_t tile, int4 *dst) {
+		const uint64_t pf_first = (tile + 2ull * gridDim.x) * RJ_P1_TILE + (uint64_t)threadIdx.x * 16;
+		if (threadIdx.x < RJ_P1_TILE / 16 && pf_first + 16 <= s.n)
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(s.keys + pf_first));
+		const int4 *t = src + tile * (RJ_P1_TILE / 2) + threadIdx.x;
+#pragma unroll
+		for (int j = 0; j < RJ_P1_LOADS; j++)
+			dst[j] = mdb_ldg_stream(t + j * RJ_P1_THREADS);
+	};
+	auto round = [&](const int4 *buf) {
+		rj_round_begin(s, pr, sm, par);
+		rj_insert_tile_fast(pr, sm, buf, par);
+		rj_round_end(s, pr, sm, par);
+		par ^= 1;
+	};
+	uint64_t tile = blockIdx.x;
+	if (tile < nfull)
+		load(tile, buf_a);
+	while (tile < nfull) {
+		uint64_t next = tile + gridDim.x;
+		if (next < nfull)
+			load(next, buf_b);
+		round(buf_a);
+		tile = next;
+		if (tile >= nfull)
+			break;
+		next = tile + gridDim.x;
+		if (next < nfull)
+			load(next, buf_a);
+		round(buf_b);
+		tile = next;
+	}
+	// ragged tail and parked keys
+	bool tail_done = blockIdx.x != 0 || nfull * RJ_P1_TILE == s.n;
+	while (!tail_done || sm->ovf_count[par ^ 1] != 0) {
+		rj_round_begin(s, pr, sm, par);
+		if (!tail_done) {
+			for (uint64_t r = nfull * RJ_P1_TILE + threadIdx.x; r < s.n; r += RJ_P1_THREADS) {
+				const uint32_t d = (uint32_t)(unsigned long long)s.keys[r] - (uint32_t)(unsigned long long)pr.kmin;
+				rj_insert(sm, pr, ((d >> pr.shift) << 16) | (d & pr.mask), par);
+			}
+			tail_done = true;
+		}
+		rj_round_end(s, pr, sm, par);
+		par ^= 1;
+	}
+	rj_drain(s, pr, sm);
+}
+
+// Pass 1.  One persistent 1024-thread CTA per SM.  Keys are streamed with 128-bit loads, double-buffered in
+// registers (ping-pong, no copies).  Each key costs one shared-memory atomic (slot in its partition's staging
+// row) and one 2-byte shared store.  The thread that fills slot 16 of a row queues the partition; after the
+// round's barrier one lane per queued partition writes 16 remainders as one aligned 32-byte sector into the
+// CTA's current 512-byte chunk of that partition: DRAM only sees full-sector writes, 2 bytes per key.
+template <bool HAS_PRESENT>
+__global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition(RJSide s, RJParams pr)
+{
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	RJP1Smem *sm = reinterpret_cast<RJP1Smem*>(smem_raw);
+	const int tid = threadIdx.x;
+
+	rj_smem_init(sm);
+
+	const uint64_t ntiles = (s.n + RJ_P1_TILE - 1) / RJ_P1_TILE;
+	const uint64_t nfull = s.n / RJ_P1_TILE; // tiles [0, nfull) are complete
+	int4 buf_a[RJ_P1_LOADS], buf_b[RJ_P1_LOADS];
+	uint64_t tile = blockIdx.x;
+	int par = 0;
+	if (tile < ntiles)
+		rj_load_tile<HAS_PRESENT>(s, tile, buf_a);
+	auto round = [&](const int4 *buf, uint64_t t) {
+		rj_round_begin(s, pr, sm, par);
+		if (t < nfull) {
+			rj_insert_tile<HAS_PRESENT, true>(s, pr, sm, buf, t, par);
+		} else if (t < ntiles) {
+			rj_insert_tile<HAS_PRESENT, false>(s, pr, sm, buf, t, par);
+		}
+		rj_round_end(s, pr, sm, par);
+		par ^= 1;
+	};
+	while (tile < ntiles) {
+		uint64_t next = tile + gridDim.x;
+		if (next < ntiles)
+			rj_load_tile<HAS_PRESENT>(s, next, buf_b);
+		round(buf_a, tile);
+		tile = next;
+		if (tile >= ntiles)
+			break;
+		next = tile + gridDim.x;
+		if (next < ntiles)
+			rj_load_tile<HAS_PRESENT>(s, next, buf_a);
+		round(buf_b, tile);
+		tile = next;
+	}
+	// keys still parked by the last round(s)
+	while (sm->ovf_count[par ^ 1] != 0) // block-uniform: written before the last barrier
+		round(buf_a, ntiles);
+
+	rj_drain(s, pr, sm);
 }
 
 // exclusive scan of the per-partition chunk counts (single block, nparts <= 4096)
@@ -341,7 +520,9 @@ static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_ta
 	s->keys = t->cols[col].data;
 	s->present = col_all_present(t, col) ? nullptr : t->cols[col].present;
 	s->n = t->n_slots;
-	uint64_t chunks = t->n_slots / RJ_CHUNK + (uint64_t)grid * RJ_MAX_PART + 1024;
+	// data chunks + one partial chunk per (CTA, partition) + ids abandoned at refills + one reserve per CTA
+	uint64_t chunks = t->n_slots / RJ_CHUNK + (uint64_t)grid * RJ_MAX_PART;
+	chunks += chunks / 2 + (uint64_t)grid * RJ_ID_BATCH + 1024;
 	if (chunks >= (1ull << 27))
 		return MDBCU_EUNSUPPORTED;
 	s->pool_chunks = (uint32_t)chunks;
@@ -354,6 +535,7 @@ static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_ta
 	MDB_TRY(tmp.alloc(&s->dir_off, RJ_MAX_PART + 2));
 	MDB_TRY(tmp.alloc(&s->dir, chunks));
 	CUDA_TRY(ctx, cudaMemsetAsync(s->pool_next, 0, sizeof(uint32_t), ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(s->chunk_part, 0xff, chunks * sizeof(uint16_t), ctx->stream)); // 0xffff = never allocated
 	CUDA_TRY(ctx, cudaMemsetAsync(s->dir_cnt, 0, (RJ_MAX_PART + 1) * sizeof(uint32_t), ctx->stream));
 	CUDA_TRY(ctx, cudaMemsetAsync(s->dir_fill, 0, (RJ_MAX_PART + 1) * sizeof(uint32_t), ctx->stream));
 	return MDBCU_OK;
@@ -363,6 +545,8 @@ static void launch_partition(mdbcu_ctx *ctx, int grid, const RJSide &s, const RJ
 {
 	if (s.present)
 		MDB_LAUNCH(ctx, k_radix_partition<true>, grid, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
+	else if (s.all_in_range && pr.range <= 0xffffffffull)
+		MDB_LAUNCH(ctx, k_radix_partition_fast, grid, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
 	else
 		MDB_LAUNCH(ctx, k_radix_partition<false>, grid, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
 }
@@ -407,6 +591,17 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	unsigned long long range = (unsigned long long)kmax - (unsigned long long)kmin + 1ull;
 	if (range == 0 || range > ((unsigned long long)RJ_MAX_PART << RJ_MAX_SHIFT) || range < 4096)
 		return MDBCU_EUNSUPPORTED;
+	{
+		// when the two columns cover almost the same interval, partition over the UNION of the intervals instead:
+		// every key of both sides is then in range and the hot loop needs no per-key range test
+		long long umin = std::min(ca.imin, cb.imin), umax = std::max(ca.imax, cb.imax);
+		unsigned long long urange = (unsigned long long)umax - (unsigned long long)umin + 1ull;
+		if (urange != 0 && urange <= ((unsigned long long)RJ_MAX_PART << RJ_MAX_SHIFT) && urange <= range + range / 4) {
+			kmin = umin;
+			kmax = umax;
+			range = urange;
+		}
+	}
 	int bits = 0;
 	while ((1ull << bits) < range)
 		bits++;
@@ -421,6 +616,8 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	RJParams pr;
 	MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1));
 	MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1));
+	sa.all_in_range = ca.imin >= kmin && ca.imax <= kmax;
+	sb.all_in_range = cb.imin >= kmin && cb.imax <= kmax;
 	pr.kmin = kmin;
 	pr.range = range;
 	pr.shift = shift;
@@ -455,6 +652,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	if (!attr_done) {
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
+		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 2 * RJ_DESC_CAP * (int)sizeof(RJDesc)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 + 2 * RJ_DESC_CAP * (int)sizeof(RJDesc)));
 		attr_done = true;

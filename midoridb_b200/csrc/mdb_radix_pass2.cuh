@@ -20,6 +20,8 @@ __global__ void k_radix_dir_fill(RJSide s)
 	uint32_t nchunks = min(*s.pool_next, s.pool_chunks);
 	for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += gridDim.x * blockDim.x) {
 		uint32_t p = s.chunk_part[c];
+		if (p == 0xffffu)
+			continue; // id reserved by a CTA but never used
 		uint32_t pos = atomicAdd(&s.dir_fill[p], 1u);
 		RJDesc d;
 		d.cid = c;
