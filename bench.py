@@ -242,6 +242,9 @@ def main():
     # strong scaling: rank r holds rows [r*n/P, (r+1)*n/P) of the same global tables (counter-based generator)
     ta.generate(n_local, [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=n_total - 1, seed=1)], row_offset=rank * n_local)
     tb.generate(n_local, [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=n_total - 1, seed=2)], row_offset=rank * n_local)
+    if world > 1:
+        ta.sync_stats()  # collective: global key range, so every rank partitions identically
+        tb.sync_stats()
     plan = capi.make_plan([ta, tb], joins=[((0, 0), (1, 0))], group=[(0, 0)],
                           out=[(capi.OUT_COLUMN, 0, 0), (capi.OUT_COUNT_STAR,)], flags=flags)
 
@@ -346,6 +349,9 @@ def run_e2e(args, be, dist, ta, tb, n_local, rows_per_step, flags):
         ea, eb = be.create_table("A", [I]), be.create_table("B", [I])
         ea.append_pages(pa)
         eb.append_pages(pb)
+        if dist.world > 1:
+            ea.sync_stats()
+            eb.sync_stats()
         res = be.select(capi.make_plan([ea, eb], joins=[((0, 0), (1, 0))], group=[(0, 0)],
                                        out=[(capi.OUT_COLUMN, 0, 0), (capi.OUT_COUNT_STAR,)], flags=flags))
         groups = res.nrows

@@ -225,6 +225,7 @@ struct mdbcu_stats {
 	int32_t _pad;
 	double dominant_ms; /* device time of the dominant kernel(s) of the path (roofline numerator's denominator) */
 	uint64_t dominant_bytes; /* algorithmic bytes attributed to the dominant kernel(s) */
+	uint64_t exchange_bytes; /* bytes this rank sent to OTHER ranks over NVLink in the last select */
 };
 #define MDBCU_PATH_GENERAL        0
 #define MDBCU_PATH_SCAN_AGG       1 /* fused filter + aggregate scan (no join, no GROUP BY) */
@@ -246,6 +247,10 @@ int mdbcu_event_elapsed_ms(mdbcu_ctx *ctx, int slot_start, int slot_stop, double
 int mdbcu_comm_unique_id(mdbcu_ctx *ctx, void *id128);
 int mdbcu_comm_init(mdbcu_ctx *ctx, int rank, int world, const void *id128);
 int mdbcu_comm_world(mdbcu_ctx *ctx, int *rank, int *world);
+/* COLLECTIVE (every rank calls it for its shard of the same table): exchanges the zone-map statistics
+ * (min / max per integer column) so every rank partitions by the same global key range.  Call after loading
+ * or changing a sharded table, before a MDBCU_PLAN_DISTRIBUTED select. */
+int mdbcu_table_sync_stats(mdbcu_table *t);
 
 const char *mdbcu_version(void);
 

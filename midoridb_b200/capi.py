@@ -33,7 +33,7 @@ EXPORTED_SYMBOLS = [
     "mdbcu_select",
     "mdbcu_result_rows", "mdbcu_result_cols", "mdbcu_result_col_type", "mdbcu_result_fetch_columns",
     "mdbcu_result_page_count", "mdbcu_result_row_size", "mdbcu_result_fetch_pages", "mdbcu_result_free",
-    "mdbcu_get_stats", "mdbcu_event_record", "mdbcu_event_elapsed_ms", "mdbcu_comm_unique_id", "mdbcu_comm_init", "mdbcu_comm_world", "mdbcu_version",
+    "mdbcu_get_stats", "mdbcu_event_record", "mdbcu_event_elapsed_ms", "mdbcu_comm_unique_id", "mdbcu_comm_init", "mdbcu_comm_world", "mdbcu_table_sync_stats", "mdbcu_version",
 ]
 
 
@@ -72,7 +72,7 @@ class Stats(C.Structure):
     _fields_ = [("total_ms", C.c_double), ("phase_ms", C.c_double * 8), ("kernel_launches", C.c_uint64),
                 ("total_kernel_launches", C.c_uint64), ("input_rows", C.c_uint64), ("result_rows", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("path", C.c_int32), ("_pad", C.c_int32),
-                ("dominant_ms", C.c_double), ("dominant_bytes", C.c_uint64)]
+                ("dominant_ms", C.c_double), ("dominant_bytes", C.c_uint64), ("exchange_bytes", C.c_uint64)]
 
 
 class MdbError(RuntimeError):
@@ -137,6 +137,7 @@ def load_library():
     L.mdbcu_comm_unique_id.argtypes = [vp, vp]
     L.mdbcu_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.mdbcu_comm_world.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.mdbcu_table_sync_stats.argtypes = [vp]
     L.mdbcu_version.restype = C.c_char_p
     _lib = L
     return L
@@ -248,6 +249,10 @@ class Table:
     def generate(self, n_rows, specs, row_offset=0):
         arr = (GenSpec * len(specs))(*specs)
         self._check(self.backend.L.mdbcu_table_generate(self.handle, n_rows, row_offset, arr))
+
+    def sync_stats(self):
+        """collective: make the column statistics global across the ranks' shards"""
+        self._check(self.backend.L.mdbcu_table_sync_stats(self.handle))
 
     @property
     def slots(self):

@@ -138,3 +138,41 @@ int mdb_comm_allgather_u64(mdbcu_ctx *ctx, const uint64_t *send, uint64_t *recv,
 	NCCL_TRY(ctx, g_nccl.AllGather(send, recv, count, NCCL_UINT64, (ncclComm_t)ctx->nccl_comm, ctx->stream));
 	return MDBCU_OK;
 }
+
+// ---- thin wrappers used by the distributed radix join (mdb_radix_dist.cuh)
+
+int mdb_comm_allgather_bytes(mdbcu_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank)
+{
+	if (!ctx->nccl_comm)
+		return mdb_fail(ctx, MDBCU_EERROR, "distributed plan without mdbcu_comm_init");
+	NCCL_TRY(ctx, g_nccl.AllGather(send, recv, bytes_per_rank, NCCL_UINT8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+	return MDBCU_OK;
+}
+
+int mdb_comm_group_begin(mdbcu_ctx *ctx)
+{
+	if (!ctx->nccl_comm)
+		return mdb_fail(ctx, MDBCU_EERROR, "distributed plan without mdbcu_comm_init");
+	NCCL_TRY(ctx, g_nccl.GroupStart());
+	return MDBCU_OK;
+}
+
+int mdb_comm_group_end(mdbcu_ctx *ctx)
+{
+	NCCL_TRY(ctx, g_nccl.GroupEnd());
+	return MDBCU_OK;
+}
+
+int mdb_comm_send(mdbcu_ctx *ctx, const void *p, size_t bytes, int peer)
+{
+	if (bytes)
+		NCCL_TRY(ctx, g_nccl.Send(p, bytes, NCCL_UINT8, peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+	return MDBCU_OK;
+}
+
+int mdb_comm_recv(mdbcu_ctx *ctx, void *p, size_t bytes, int peer)
+{
+	if (bytes)
+		NCCL_TRY(ctx, g_nccl.Recv(p, bytes, NCCL_UINT8, peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+	return MDBCU_OK;
+}

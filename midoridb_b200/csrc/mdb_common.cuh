@@ -42,6 +42,8 @@ struct DevColumn {
 	bool has_nulls = false;
 	bool stats_ok = false;     // imin/imax valid (conservative bounds over present cells)
 	int64_t imin = 0, imax = 0;
+	bool gstats_ok = false;    // gmin/gmax = bounds over ALL ranks' shards (mdbcu_table_sync_stats)
+	int64_t gmin = 0, gmax = 0;
 };
 
 struct mdbcu_table {
@@ -229,6 +231,11 @@ int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result 
 int mdb_comm_alltoallv_bytes(mdbcu_ctx *ctx, const void *send, const uint64_t *send_off, void *recv,
 		const uint64_t *recv_off);
 void mdb_comm_destroy(mdbcu_ctx *ctx);
+int mdb_comm_allgather_bytes(mdbcu_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
+int mdb_comm_group_begin(mdbcu_ctx *ctx);
+int mdb_comm_group_end(mdbcu_ctx *ctx);
+int mdb_comm_send(mdbcu_ctx *ctx, const void *p, size_t bytes, int peer);
+int mdb_comm_recv(mdbcu_ctx *ctx, void *p, size_t bytes, int peer);
 int mdb_comm_allgather_u64(mdbcu_ctx *ctx, const uint64_t *send, uint64_t *recv, size_t count);
 
 // phase clock: events are only recorded while the query runs; one synchronise at the end

@@ -39,8 +39,9 @@ static bool col_all_present(const mdbcu_table *t, int col)
 	return t->all_live && !t->cols[col].has_nulls;
 }
 
+// one run of <= RJ_CHUNK remainders: 16-byte aligned offset into a remainder buffer, valid entries
 struct RJDesc {
-	uint32_t cid;
+	uint32_t off16; // in units of 16 bytes (8 remainders)
 	uint32_t ne;
 };
 
@@ -66,6 +67,7 @@ struct RJParams {
 	int shift;                 // remainder bits
 	uint32_t mask;             // (1 << shift) - 1
 	int nparts;
+	int part_first, part_end;  // pass 2 handles partitions [part_first, part_end) (all of them on one GPU)
 	uint32_t *error_flag;
 };
 
@@ -513,6 +515,7 @@ __global__ void k_radix_dir_scan(RJSide s, int nparts)
 }
 
 #include "mdb_radix_pass2.cuh"
+#include "mdb_radix_dist.cuh"
 
 static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_table *t, int col, int grid)
 {
@@ -556,18 +559,28 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	if (plan->n_tables != 2 || plan->n_joins != 1 || plan->joins[0].cross || plan->n_pred != 0 || plan->n_group != 1 ||
 			plan->n_out < 1 || plan->n_out > 4)
 		return MDBCU_EUNSUPPORTED;
-	if (plan->flags & MDBCU_PLAN_DISTRIBUTED)
-		return MDBCU_EUNSUPPORTED;
+	const bool dist = (plan->flags & MDBCU_PLAN_DISTRIBUTED) != 0;
+	if (dist && !ctx->nccl_comm)
+		return mdb_fail(ctx, MDBCU_EERROR, "MDBCU_PLAN_DISTRIBUTED needs mdbcu_comm_init first");
 	const mdbcu_join &jn = plan->joins[0];
 	if (jn.left.tbl != 0 || jn.right.tbl != 1)
 		return MDBCU_EUNSUPPORTED;
 	const mdbcu_table *ta = plan->tables[0], *tb = plan->tables[1];
 	if (jn.left.col < 0 || jn.left.col >= ta->ncols || jn.right.col < 0 || jn.right.col >= tb->ncols)
 		return MDBCU_EUNSUPPORTED;
-	const DevColumn &ca = ta->cols[jn.left.col], &cb = tb->cols[jn.right.col];
+	DevColumn ca = ta->cols[jn.left.col], cb = tb->cols[jn.right.col]; // copies: distributed plans overwrite the bounds
 	auto intlike = [](int type) { return type == MDBCU_CT_INTEGER || type == MDBCU_CT_DATE || type == MDBCU_CT_DATETIME; };
 	if (!intlike(ca.type) || !intlike(cb.type) || !ca.stats_ok || !cb.stats_ok)
 		return MDBCU_EUNSUPPORTED;
+	if (dist) {
+		// every rank must take the same decisions: use the bounds over ALL shards
+		if (!ca.gstats_ok || !cb.gstats_ok)
+			return mdb_fail(ctx, MDBCU_EERROR, "distributed plan: call mdbcu_table_sync_stats on every sharded table first");
+		ca.imin = ca.gmin;
+		ca.imax = ca.gmax;
+		cb.imin = cb.gmin;
+		cb.imax = cb.gmax;
+	}
 	auto is_key = [&](const mdbcu_colref &r) {
 		return (r.tbl == 0 && r.col == jn.left.col) || (r.tbl == 1 && r.col == jn.right.col);
 	};
@@ -579,7 +592,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		if (plan->out[o].kind != MDBCU_OUT_COLUMN || !is_key(plan->out[o].ref))
 			return MDBCU_EUNSUPPORTED;
 	}
-	if (ta->n_slots + tb->n_slots < (1ull << 20))
+	if (!dist && ta->n_slots + tb->n_slots < (1ull << 20))
 		return MDBCU_EUNSUPPORTED; // small inputs: general operators (they also return the reference's row order)
 
 	// only keys inside both columns' [min, max] (zone-map statistics kept by the mirror) can ever match
@@ -623,6 +636,12 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	pr.shift = shift;
 	pr.mask = (1u << shift) - 1u;
 	pr.nparts = nparts;
+	pr.part_first = 0;
+	pr.part_end = nparts;
+	if (dist) {
+		pr.part_first = (int)((uint64_t)ctx->rank * nparts / ctx->world);
+		pr.part_end = (int)((uint64_t)(ctx->rank + 1) * nparts / ctx->world);
+	}
 	uint32_t *d_flags; // [0] error flags, [1] partition counter
 	unsigned long long *d_cursor;
 	MDB_TRY(tmp.alloc(&d_flags, 2));
@@ -631,7 +650,10 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
 	pr.error_flag = d_flags;
 
-	uint64_t cap_groups = std::min<uint64_t>(std::min<uint64_t>(ta->n_slots, tb->n_slots), range);
+	// upper bound of groups this rank can emit: one per key of the partitions it owns
+	uint64_t cap_groups = std::min<uint64_t>((uint64_t)(pr.part_end - pr.part_first) << shift, range);
+	if (!dist)
+		cap_groups = std::min<uint64_t>(cap_groups, std::min<uint64_t>(ta->n_slots, tb->n_slots));
 	MDB_TRY(mdb_result_alloc(ctx, plan, res, 0, false));
 	RJOut out;
 	memset(&out, 0, sizeof(out));
@@ -666,6 +688,12 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	MDB_LAUNCH(ctx, k_radix_dir_scan, 1, 1024, 0, sb, nparts);
 	MDB_LAUNCH(ctx, k_radix_dir_fill, ctx->num_sms * 4, 256, 0, sa);
 	MDB_LAUNCH(ctx, k_radix_dir_fill, ctx->num_sms * 4, 256, 0, sb);
+	uint64_t exchanged = 0;
+	if (dist) {
+		clock.begin(6);
+		RJSide *both[2] = {&sa, &sb};
+		MDB_TRY(rj_exchange(ctx, tmp, &pr, both, &exchanged));
+	}
 	clock.begin(2);
 
 	// 4-bit counters (two CTAs per SM) when keys are mostly unique per side, 8-bit otherwise; a wrapped
@@ -677,7 +705,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	for (int attempt = try4 ? 0 : 1; attempt < 2; attempt++) {
 		const int bitsw = attempt == 0 ? 4 : 8;
 		const size_t smem2 = 2 * (size_t)std::max<uint64_t>(1, D * bitsw / 32) * sizeof(uint32_t) + 2 * RJ_DESC_CAP * sizeof(RJDesc);
-		const int grid2 = std::min(nparts, ctx->num_sms * (bitsw == 4 ? 2 : 1));
+		const int grid2 = std::max(1, std::min(pr.part_end - pr.part_first, ctx->num_sms * (bitsw == 4 ? 2 : 1)));
 		if (bitsw == 4)
 			MDB_LAUNCH(ctx, (k_radix_joincount<4, 512>), grid2, 512, smem2, sa, sb, pr, out, d_flags + 1);
 		else
@@ -697,9 +725,14 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
 	}
 	clock.finish();
-	if (flags || ngroups > cap_groups)
+	if (flags || ngroups > cap_groups) {
+		if (dist)
+			return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "distributed radix join: key multiplicity or skew beyond the counter width "
+					"(flags %u); the general operators are single-GPU only", flags);
 		return MDBCU_EUNSUPPORTED; // heavy duplicates / skew / pool exhaustion: the general operators redo the query
+	}
 	res->nrows = ngroups;
+	ctx->stats.exchange_bytes = exchanged;
 
 	ctx->stats.algorithmic_bytes = 8ull * (ta->n_slots + tb->n_slots) + 8ull * plan->n_out * ngroups;
 	ctx->stats.dominant_ms = ctx->stats.phase_ms[1] + ctx->stats.phase_ms[2];

@@ -24,7 +24,7 @@ __global__ void k_radix_dir_fill(RJSide s)
 			continue; // id reserved by a CTA but never used
 		uint32_t pos = atomicAdd(&s.dir_fill[p], 1u);
 		RJDesc d;
-		d.cid = c;
+		d.off16 = c * (RJ_CHUNK / 8);
 		d.ne = s.chunk_entries[c];
 		s.dir[s.dir_off[p] + pos] = d;
 	}
@@ -82,7 +82,7 @@ __device__ __forceinline__ uint32_t rj_histogram(const uint16_t *__restrict__ po
 				const RJDesc d = descs[c + u];
 				ne[u] = d.ne;
 				if ((uint32_t)lane * 8 < d.ne) // partially filled chunks: only touch the sectors that hold data
-					v[u] = mdb_ldg_stream(reinterpret_cast<const int4*>(pool + (size_t)d.cid * RJ_CHUNK) + lane);
+					v[u] = mdb_ldg_stream(reinterpret_cast<const int4*>(pool) + (size_t)d.off16 + lane);
 			}
 		}
 #pragma unroll
@@ -129,12 +129,12 @@ k_radix_joincount(RJSide a, RJSide b, RJParams pr, RJOut out, uint32_t *__restri
 
 	while (true) {
 		if (tid == 0) {
-			s_part = atomicAdd(part_counter, 1u);
+			s_part = (uint32_t)pr.part_first + atomicAdd(part_counter, 1u);
 			s_totA = s_totB = s_sumA = s_sumB = 0;
 		}
 		__syncthreads();
 		const uint32_t p = s_part;
-		if (p >= (uint32_t)pr.nparts)
+		if (p >= (uint32_t)pr.part_end) // this rank owns partitions [part_first, part_end)
 			break;
 
 		// ---- count both sides (descriptor batches of RJ_DESC_CAP chunks per side; one batch is the common case)

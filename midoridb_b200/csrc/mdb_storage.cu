@@ -939,6 +939,54 @@ int mdb_table_refresh_stats(mdbcu_table *t, int col)
 	return sync_stats(impl(t));
 }
 
+// collective: all-gather every rank's {min, max, has-data} per column and fold them into global bounds
+extern "C" int mdbcu_table_sync_stats(mdbcu_table *tt)
+{
+	if (!tt)
+		return MDBCU_EERROR;
+	TableImpl *t = impl(tt);
+	mdbcu_ctx *ctx = t->ctx;
+	cudaSetDevice(ctx->device);
+	const int W = ctx->world;
+	if (W == 1 && !ctx->nccl_comm) {
+		for (auto &c : t->cols) {
+			c.gstats_ok = c.stats_ok;
+			c.gmin = c.imin;
+			c.gmax = c.imax;
+		}
+		return MDBCU_OK;
+	}
+	const size_t per_rank = (size_t)3 * t->ncols;
+	std::vector<int64_t> mine(per_rank), all(per_rank * W);
+	for (int c = 0; c < t->ncols; c++) {
+		mine[3 * c] = t->cols[c].imin;
+		mine[3 * c + 1] = t->cols[c].imax;
+		mine[3 * c + 2] = t->cols[c].stats_ok ? 1 : 0;
+	}
+	DevTemp tmp(ctx);
+	int64_t *d_mine, *d_all;
+	MDB_TRY(tmp.alloc(&d_mine, per_rank));
+	MDB_TRY(tmp.alloc(&d_all, per_rank * W));
+	CUDA_TRY(ctx, cudaMemcpyAsync(d_mine, mine.data(), per_rank * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+	MDB_TRY(mdb_comm_allgather_bytes(ctx, d_mine, d_all, per_rank * sizeof(int64_t)));
+	CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), d_all, per_rank * W * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	for (int c = 0; c < t->ncols; c++) {
+		DevColumn &col = t->cols[c];
+		col.gstats_ok = true;
+		col.gmin = INT64_MAX;
+		col.gmax = INT64_MIN;
+		for (int r = 0; r < W; r++) {
+			const int64_t *p = &all[(size_t)r * per_rank + 3 * c];
+			if (!p[2])
+				col.gstats_ok = false;
+			col.gmin = std::min(col.gmin, p[0]);
+			col.gmax = std::max(col.gmax, p[1]);
+		}
+	}
+	return MDBCU_OK;
+}
+
 // ----------------------------------------------------------------------------------- inspection
 
 extern "C" uint64_t mdbcu_table_slots(const mdbcu_table *t)

@@ -36,7 +36,7 @@ def test_plan_struct_layout_matches_header():
     assert C.sizeof(capi.ColRef) == 8
     assert C.sizeof(capi.Join) == 24
     assert C.sizeof(capi.Out) == 12
-    assert C.sizeof(capi.Stats) == 8 + 64 + 8 * 5 + 8 + 8 + 8
+    assert C.sizeof(capi.Stats) == 8 + 64 + 8 * 5 + 8 + 8 + 8 + 8
 
 
 @pytest.mark.skipif(_has_gpu(), reason="only meaningful on a box without a GPU")
