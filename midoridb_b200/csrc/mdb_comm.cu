@@ -176,3 +176,90 @@ int mdb_comm_recv(mdbcu_ctx *ctx, void *p, size_t bytes, int peer)
 		NCCL_TRY(ctx, g_nccl.Recv(p, bytes, NCCL_UINT8, peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
 	return MDBCU_OK;
 }
+
+// ---- peer-mapped exchange arena: one cudaMalloc'd block per rank, mapped into every other rank's address
+// space with CUDA IPC, so a kernel can store straight into the owner GPU's memory over NVLink / NVSwitch.
+// COLLECTIVE: every rank calls it with the same size; the mapping is cached until a larger one is needed.
+
+static void arena_release(mdbcu_ctx *ctx)
+{
+	for (int r = 0; r < MDB_MAX_RANKS; r++) {
+		if (ctx->arena_peer[r] && r != ctx->rank)
+			cudaIpcCloseMemHandle(ctx->arena_peer[r]);
+		ctx->arena_peer[r] = nullptr;
+	}
+	if (ctx->arena_local)
+		cudaFree(ctx->arena_local);
+	ctx->arena_local = nullptr;
+	ctx->arena_bytes = 0;
+}
+
+void mdb_comm_arena_destroy(mdbcu_ctx *ctx)
+{
+	arena_release(ctx);
+}
+
+int mdb_comm_arena(mdbcu_ctx *ctx, size_t bytes, void **bases)
+{
+	const int W = ctx->world;
+	if (W > MDB_MAX_RANKS)
+		return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "at most %d ranks", MDB_MAX_RANKS);
+	if (ctx->arena_bytes < bytes) {
+		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+		arena_release(ctx);
+		bytes += bytes / 8; // head-room so slightly larger follow-up queries reuse the mapping
+		cudaError_t e = cudaMalloc(&ctx->arena_local, bytes);
+		if (e != cudaSuccess) {
+			ctx->arena_local = nullptr;
+			return mdb_fail(ctx, MDBCU_ENOMEM, "cannot allocate the %zu-byte exchange arena: %s", bytes, cudaGetErrorString(e));
+		}
+		ctx->arena_bytes = bytes;
+		ctx->arena_peer[ctx->rank] = ctx->arena_local;
+		if (W > 1) {
+			cudaIpcMemHandle_t mine;
+			CUDA_TRY(ctx, cudaIpcGetMemHandle(&mine, ctx->arena_local));
+			DevTemp tmp(ctx);
+			unsigned char *d_mine, *d_all;
+			MDB_TRY(tmp.alloc(&d_mine, sizeof(mine)));
+			MDB_TRY(tmp.alloc(&d_all, sizeof(mine) * W));
+			CUDA_TRY(ctx, cudaMemcpyAsync(d_mine, &mine, sizeof(mine), cudaMemcpyHostToDevice, ctx->stream));
+			MDB_TRY(mdb_comm_allgather_bytes(ctx, d_mine, d_all, sizeof(mine)));
+			std::vector<cudaIpcMemHandle_t> all(W);
+			CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), d_all, sizeof(mine) * W, cudaMemcpyDeviceToHost, ctx->stream));
+			CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+			for (int r = 0; r < W; r++) {
+				if (r == ctx->rank)
+					continue;
+				e = cudaIpcOpenMemHandle(&ctx->arena_peer[r], all[r], cudaIpcMemLazyEnablePeerAccess);
+				if (e != cudaSuccess) {
+					ctx->arena_peer[r] = nullptr;
+					return mdb_fail(ctx, MDBCU_ECUDA, "cannot map rank %d's exchange arena (CUDA IPC / peer access): %s", r,
+							cudaGetErrorString(e));
+				}
+			}
+		}
+	}
+	for (int r = 0; r < W; r++)
+		bases[r] = ctx->arena_peer[r];
+	return MDBCU_OK;
+}
+
+// cross-rank barrier on the context's stream that also ORs a 32-bit flag word over all ranks
+int mdb_comm_barrier_or(mdbcu_ctx *ctx, uint32_t *d_flag, uint32_t *h_or_out)
+{
+	const int W = ctx->world;
+	DevTemp tmp(ctx);
+	uint32_t *d_all;
+	MDB_TRY(tmp.alloc(&d_all, W));
+	MDB_TRY(mdb_comm_allgather_bytes(ctx, d_flag, d_all, sizeof(uint32_t)));
+	if (h_or_out) {
+		std::vector<uint32_t> h(W);
+		CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), d_all, sizeof(uint32_t) * W, cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+		uint32_t v = 0;
+		for (int r = 0; r < W; r++)
+			v |= h[r];
+		*h_or_out = v;
+	}
+	return MDBCU_OK;
+}

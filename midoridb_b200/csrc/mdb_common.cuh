@@ -16,6 +16,7 @@
 #include "midoridb_cuda.h"
 
 #define MDB_WARP 32
+#define MDB_MAX_RANKS 8 // one node: up to 8 GPUs behind NVSwitch
 
 struct mdbcu_ctx {
 	int device = 0;
@@ -27,6 +28,10 @@ struct mdbcu_ctx {
 	// multi-GPU
 	int rank = 0, world = 1;
 	void *nccl_comm = nullptr;
+	// exchange arena of the multi-GPU radix join: own block + every peer's block mapped with CUDA IPC
+	void *arena_local = nullptr;
+	size_t arena_bytes = 0;
+	void *arena_peer[MDB_MAX_RANKS] = {};
 	// reusable scratch: pinned host word for small D2H reads
 	uint64_t *h_scalar = nullptr; // pinned, 64 entries
 	uint64_t *d_scalar = nullptr; // device, 64 entries
@@ -57,6 +62,7 @@ struct mdbcu_table {
 	uint64_t n_pages = 0;
 	bool paged = false;
 	bool all_live = true;      // every slot in [0, n_slots) is live
+	uint64_t global_slots = 0; // sum of n_slots over all ranks' shards (mdbcu_table_sync_stats)
 	uint32_t *live = nullptr;  // bitmap
 	std::vector<DevColumn> cols;
 };
@@ -236,6 +242,9 @@ int mdb_comm_group_begin(mdbcu_ctx *ctx);
 int mdb_comm_group_end(mdbcu_ctx *ctx);
 int mdb_comm_send(mdbcu_ctx *ctx, const void *p, size_t bytes, int peer);
 int mdb_comm_recv(mdbcu_ctx *ctx, void *p, size_t bytes, int peer);
+int mdb_comm_arena(mdbcu_ctx *ctx, size_t bytes, void **bases);
+void mdb_comm_arena_destroy(mdbcu_ctx *ctx);
+int mdb_comm_barrier_or(mdbcu_ctx *ctx, uint32_t *d_flag, uint32_t *h_or_out);
 int mdb_comm_allgather_u64(mdbcu_ctx *ctx, const uint64_t *send, uint64_t *recv, size_t count);
 
 // phase clock: events are only recorded while the query runs; one synchronise at the end

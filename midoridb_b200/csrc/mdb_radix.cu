@@ -45,18 +45,29 @@ struct RJDesc {
 	uint32_t ne;
 };
 
+#define RJ_MAX_RANKS 8
+
+// where the chunks of the partitions owned by one rank are written: this GPU's own arrays, or - in a
+// multi-GPU plan - the owner's arena mapped over NVLink (CUDA IPC), so pass 1 IS the exchange
+struct RJTarget {
+	uint16_t *pool;            // pool_chunks * RJ_CHUNK remainders
+	uint32_t *pool_next;       // allocation cursor
+	uint16_t *chunk_part;      // partition of each chunk
+	uint16_t *chunk_entries;   // valid remainders in each chunk
+	uint32_t *dir_cnt;         // chunks per partition
+};
+
 struct RJSide {
 	const int64_t *keys;
 	const uint32_t *present;
 	uint64_t n;
 	int all_in_range;          // every key of the column lies in [kmin, kmin + range): no per-key range test
-	uint16_t *pool;            // pool_chunks * RJ_CHUNK remainders
-	uint32_t pool_chunks;
-	uint32_t *pool_next;       // allocation cursor
-	uint16_t *chunk_part;      // partition of each chunk
-	uint16_t *chunk_entries;   // valid remainders in each chunk
-	uint32_t *dir_cnt;         // chunks per partition
-	RJDesc *dir;               // (chunk id, entries) grouped by partition
+	int world, self;           // owner ranks; index of this GPU in dst[]
+	uint32_t pool_chunks;      // capacity of every target's pool
+	uint32_t id_batch, id_low; // chunk ids a CTA reserves per owner at a time / refill threshold
+	RJTarget dst[RJ_MAX_RANKS];
+	uint16_t *pool;            // pass 2 reads remainders from here (dst[self].pool unless an NCCL exchange staged them)
+	RJDesc *dir;               // (offset, entries) of this GPU's chunks grouped by partition
 	uint64_t *dir_off;         // exclusive offsets into dir
 	uint32_t *dir_fill;
 };
@@ -79,7 +90,8 @@ struct RJP1Smem {
 	uint32_t ovf[2][RJ_OVF_CAP];              // (partition << 16 | remainder) waiting for the next round
 	uint32_t wl_count[2];
 	uint32_t ovf_count[2];
-	uint32_t local_next, local_end;           // chunk ids reserved by this CTA (refilled in bulk by thread 0)
+	uint32_t local_next[RJ_MAX_RANKS];        // chunk ids reserved by this CTA in each owner's pool
+	uint32_t local_end[RJ_MAX_RANKS];         // (refilled in bulk by thread 0)
 };
 
 static_assert(sizeof(RJP1Smem) <= 227 * 1024, "pass-1 shared memory exceeds the 227 KiB a CTA can opt into");
@@ -97,35 +109,43 @@ __device__ __forceinline__ void rj_global_red_inc(uint32_t *p)
 	asm volatile("red.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
 }
 
-// chunk ids come from the CTA's reserved range (one shared-memory atomic); thread 0 tops the range up with ONE
-// global atomic per RJ_ID_BATCH chunks while the other threads insert keys, so no flush ever waits on L2
-#define RJ_ID_BATCH 8192
-#define RJ_ID_LOW 2048
+// rank that owns partition p: ranks own the contiguous blocks [r*P/W, (r+1)*P/W)
+__device__ __forceinline__ int rj_owner(const RJSide &s, const RJParams &pr, uint32_t p)
+{
+	return s.world == 1 ? 0 : (int)(((p + 1) * (uint32_t)s.world - 1) / (uint32_t)pr.nparts);
+}
 
+// chunk ids come from the CTA's reserved range in the owner's pool (one shared-memory atomic); thread 0 tops a
+// range up with ONE global (for a remote owner: NVLink) atomic per id_batch chunks while the other threads
+// insert keys, so no flush ever waits on L2 or on the link
 __device__ static inline void rj_new_chunk(const RJSide &s, const RJParams &pr, RJP1Smem *sm, uint32_t p)
 {
+	const int o = rj_owner(s, pr, p);
+	const RJTarget &t = s.dst[o];
 	const uint32_t old = sm->chunk[p];
-	uint32_t cid = rj_smem_inc(&sm->local_next);
-	if (cid >= sm->local_end)
-		cid = atomicAdd(s.pool_next, 1u); // reserve ran dry inside one round (extreme skew)
+	uint32_t cid = rj_smem_inc(&sm->local_next[o]);
+	if (cid >= sm->local_end[o])
+		cid = atomicAdd(t.pool_next, 1u); // reserve ran dry inside one round (extreme skew)
 	if (cid >= s.pool_chunks) {
 		atomicOr(pr.error_flag, RJ_ERR_POOL);
 		return;
 	}
 	if (old != RJ_NONE)
-		s.chunk_entries[old >> 5] = RJ_CHUNK; // a chunk is only replaced when all its sectors are written
-	s.chunk_part[cid] = (uint16_t)p;
-	rj_global_red_inc(&s.dir_cnt[p]);
+		t.chunk_entries[old >> 5] = RJ_CHUNK; // a chunk is only replaced when all its sectors are written
+	t.chunk_part[cid] = (uint16_t)p;
+	rj_global_red_inc(&t.dir_cnt[p]);
 	sm->chunk[p] = cid << 5;
 }
 
 __device__ static inline void rj_refill_ids(const RJSide &s, RJP1Smem *sm)
 {
 	// thread 0 only, during the insert phase (no flush lane is allocating then)
-	if (sm->local_end - min(sm->local_next, sm->local_end) < RJ_ID_LOW) {
-		const uint32_t base = atomicAdd(s.pool_next, (uint32_t)RJ_ID_BATCH);
-		sm->local_next = base;
-		sm->local_end = base + RJ_ID_BATCH; // ids left in the old range stay unused (chunk_part 0xffff)
+	for (int o = 0; o < s.world; o++) {
+		if (sm->local_end[o] - min(sm->local_next[o], sm->local_end[o]) < s.id_low) {
+			const uint32_t base = atomicAdd(s.dst[o].pool_next, s.id_batch);
+			sm->local_next[o] = base;
+			sm->local_end[o] = base + s.id_batch; // ids left in the old range stay unused (chunk_part 0xffff)
+		}
 	}
 }
 
@@ -284,7 +304,7 @@ __device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, 
 		uint2 *row = reinterpret_cast<uint2*>(&sm->stage[p * RJ_CAP]); // 40-byte rows are 8-byte aligned
 		const uint2 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4];
 		if (ch != RJ_NONE && (ch & 31u) < RJ_BLOCKS_PER_CHUNK) {
-			int4 *dst = reinterpret_cast<int4*>(s.pool + (size_t)(ch >> 5) * RJ_CHUNK + (ch & 31u) * RJ_FLUSH);
+			int4 *dst = reinterpret_cast<int4*>(s.dst[rj_owner(s, pr, p)].pool + (size_t)(ch >> 5) * RJ_CHUNK + (ch & 31u) * RJ_FLUSH);
 			dst[0] = make_int4((int)a.x, (int)a.y, (int)b.x, (int)b.y);
 			dst[1] = make_int4((int)c.x, (int)c.y, (int)d.x, (int)d.y);
 			sm->chunk[p] = ch + 1;
@@ -330,6 +350,7 @@ __device__ static inline void rj_drain(const RJSide &s, const RJParams &pr, RJP1
 {
 	for (int p = threadIdx.x; p < pr.nparts; p += RJ_P1_THREADS) {
 		const uint32_t f = min(sm->fill[p], (uint32_t)RJ_CAP);
+		const RJTarget &t = s.dst[rj_owner(s, pr, p)];
 		uint32_t ch = sm->chunk[p];
 		if (f > 0) {
 			if (ch == RJ_NONE || (ch & 31u) == RJ_BLOCKS_PER_CHUNK) {
@@ -337,15 +358,16 @@ __device__ static inline void rj_drain(const RJSide &s, const RJParams &pr, RJP1
 				ch = sm->chunk[p];
 			}
 			if (ch != RJ_NONE && (ch & 31u) < RJ_BLOCKS_PER_CHUNK) {
-				uint16_t *dst = s.pool + (size_t)(ch >> 5) * RJ_CHUNK + (ch & 31u) * RJ_FLUSH;
+				uint16_t *dst = t.pool + (size_t)(ch >> 5) * RJ_CHUNK + (ch & 31u) * RJ_FLUSH;
 				for (uint32_t i = 0; i < f; i++)
 					dst[i] = sm->stage[p * RJ_CAP + i];
-				s.chunk_entries[ch >> 5] = (uint16_t)((ch & 31u) * RJ_FLUSH + f);
+				t.chunk_entries[ch >> 5] = (uint16_t)((ch & 31u) * RJ_FLUSH + f);
 			}
 		} else if (ch != RJ_NONE) {
-			s.chunk_entries[ch >> 5] = (uint16_t)((ch & 31u) * RJ_FLUSH);
+			t.chunk_entries[ch >> 5] = (uint16_t)((ch & 31u) * RJ_FLUSH);
 		}
 	}
+	__threadfence_system(); // remote owners read these chunks after the next cross-rank barrier
 }
 
 __device__ static inline void rj_smem_init(RJP1Smem *sm)
@@ -359,8 +381,8 @@ __device__ static inline void rj_smem_init(RJP1Smem *sm)
 		sm->ovf_count[tid] = 0;
 		sm->wl_count[tid] = 0;
 	}
-	if (tid == 0)
-		sm->local_next = sm->local_end = 0;
+	if (tid < RJ_MAX_RANKS)
+		sm->local_next[tid] = sm->local_end[tid] = 0;
 	__syncthreads();
 }
 
@@ -484,7 +506,7 @@ __global__ void k_radix_dir_scan(RJSide s, int nparts)
 	uint64_t carry = 0;
 	for (int base = 0; base < nparts + 1; base += blockDim.x) {
 		int i = base + threadIdx.x;
-		uint64_t v = i < nparts ? s.dir_cnt[i] : 0;
+		uint64_t v = i < nparts ? s.dst[s.self].dir_cnt[i] : 0;
 		uint64_t incl = v;
 		int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 		for (int o = 1; o < 32; o <<= 1) {
@@ -517,29 +539,86 @@ __global__ void k_radix_dir_scan(RJSide s, int nparts)
 #include "mdb_radix_pass2.cuh"
 #include "mdb_radix_dist.cuh"
 
-static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_table *t, int col, int grid)
+// chunk-id reservation sizes: a CTA needs at most one fresh chunk per owned partition at start-up
+static void rj_id_policy(int world, uint32_t *batch, uint32_t *low)
+{
+	*batch = world == 1 ? 8192u : std::max(1024u, 2u * RJ_MAX_PART / (uint32_t)world);
+	*low = *batch / 4;
+}
+
+// chunks one owner's pool must hold: data chunks (with slack for imbalance) + one ragged chunk per
+// (source CTA, owned partition) + ids abandoned at refills + one reserve per (source CTA, owner)
+static uint64_t rj_pool_chunks(uint64_t rows_for_owner, int world, int grid)
+{
+	uint32_t batch, low;
+	rj_id_policy(world, &batch, &low);
+	uint64_t chunks = rows_for_owner / RJ_CHUNK + (uint64_t)grid * RJ_MAX_PART;
+	chunks += chunks / 2 + (uint64_t)world * grid * batch + 1024;
+	return chunks;
+}
+
+// byte layout of one side inside an exchange arena (identical on every rank)
+struct RJArenaLayout {
+	size_t pool, chunk_part, chunk_entries, dir_cnt, pool_next, bytes;
+};
+
+static RJArenaLayout rj_arena_layout(uint64_t chunks)
+{
+	auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+	RJArenaLayout l;
+	l.pool = 0;
+	l.chunk_part = up(l.pool + chunks * RJ_CHUNK * sizeof(uint16_t));
+	l.chunk_entries = up(l.chunk_part + chunks * sizeof(uint16_t));
+	l.dir_cnt = up(l.chunk_entries + chunks * sizeof(uint16_t));
+	l.pool_next = up(l.dir_cnt + (RJ_MAX_PART + 1) * sizeof(uint32_t));
+	l.bytes = up(l.pool_next + 256);
+	return l;
+}
+
+static void rj_target_at(RJTarget *t, void *base, const RJArenaLayout &l)
+{
+	char *b = (char*)base;
+	t->pool = (uint16_t*)(b + l.pool);
+	t->chunk_part = (uint16_t*)(b + l.chunk_part);
+	t->chunk_entries = (uint16_t*)(b + l.chunk_entries);
+	t->dir_cnt = (uint32_t*)(b + l.dir_cnt);
+	t->pool_next = (uint32_t*)(b + l.pool_next);
+}
+
+// arena_bases == nullptr: all chunks stay on this GPU (single-GPU plan, or NCCL exchange afterwards);
+// otherwise dst[r] points into rank r's arena (at byte offset arena_off) and pass 1 writes over NVLink
+static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_table *t, int col, int grid, uint64_t chunks,
+		void *const *arena_bases, size_t arena_off)
 {
 	memset(s, 0, sizeof(*s));
 	s->keys = t->cols[col].data;
 	s->present = col_all_present(t, col) ? nullptr : t->cols[col].present;
 	s->n = t->n_slots;
-	// data chunks + one partial chunk per (CTA, partition) + ids abandoned at refills + one reserve per CTA
-	uint64_t chunks = t->n_slots / RJ_CHUNK + (uint64_t)grid * RJ_MAX_PART;
-	chunks += chunks / 2 + (uint64_t)grid * RJ_ID_BATCH + 1024;
 	if (chunks >= (1ull << 27))
 		return MDBCU_EUNSUPPORTED;
 	s->pool_chunks = (uint32_t)chunks;
-	MDB_TRY(tmp.alloc(&s->pool, chunks * RJ_CHUNK));
-	MDB_TRY(tmp.alloc(&s->pool_next, 1));
-	MDB_TRY(tmp.alloc(&s->chunk_part, chunks));
-	MDB_TRY(tmp.alloc(&s->chunk_entries, chunks));
-	MDB_TRY(tmp.alloc(&s->dir_cnt, RJ_MAX_PART + 1));
+	s->world = arena_bases ? ctx->world : 1;
+	s->self = arena_bases ? ctx->rank : 0;
+	rj_id_policy(s->world, &s->id_batch, &s->id_low);
+	RJTarget &own = s->dst[s->self];
+	if (arena_bases) {
+		const RJArenaLayout l = rj_arena_layout(chunks);
+		for (int r = 0; r < ctx->world; r++)
+			rj_target_at(&s->dst[r], (char*)arena_bases[r] + arena_off, l);
+	} else {
+		MDB_TRY(tmp.alloc(&own.pool, chunks * RJ_CHUNK));
+		MDB_TRY(tmp.alloc(&own.pool_next, 1));
+		MDB_TRY(tmp.alloc(&own.chunk_part, chunks));
+		MDB_TRY(tmp.alloc(&own.chunk_entries, chunks));
+		MDB_TRY(tmp.alloc(&own.dir_cnt, RJ_MAX_PART + 1));
+	}
+	s->pool = own.pool;
 	MDB_TRY(tmp.alloc(&s->dir_fill, RJ_MAX_PART + 1));
 	MDB_TRY(tmp.alloc(&s->dir_off, RJ_MAX_PART + 2));
 	MDB_TRY(tmp.alloc(&s->dir, chunks));
-	CUDA_TRY(ctx, cudaMemsetAsync(s->pool_next, 0, sizeof(uint32_t), ctx->stream));
-	CUDA_TRY(ctx, cudaMemsetAsync(s->chunk_part, 0xff, chunks * sizeof(uint16_t), ctx->stream)); // 0xffff = never allocated
-	CUDA_TRY(ctx, cudaMemsetAsync(s->dir_cnt, 0, (RJ_MAX_PART + 1) * sizeof(uint32_t), ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(own.pool_next, 0, sizeof(uint32_t), ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(own.chunk_part, 0xff, chunks * sizeof(uint16_t), ctx->stream)); // 0xffff = never allocated
+	CUDA_TRY(ctx, cudaMemsetAsync(own.dir_cnt, 0, (RJ_MAX_PART + 1) * sizeof(uint32_t), ctx->stream));
 	CUDA_TRY(ctx, cudaMemsetAsync(s->dir_fill, 0, (RJ_MAX_PART + 1) * sizeof(uint32_t), ctx->stream));
 	return MDBCU_OK;
 }
@@ -627,8 +706,24 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	const int grid1 = ctx->num_sms;
 	RJSide sa, sb;
 	RJParams pr;
-	MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1));
-	MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1));
+	// multi-GPU plans: pass 1 writes every chunk straight into the owner GPU's arena over NVLink (CUDA IPC);
+	// MDBCU_EXCHANGE=nccl selects the staged variant instead (partition locally, then a grouped send/recv)
+	static const bool use_nccl_exchange = getenv("MDBCU_EXCHANGE") && strcmp(getenv("MDBCU_EXCHANGE"), "nccl") == 0;
+	const bool p2p = dist && !use_nccl_exchange;
+	if (p2p) {
+		if (!ta->global_slots || !tb->global_slots)
+			return mdb_fail(ctx, MDBCU_EERROR, "distributed plan: call mdbcu_table_sync_stats on every sharded table first");
+		const uint64_t ca_chunks = rj_pool_chunks(ta->global_slots / ctx->world + 1, ctx->world, grid1);
+		const uint64_t cb_chunks = rj_pool_chunks(tb->global_slots / ctx->world + 1, ctx->world, grid1);
+		const RJArenaLayout la = rj_arena_layout(ca_chunks), lb = rj_arena_layout(cb_chunks);
+		void *bases[MDB_MAX_RANKS];
+		MDB_TRY(mdb_comm_arena(ctx, la.bytes + lb.bytes, bases));
+		MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, ca_chunks, bases, 0));
+		MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, cb_chunks, bases, la.bytes));
+	} else {
+		MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, rj_pool_chunks(ta->n_slots, 1, grid1), nullptr, 0));
+		MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, rj_pool_chunks(tb->n_slots, 1, grid1), nullptr, 0));
+	}
 	sa.all_in_range = ca.imin >= kmin && ca.imax <= kmax;
 	sb.all_in_range = cb.imin >= kmin && cb.imax <= kmax;
 	pr.kmin = kmin;
@@ -680,16 +775,31 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		attr_done = true;
 	}
 
+	if (p2p) {
+		// every rank's arena must be reset before any peer starts writing into it
+		clock.begin(6);
+		MDB_TRY(mdb_comm_barrier_or(ctx, d_flags, nullptr));
+	}
 	clock.begin(1);
 	launch_partition(ctx, grid1, sa, pr);
 	launch_partition(ctx, grid1, sb, pr);
+	if (p2p) {
+		// all remote stores have landed once every rank's pass 1 has completed; error flags are shared so that
+		// every rank takes the same exit
+		clock.begin(6);
+		uint32_t any = 0;
+		MDB_TRY(mdb_comm_barrier_or(ctx, d_flags, &any));
+		if (any)
+			return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "distributed radix join: pass 1 failed on some rank (flags %u: "
+					"1 = chunk pool exhausted, 4 = extreme skew)", any);
+	}
 	clock.begin(7);
 	MDB_LAUNCH(ctx, k_radix_dir_scan, 1, 1024, 0, sa, nparts);
 	MDB_LAUNCH(ctx, k_radix_dir_scan, 1, 1024, 0, sb, nparts);
 	MDB_LAUNCH(ctx, k_radix_dir_fill, ctx->num_sms * 4, 256, 0, sa);
 	MDB_LAUNCH(ctx, k_radix_dir_fill, ctx->num_sms * 4, 256, 0, sb);
 	uint64_t exchanged = 0;
-	if (dist) {
+	if (dist && !p2p) {
 		clock.begin(6);
 		RJSide *both[2] = {&sa, &sb};
 		MDB_TRY(rj_exchange(ctx, tmp, &pr, both, &exchanged));

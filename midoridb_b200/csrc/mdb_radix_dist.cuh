@@ -10,6 +10,8 @@
 // both sides together, preceded by one small all-gather of per-partition chunk counts.
 #pragma once
 
+#include <chrono>
+#include <cstdlib>
 #include <vector>
 
 __global__ void k_dist_granules(const RJDesc *__restrict__ dir, uint64_t n, uint32_t *__restrict__ gran, uint32_t *__restrict__ ne)
@@ -90,6 +92,19 @@ static int rj_exchange(mdbcu_ctx *ctx, DevTemp &tmp, RJParams *pr, RJSide *sides
 	const int nmine = phi - plo;
 	const size_t hdr_len = (size_t)P + W; // per side
 	RJDistSide ds[2];
+	// MDBCU_TRACE=1: wall-clock of every step of the exchange on stderr (synchronises the stream; debugging aid only)
+	static const bool trace = getenv("MDBCU_TRACE") != nullptr;
+	auto t_last = std::chrono::steady_clock::now();
+	auto lap = [&](const char *what) {
+		if (!trace)
+			return;
+		cudaStreamSynchronize(ctx->stream);
+		auto now = std::chrono::steady_clock::now();
+		fprintf(stderr, "[mdbcu rank %d] exchange %-28s %8.1f us\n", rank, what,
+				std::chrono::duration<double, std::micro>(now - t_last).count());
+		t_last = now;
+	};
+	lap("start (waits for pass 1)");
 
 	// 1. local chunk counts: dir_off[P] of each side (two 8-byte reads), then granules / descriptors in directory order
 	for (int s = 0; s < 2; s++) {
@@ -111,16 +126,18 @@ static int rj_exchange(mdbcu_ctx *ctx, DevTemp &tmp, RJParams *pr, RJSide *sides
 			MDB_LAUNCH(ctx, k_dist_granules, grid, 256, 0, (const RJDesc*)sides[s]->dir, d.nchunks, d.gran, d.ne);
 		}
 		MDB_TRY(mdb_scan_u32_u64(ctx, d.gran, d.goff, d.nchunks, d.gtotal));
-		MDB_LAUNCH(ctx, k_dist_header, 8, 256, 0, (const uint32_t*)sides[s]->dir_cnt, (const uint64_t*)sides[s]->dir_off,
+		MDB_LAUNCH(ctx, k_dist_header, 8, 256, 0, (const uint32_t*)sides[s]->dst[sides[s]->self].dir_cnt, (const uint64_t*)sides[s]->dir_off,
 				(const uint64_t*)d.goff, (const uint64_t*)d.gtotal, d.nchunks, P, W, hdr_local + s * hdr_len);
 	}
 	CUDA_CHECK_LAUNCH(ctx);
+	lap("granules+scan+header");
 
 	// 2. everyone learns everyone's per-partition chunk counts and per-destination granule counts
 	MDB_TRY(mdb_comm_allgather_bytes(ctx, hdr_local, hdr_all, 2 * hdr_len * sizeof(uint64_t)));
 	std::vector<uint64_t> h((size_t)2 * hdr_len * W);
 	CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), hdr_all, h.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	lap("allgather header + D2H");
 	auto cnt_of = [&](int src, int side, int p) { return h[((size_t)src * 2 + side) * hdr_len + p]; };
 	auto gran_to = [&](int src, int side, int dst) { return h[((size_t)src * 2 + side) * hdr_len + P + dst]; };
 
@@ -156,6 +173,7 @@ static int rj_exchange(mdbcu_ctx *ctx, DevTemp &tmp, RJParams *pr, RJSide *sides
 		MDB_TRY(tmp.alloc(&d.gran_recv, RG));
 		MDB_TRY(tmp.alloc(&d.dir2, RC));
 		MDB_TRY(tmp.alloc(&d.dir_off2, (size_t)P + 2));
+		lap("  offsets + alloc");
 		if (d.nchunks) {
 			int grid = (int)std::min<uint64_t>(mdb_div_up(d.nchunks * 32, 256), (uint64_t)ctx->num_sms * 16);
 			MDB_LAUNCH(ctx, k_dist_gather, grid, 256, 0, (const uint16_t*)sides[s]->pool, (const RJDesc*)sides[s]->dir,
@@ -163,6 +181,7 @@ static int rj_exchange(mdbcu_ctx *ctx, DevTemp &tmp, RJParams *pr, RJSide *sides
 		}
 	}
 	CUDA_CHECK_LAUNCH(ctx);
+	lap("offsets + alloc + gather");
 
 	// 4. the exchange: descriptors (4 B per chunk) and granules (16 B each) of both sides in ONE grouped all-to-all
 	MDB_TRY(mdb_comm_group_begin(ctx));
@@ -179,6 +198,7 @@ static int rj_exchange(mdbcu_ctx *ctx, DevTemp &tmp, RJParams *pr, RJSide *sides
 		}
 	}
 	MDB_TRY(mdb_comm_group_end(ctx));
+	lap("grouped send/recv");
 
 	// 5. descriptors of the received chunks, grouped by (owned) partition
 	for (int s = 0; s < 2; s++) {
@@ -232,6 +252,7 @@ static int rj_exchange(mdbcu_ctx *ctx, DevTemp &tmp, RJParams *pr, RJSide *sides
 		sides[s]->dir_off = d.dir_off2;
 	}
 	CUDA_CHECK_LAUNCH(ctx);
+	lap("remote directory");
 	pr->part_first = plo;
 	pr->part_end = phi;
 	return MDBCU_OK;

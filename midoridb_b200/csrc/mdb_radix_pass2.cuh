@@ -17,15 +17,16 @@
 
 __global__ void k_radix_dir_fill(RJSide s)
 {
-	uint32_t nchunks = min(*s.pool_next, s.pool_chunks);
+	const RJTarget &t = s.dst[s.self];
+	uint32_t nchunks = min(*t.pool_next, s.pool_chunks);
 	for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += gridDim.x * blockDim.x) {
-		uint32_t p = s.chunk_part[c];
+		uint32_t p = t.chunk_part[c];
 		if (p == 0xffffu)
 			continue; // id reserved by a CTA but never used
 		uint32_t pos = atomicAdd(&s.dir_fill[p], 1u);
 		RJDesc d;
 		d.off16 = c * (RJ_CHUNK / 8);
-		d.ne = s.chunk_entries[c];
+		d.ne = t.chunk_entries[c];
 		s.dir[s.dir_off[p] + pos] = d;
 	}
 }

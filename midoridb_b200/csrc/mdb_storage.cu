@@ -101,6 +101,7 @@ extern "C" void mdbcu_shutdown(mdbcu_ctx *ctx)
 		return;
 	cudaSetDevice(ctx->device);
 	cudaStreamSynchronize(ctx->stream);
+	mdb_comm_arena_destroy(ctx);
 	mdb_comm_destroy(ctx);
 	cudaFreeHost(ctx->h_scalar);
 	cudaFree(ctx->d_scalar);
@@ -954,15 +955,17 @@ extern "C" int mdbcu_table_sync_stats(mdbcu_table *tt)
 			c.gmin = c.imin;
 			c.gmax = c.imax;
 		}
+		t->global_slots = t->n_slots;
 		return MDBCU_OK;
 	}
-	const size_t per_rank = (size_t)3 * t->ncols;
+	const size_t per_rank = (size_t)3 * t->ncols + 1;
 	std::vector<int64_t> mine(per_rank), all(per_rank * W);
 	for (int c = 0; c < t->ncols; c++) {
 		mine[3 * c] = t->cols[c].imin;
 		mine[3 * c + 1] = t->cols[c].imax;
 		mine[3 * c + 2] = t->cols[c].stats_ok ? 1 : 0;
 	}
+	mine[per_rank - 1] = (int64_t)t->n_slots;
 	DevTemp tmp(ctx);
 	int64_t *d_mine, *d_all;
 	MDB_TRY(tmp.alloc(&d_mine, per_rank));
@@ -971,6 +974,9 @@ extern "C" int mdbcu_table_sync_stats(mdbcu_table *tt)
 	MDB_TRY(mdb_comm_allgather_bytes(ctx, d_mine, d_all, per_rank * sizeof(int64_t)));
 	CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), d_all, per_rank * W * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
 	CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+	t->global_slots = 0;
+	for (int r = 0; r < W; r++)
+		t->global_slots += (uint64_t)all[(size_t)r * per_rank + per_rank - 1];
 	for (int c = 0; c < t->ncols; c++) {
 		DevColumn &col = t->cols[c];
 		col.gstats_ok = true;
