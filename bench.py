@@ -52,6 +52,13 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def count(self):
+        try:
+            self.f.flush()
+            return sum(1 for _ in open(self.path))
+        except Exception:
+            return 0
+
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if not self.proc:
@@ -276,9 +283,16 @@ def main():
     dev_ms = be.event_elapsed_ms(0, 1)
     dist.barrier()
     launches = be.stats().total_kernel_launches - launches0
-    clocks = sampler.stop() if sampler else None
-
     ms_per_step = dist.max(dev_ms) / args.steps
+    # nvidia-smi needs ~100 ms per sample: when the timed region is shorter than that, keep the SAME load running
+    # (untimed, same step count on every rank) so that the clocks line is sampled under load
+    n_extra = int(min(4000, max(0.0, np.ceil((800.0 - ms_per_step * args.steps) / ms_per_step))))
+    for _ in range(n_extra):
+        step()
+    be.sync()
+    clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["window"] = "timed region + %d further untimed steps of the same load" % n_extra
     total_groups = dist.sum(groups)
     rows_per_step = 2 * n_total
     value = rows_per_step / (ms_per_step / 1000.0)

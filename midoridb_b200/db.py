@@ -1,4 +1,4 @@
-"""ctypes binding of libmidoridb_b200.so (midoridb_b200/host/midoridb.h): MidoriDB's own public C API -
+"""ctypes binding of libmidoridb_b200.so (include/midoridb.h): MidoriDB's own public C API -
 database_open / query_execute / query_cur_step / query_column_int64 / query_free / database_close
 (reference: include/engine/query.h:42-69, include/engine/database.h:26-32) - served by the B200 backend.
 
