@@ -18,486 +18,15 @@
 #include <string.h>
 #include <algorithm>
 
-#define RJ_MAX_PART 4096           // partitions (12 radix bits)
-#define RJ_MAX_SHIFT 16            // remainder bits: 2-byte remainders
-#define RJ_CAP 20                  // staging slots per partition in shared memory
-#define RJ_FLUSH 16                // a partition is flushed when 16 remainders (= one 32-byte sector) are staged
-#define RJ_CHUNK 256               // remainders per chunk (512 bytes = one warp-wide 128-bit load)
-#define RJ_BLOCKS_PER_CHUNK (RJ_CHUNK / RJ_FLUSH)
-#define RJ_P1_THREADS 1024
-#define RJ_P1_LOADS 4              // 128-bit loads (2 keys each) per thread per round
-#define RJ_P1_TILE (RJ_P1_THREADS * RJ_P1_LOADS * 2)
-#define RJ_OVF_CAP 1536            // keys per round that may find their staging row full and wait one round
-#define RJ_NONE 0xffffffffu
-
-#define RJ_ERR_POOL 1u             // chunk pool exhausted
-#define RJ_ERR_COUNTER 2u          // a packed counter wrapped (too many equal keys for the counter width)
-#define RJ_ERR_SKEW 4u             // more than RJ_OVF_CAP keys per round hit full staging rows
+#include "mdb_radix_types.cuh"
 
 static bool col_all_present(const mdbcu_table *t, int col)
 {
 	return t->all_live && !t->cols[col].has_nulls;
 }
 
-// one run of <= RJ_CHUNK remainders: 16-byte aligned offset into a remainder buffer, valid entries
-struct RJDesc {
-	uint32_t off16; // in units of 16 bytes (8 remainders)
-	uint32_t ne;
-};
+#include "mdb_radix_pass1.cuh"
 
-#define RJ_MAX_RANKS 8
-
-// where the chunks of the partitions owned by one rank are written: this GPU's own arrays, or - in a
-// multi-GPU plan - the owner's arena mapped over NVLink (CUDA IPC), so pass 1 IS the exchange
-struct RJTarget {
-	uint16_t *pool;            // pool_chunks * RJ_CHUNK remainders
-	uint32_t *pool_next;       // allocation cursor
-	uint16_t *chunk_part;      // partition of each chunk
-	uint16_t *chunk_entries;   // valid remainders in each chunk
-	uint32_t *dir_cnt;         // chunks per partition
-};
-
-struct RJSide {
-	const int64_t *keys;
-	const uint32_t *present;
-	uint64_t n;
-	int all_in_range;          // every key of the column lies in [kmin, kmin + range): no per-key range test
-	int world, self;           // owner ranks; index of this GPU in dst[]
-	uint32_t pool_chunks;      // capacity of every target's pool
-	uint32_t id_batch, id_low; // chunk ids a CTA reserves per owner at a time / refill threshold
-	RJTarget dst[RJ_MAX_RANKS];
-	uint16_t *pool;            // pass 2 reads remainders from here (dst[self].pool unless an NCCL exchange staged them)
-	RJDesc *dir;               // (offset, entries) of this GPU's chunks grouped by partition
-	uint64_t *dir_off;         // exclusive offsets into dir
-	uint32_t *dir_fill;
-};
-
-struct RJParams {
-	long long kmin;
-	unsigned long long range;  // keys in [kmin, kmin + range) can match
-	int shift;                 // remainder bits
-	uint32_t mask;             // (1 << shift) - 1
-	int nparts;
-	int part_first, part_end;  // pass 2 handles partitions [part_first, part_end) (all of them on one GPU)
-	uint32_t *error_flag;
-};
-
-struct RJP1Smem {
-	uint16_t stage[RJ_MAX_PART * RJ_CAP];     // 160 KiB: 20 two-byte slots per partition
-	uint32_t fill[RJ_MAX_PART];               // slots handed out this round (may overshoot RJ_CAP)
-	uint32_t chunk[RJ_MAX_PART];              // current chunk of this CTA: chunk id * 32 + sectors used, or RJ_NONE
-	uint16_t worklist[2][RJ_MAX_PART];        // partitions whose 16th slot filled this round
-	uint32_t ovf[2][RJ_OVF_CAP];              // (partition << 16 | remainder) waiting for the next round
-	uint32_t wl_count[2];
-	uint32_t ovf_count[2];
-	uint32_t local_next[RJ_MAX_RANKS];        // chunk ids reserved by this CTA in each owner's pool
-	uint32_t local_end[RJ_MAX_RANKS];         // (refilled in bulk by thread 0)
-};
-
-static_assert(sizeof(RJP1Smem) <= 227 * 1024, "pass-1 shared memory exceeds the 227 KiB a CTA can opt into");
-
-// plain shared-memory atomic: kept in PTX so the compiler does not expand it into warp-aggregation code
-__device__ __forceinline__ uint32_t rj_smem_inc(uint32_t *p)
-{
-	uint32_t old;
-	asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
-	return old;
-}
-
-__device__ __forceinline__ void rj_global_red_inc(uint32_t *p)
-{
-	asm volatile("red.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
-}
-
-// rank that owns partition p: ranks own the contiguous blocks [r*P/W, (r+1)*P/W)
-__device__ __forceinline__ int rj_owner(const RJSide &s, const RJParams &pr, uint32_t p)
-{
-	return s.world == 1 ? 0 : (int)(((p + 1) * (uint32_t)s.world - 1) / (uint32_t)pr.nparts);
-}
-
-// chunk ids come from the CTA's reserved range in the owner's pool (one shared-memory atomic); thread 0 tops a
-// range up with ONE global (for a remote owner: NVLink) atomic per id_batch chunks while the other threads
-// insert keys, so no flush ever waits on L2 or on the link
-__device__ static inline void rj_new_chunk(const RJSide &s, const RJParams &pr, RJP1Smem *sm, uint32_t p)
-{
-	const int o = rj_owner(s, pr, p);
-	const RJTarget &t = s.dst[o];
-	const uint32_t old = sm->chunk[p];
-	uint32_t cid = rj_smem_inc(&sm->local_next[o]);
-	if (cid >= sm->local_end[o])
-		cid = atomicAdd(t.pool_next, 1u); // reserve ran dry inside one round (extreme skew)
-	if (cid >= s.pool_chunks) {
-		atomicOr(pr.error_flag, RJ_ERR_POOL);
-		return;
-	}
-	if (old != RJ_NONE)
-		t.chunk_entries[old >> 5] = RJ_CHUNK; // a chunk is only replaced when all its sectors are written
-	t.chunk_part[cid] = (uint16_t)p;
-	rj_global_red_inc(&t.dir_cnt[p]);
-	sm->chunk[p] = cid << 5;
-}
-
-__device__ static inline void rj_refill_ids(const RJSide &s, RJP1Smem *sm)
-{
-	// thread 0 only, during the insert phase (no flush lane is allocating then)
-	for (int o = 0; o < s.world; o++) {
-		if (sm->local_end[o] - min(sm->local_next[o], sm->local_end[o]) < s.id_low) {
-			const uint32_t base = atomicAdd(s.dst[o].pool_next, s.id_batch);
-			sm->local_next[o] = base;
-			sm->local_end[o] = base + s.id_batch; // ids left in the old range stay unused (chunk_part 0xffff)
-		}
-	}
-}
-
-__device__ static inline void rj_park(RJP1Smem *sm, const RJParams &pr, uint32_t item, int par)
-{
-	// staging row full until this round's flush: the key waits one round
-	const uint32_t o = rj_smem_inc(&sm->ovf_count[par]);
-	if (o < RJ_OVF_CAP)
-		sm->ovf[par][o] = item;
-	else
-		atomicOr(pr.error_flag, RJ_ERR_SKEW);
-}
-
-__device__ static inline void rj_insert(RJP1Smem *sm, const RJParams &pr, uint32_t item, int par)
-{
-	const uint32_t p = item >> 16;
-	const uint32_t pos = rj_smem_inc(&sm->fill[p]);
-	if (pos < RJ_CAP) {
-		sm->stage[p * RJ_CAP + pos] = (uint16_t)item;
-		if (pos == RJ_FLUSH - 1)
-			sm->worklist[par][rj_smem_inc(&sm->wl_count[par])] = (uint16_t)p;
-	} else {
-		rj_park(sm, pr, item, par);
-	}
-}
-
-__device__ static inline void rj_round_begin(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par)
-{
-	const int tid = threadIdx.x;
-	if (tid == 0)
-		rj_refill_ids(s, sm);
-	// keys parked by the previous round go first (their rows were flushed since)
-	const uint32_t novf = min(sm->ovf_count[par ^ 1], (uint32_t)RJ_OVF_CAP);
-	for (uint32_t i = tid; i < novf; i += RJ_P1_THREADS)
-		rj_insert(sm, pr, sm->ovf[par ^ 1][i], par);
-}
-
-// Hot loop of pass 1 for the common case: a complete tile of a column without NULLs/tombstones whose
-// [min, max] lies inside the partitioned key range, so no per-key validity test is needed and all arithmetic
-// is 32-bit.  Per key: subtract, shift, one shared-memory atomic (slot), one 2-byte shared store; the rare
-// events (row completed a sector -> queue it; row full -> park the key) are predicated, never branched on.
-__device__ static inline void rj_insert_tile_fast(const RJParams &pr, RJP1Smem *sm, const int4 *buf, int par)
-{
-	constexpr int NK = RJ_P1_LOADS * 2;
-	uint32_t d[NK], pos[NK], widx[NK];
-	const uint32_t kmin_lo = (uint32_t)(unsigned long long)pr.kmin;
-#pragma unroll
-	for (int j = 0; j < RJ_P1_LOADS; j++) {
-		d[2 * j] = (uint32_t)buf[j].x - kmin_lo;     // low words: key - kmin < 2^32 is guaranteed by the caller
-		d[2 * j + 1] = (uint32_t)buf[j].z - kmin_lo;
-	}
-#pragma unroll
-	for (int k = 0; k < NK; k++)
-		pos[k] = rj_smem_inc(&sm->fill[d[k] >> pr.shift]);
-#pragma unroll
-	for (int k = 0; k < NK; k++) {
-		widx[k] = 0;
-		if (pos[k] == RJ_FLUSH - 1)
-			widx[k] = rj_smem_inc(&sm->wl_count[par]);
-	}
-	uint32_t park_mask = 0;
-#pragma unroll
-	for (int k = 0; k < NK; k++) {
-		const uint32_t p = d[k] >> pr.shift;
-		if (pos[k] < RJ_CAP)
-			sm->stage[p * RJ_CAP + pos[k]] = (uint16_t)(d[k] & pr.mask);
-		if (pos[k] == RJ_FLUSH - 1)
-			sm->worklist[par][widx[k]] = (uint16_t)p;
-		park_mask |= pos[k] >= RJ_CAP ? (1u << k) : 0u;
-	}
-	if (park_mask) {
-#pragma unroll
-		for (int k = 0; k < NK; k++)
-			if (park_mask & (1u << k))
-				rj_park(sm, pr, ((d[k] >> pr.shift) << 16) | (d[k] & pr.mask), par);
-	}
-}
-
-// generic insert phase.  FULL: every row of the tile exists (no bounds checks)
-template <bool HAS_PRESENT, bool FULL>
-__device__ static inline void rj_insert_tile(const RJSide &s, const RJParams &pr, RJP1Smem *sm, const int4 *buf, uint64_t tile,
-		int par)
-{
-	const int tid = threadIdx.x;
-	{
-		const uint64_t base_pair = tile * (RJ_P1_TILE / 2);
-		uint32_t item[RJ_P1_LOADS * 2], pos[RJ_P1_LOADS * 2];
-#pragma unroll
-		for (int j = 0; j < RJ_P1_LOADS; j++) {
-			const uint64_t pi = base_pair + (uint64_t)j * RJ_P1_THREADS + tid;
-			const unsigned long long k0 = ((unsigned long long)(unsigned)buf[j].y << 32) | (unsigned)buf[j].x;
-			const unsigned long long k1 = ((unsigned long long)(unsigned)buf[j].w << 32) | (unsigned)buf[j].z;
-			const unsigned long long d0 = k0 - (unsigned long long)pr.kmin, d1 = k1 - (unsigned long long)pr.kmin;
-			bool ok0 = d0 < pr.range, ok1 = d1 < pr.range;
-			if (!FULL) {
-				ok0 = ok0 && pi * 2 < s.n;
-				ok1 = ok1 && pi * 2 + 1 < s.n;
-			}
-			if (HAS_PRESENT) {
-				const uint32_t pw = (FULL || pi * 2 < s.n) ? (s.present[pi >> 4] >> ((pi & 15) * 2)) : 0u;
-				ok0 = ok0 && (pw & 1u);
-				ok1 = ok1 && (pw & 2u);
-			}
-			item[2 * j] = ok0 ? ((((uint32_t)d0 >> pr.shift) << 16) | ((uint32_t)d0 & pr.mask)) : RJ_NONE;
-			item[2 * j + 1] = ok1 ? ((((uint32_t)d1 >> pr.shift) << 16) | ((uint32_t)d1 & pr.mask)) : RJ_NONE;
-		}
-		// all slot requests of this thread are issued back to back (independent shared-memory atomics) ...
-#pragma unroll
-		for (int k = 0; k < RJ_P1_LOADS * 2; k++)
-			pos[k] = item[k] != RJ_NONE ? rj_smem_inc(&sm->fill[item[k] >> 16]) : RJ_NONE;
-		// ... then consumed; the two rare events (row just completed a sector / row full) are only recorded here
-		uint32_t queue_mask = 0, park_mask = 0;
-#pragma unroll
-		for (int k = 0; k < RJ_P1_LOADS * 2; k++) {
-			if (pos[k] < RJ_CAP)
-				sm->stage[(item[k] >> 16) * RJ_CAP + pos[k]] = (uint16_t)item[k];
-			queue_mask |= (pos[k] == RJ_FLUSH - 1) ? (1u << k) : 0u;
-			park_mask |= (pos[k] >= RJ_CAP && item[k] != RJ_NONE) ? (1u << k) : 0u;
-		}
-		if (queue_mask) {
-#pragma unroll
-			for (int k = 0; k < RJ_P1_LOADS * 2; k++)
-				if (queue_mask & (1u << k))
-					sm->worklist[par][rj_smem_inc(&sm->wl_count[par])] = (uint16_t)(item[k] >> 16);
-		}
-		if (park_mask) {
-#pragma unroll
-			for (int k = 0; k < RJ_P1_LOADS * 2; k++)
-				if (park_mask & (1u << k))
-					rj_park(sm, pr, item[k], par);
-		}
-	}
-}
-
-// barrier, flush the queued rows, barrier
-__device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par)
-{
-	const int tid = threadIdx.x;
-	__syncthreads();
-
-	const uint32_t nwl = sm->wl_count[par];
-	if (tid == 0) {
-		// the other parity's lists were consumed (worklist: last round's flush; parked keys: above)
-		sm->wl_count[par ^ 1] = 0;
-		sm->ovf_count[par ^ 1] = 0;
-	}
-	// flush: one lane per queued partition writes its first 16 remainders as ONE aligned 32-byte sector
-	for (uint32_t w = tid; w < nwl; w += RJ_P1_THREADS) {
-		const uint32_t p = sm->worklist[par][w];
-		const uint32_t f = min(sm->fill[p], (uint32_t)RJ_CAP);
-		uint32_t ch = sm->chunk[p];
-		if (ch == RJ_NONE || (ch & 31u) == RJ_BLOCKS_PER_CHUNK) {
-			rj_new_chunk(s, pr, sm, p);
-			ch = sm->chunk[p];
-		}
-		uint2 *row = reinterpret_cast<uint2*>(&sm->stage[p * RJ_CAP]); // 40-byte rows are 8-byte aligned
-		const uint2 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4];
-		if (ch != RJ_NONE && (ch & 31u) < RJ_BLOCKS_PER_CHUNK) {
-			int4 *dst = reinterpret_cast<int4*>(s.dst[rj_owner(s, pr, p)].pool + (size_t)(ch >> 5) * RJ_CHUNK + (ch & 31u) * RJ_FLUSH);
-			dst[0] = make_int4((int)a.x, (int)a.y, (int)b.x, (int)b.y);
-			dst[1] = make_int4((int)c.x, (int)c.y, (int)d.x, (int)d.y);
-			sm->chunk[p] = ch + 1;
-		}
-		row[0] = e; // keep the (at most 4) remainders behind the flushed sector
-		sm->fill[p] = f - RJ_FLUSH;
-	}
-	__syncthreads();
-}
-
-template <bool HAS_PRESENT>
-__device__ static inline void rj_load_tile(const RJSide &s, uint64_t tile, int4 *dst)
-{
-	const int4 *src = reinterpret_cast<const int4*>(s.keys);
-	const uint64_t npairs = s.n / 2;
-	const uint64_t base_pair = tile * (RJ_P1_TILE / 2);
-	// pull the tile this CTA will load two rounds from now into L2 (one 128-byte line per thread)
-	const uint64_t pf_first = (tile + 2ull * gridDim.x) * RJ_P1_TILE + (uint64_t)threadIdx.x * 16;
-	if (threadIdx.x < RJ_P1_TILE / 16 && pf_first + 16 <= s.n)
-		asm volatile("prefetch.global.L2 [%0];" ::"l"(s.keys + pf_first));
-	if (base_pair + RJ_P1_TILE / 2 <= npairs) {
-#pragma unroll
-		for (int j = 0; j < RJ_P1_LOADS; j++)
-			dst[j] = mdb_ldg_stream(src + base_pair + (uint64_t)j * RJ_P1_THREADS + threadIdx.x);
-	} else {
-#pragma unroll
-		for (int j = 0; j < RJ_P1_LOADS; j++) {
-			const uint64_t pi = base_pair + (uint64_t)j * RJ_P1_THREADS + threadIdx.x;
-			if (pi < npairs) {
-				dst[j] = mdb_ldg_stream(src + pi);
-			} else if (pi == npairs && (s.n & 1)) {
-				const unsigned long long last = (unsigned long long)s.keys[s.n - 1];
-				dst[j] = make_int4((int)(unsigned)last, (int)(unsigned)(last >> 32), 0, 0);
-			} else {
-				dst[j] = make_int4(0, 0, 0, 0);
-			}
-		}
-	}
-}
-
-// every partition's partial sector goes out, chunk entry counts are finalised
-__device__ static inline void rj_drain(const RJSide &s, const RJParams &pr, RJP1Smem *sm)
-{
-	for (int p = threadIdx.x; p < pr.nparts; p += RJ_P1_THREADS) {
-		const uint32_t f = min(sm->fill[p], (uint32_t)RJ_CAP);
-		const RJTarget &t = s.dst[rj_owner(s, pr, p)];
-		uint32_t ch = sm->chunk[p];
-		if (f > 0) {
-			if (ch == RJ_NONE || (ch & 31u) == RJ_BLOCKS_PER_CHUNK) {
-				rj_new_chunk(s, pr, sm, p);
-				ch = sm->chunk[p];
-			}
-			if (ch != RJ_NONE && (ch & 31u) < RJ_BLOCKS_PER_CHUNK) {
-				uint16_t *dst = t.pool + (size_t)(ch >> 5) * RJ_CHUNK + (ch & 31u) * RJ_FLUSH;
-				for (uint32_t i = 0; i < f; i++)
-					dst[i] = sm->stage[p * RJ_CAP + i];
-				t.chunk_entries[ch >> 5] = (uint16_t)((ch & 31u) * RJ_FLUSH + f);
-			}
-		} else if (ch != RJ_NONE) {
-			t.chunk_entries[ch >> 5] = (uint16_t)((ch & 31u) * RJ_FLUSH);
-		}
-	}
-	__threadfence_system(); // remote owners read these chunks after the next cross-rank barrier
-}
-
-__device__ static inline void rj_smem_init(RJP1Smem *sm)
-{
-	const int tid = threadIdx.x;
-	for (int p = tid; p < RJ_MAX_PART; p += RJ_P1_THREADS) {
-		sm->fill[p] = 0;
-		sm->chunk[p] = RJ_NONE;
-	}
-	if (tid < 2) {
-		sm->ovf_count[tid] = 0;
-		sm->wl_count[tid] = 0;
-	}
-	if (tid < RJ_MAX_RANKS)
-		sm->local_next[tid] = sm->local_end[tid] = 0;
-	__syncthreads();
-}
-
-// Pass 1, lean variant: column without NULLs/tombstones whose [min, max] lies inside the partitioned range.
-// Complete tiles run the branch-free 32-bit hot loop; the ragged tail (< one tile) is inserted key by key by CTA 0.
-__global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSide s, RJParams pr)
-{
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	RJP1Smem *sm = reinterpret_cast<RJP1Smem*>(smem_raw);
-	rj_smem_init(sm);
-
-	const uint64_t nfull = s.n / RJ_P1_TILE;
-	const int4 *src = reinterpret_cast<const int4*>(s.keys);
-	int4 buf_a[RJ_P1_LOADS], buf_b[RJ_P1_LOADS];
-	int par = 0;
-	auto load = [&](uint64_t tile, int4 *dst) {
-		const uint64_t pf_first = (tile + 2ull * gridDim.x) * RJ_P1_TILE + (uint64_t)threadIdx.x * 16;
-		if (threadIdx.x < RJ_P1_TILE / 16 && pf_first + 16 <= s.n)
-			asm volatile("prefetch.global.L2 [%0];" ::"l"(s.keys + pf_first));
-		const int4 *t = src + tile * (RJ_P1_TILE / 2) + threadIdx.x;
-#pragma unroll
-		for (int j = 0; j < RJ_P1_LOADS; j++)
-			dst[j] = mdb_ldg_stream(t + j * RJ_P1_THREADS);
-	};
-	auto round = [&](const int4 *buf) {
-		rj_round_begin(s, pr, sm, par);
-		rj_insert_tile_fast(pr, sm, buf, par);
-		rj_round_end(s, pr, sm, par);
-		par ^= 1;
-	};
-	uint64_t tile = blockIdx.x;
-	if (tile < nfull)
-		load(tile, buf_a);
-	while (tile < nfull) {
-		uint64_t next = tile + gridDim.x;
-		if (next < nfull)
-			load(next, buf_b);
-		round(buf_a);
-		tile = next;
-		if (tile >= nfull)
-			break;
-		next = tile + gridDim.x;
-		if (next < nfull)
-			load(next, buf_a);
-		round(buf_b);
-		tile = next;
-	}
-	// ragged tail and parked keys
-	bool tail_done = blockIdx.x != 0 || nfull * RJ_P1_TILE == s.n;
-	while (!tail_done || sm->ovf_count[par ^ 1] != 0) {
-		rj_round_begin(s, pr, sm, par);
-		if (!tail_done) {
-			for (uint64_t r = nfull * RJ_P1_TILE + threadIdx.x; r < s.n; r += RJ_P1_THREADS) {
-				const uint32_t d = (uint32_t)(unsigned long long)s.keys[r] - (uint32_t)(unsigned long long)pr.kmin;
-				rj_insert(sm, pr, ((d >> pr.shift) << 16) | (d & pr.mask), par);
-			}
-			tail_done = true;
-		}
-		rj_round_end(s, pr, sm, par);
-		par ^= 1;
-	}
-	rj_drain(s, pr, sm);
-}
-
-// Pass 1.  One persistent 1024-thread CTA per SM.  Keys are streamed with 128-bit loads, double-buffered in
-// registers (ping-pong, no copies).  Each key costs one shared-memory atomic (slot in its partition's staging
-// row) and one 2-byte shared store.  The thread that fills slot 16 of a row queues the partition; after the
-// round's barrier one lane per queued partition writes 16 remainders as one aligned 32-byte sector into the
-// CTA's current 512-byte chunk of that partition: DRAM only sees full-sector writes, 2 bytes per key.
-template <bool HAS_PRESENT>
-__global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition(RJSide s, RJParams pr)
-{
-	extern __shared__ __align__(16) unsigned char smem_raw[];
-	RJP1Smem *sm = reinterpret_cast<RJP1Smem*>(smem_raw);
-	const int tid = threadIdx.x;
-
-	rj_smem_init(sm);
-
-	const uint64_t ntiles = (s.n + RJ_P1_TILE - 1) / RJ_P1_TILE;
-	const uint64_t nfull = s.n / RJ_P1_TILE; // tiles [0, nfull) are complete
-	int4 buf_a[RJ_P1_LOADS], buf_b[RJ_P1_LOADS];
-	uint64_t tile = blockIdx.x;
-	int par = 0;
-	if (tile < ntiles)
-		rj_load_tile<HAS_PRESENT>(s, tile, buf_a);
-	auto round = [&](const int4 *buf, uint64_t t) {
-		rj_round_begin(s, pr, sm, par);
-		if (t < nfull) {
-			rj_insert_tile<HAS_PRESENT, true>(s, pr, sm, buf, t, par);
-		} else if (t < ntiles) {
-			rj_insert_tile<HAS_PRESENT, false>(s, pr, sm, buf, t, par);
-		}
-		rj_round_end(s, pr, sm, par);
-		par ^= 1;
-	};
-	while (tile < ntiles) {
-		uint64_t next = tile + gridDim.x;
-		if (next < ntiles)
-			rj_load_tile<HAS_PRESENT>(s, next, buf_b);
-		round(buf_a, tile);
-		tile = next;
-		if (tile >= ntiles)
-			break;
-		next = tile + gridDim.x;
-		if (next < ntiles)
-			rj_load_tile<HAS_PRESENT>(s, next, buf_a);
-		round(buf_b, tile);
-		tile = next;
-	}
-	// keys still parked by the last round(s)
-	while (sm->ovf_count[par ^ 1] != 0) // block-uniform: written before the last barrier
-		round(buf_a, ntiles);
-
-	rj_drain(s, pr, sm);
-}
 
 // exclusive scan of the per-partition chunk counts (single block, nparts <= 4096)
 __global__ void k_radix_dir_scan(RJSide s, int nparts)
@@ -600,6 +129,8 @@ static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_ta
 	s->world = arena_bases ? ctx->world : 1;
 	s->self = arena_bases ? ctx->rank : 0;
 	rj_id_policy(s->world, &s->id_batch, &s->id_low);
+	static const uint32_t hints = getenv("MDBCU_P1_HINTS") ? (uint32_t)atoi(getenv("MDBCU_P1_HINTS")) : RJ_HINT_DEFAULT;
+	s->hints = hints;
 	RJTarget &own = s->dst[s->self];
 	if (arena_bases) {
 		const RJArenaLayout l = rj_arena_layout(chunks);
@@ -627,7 +158,7 @@ static void launch_partition(mdbcu_ctx *ctx, int grid, const RJSide &s, const RJ
 {
 	if (s.present)
 		MDB_LAUNCH(ctx, k_radix_partition<true>, grid, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
-	else if (s.all_in_range && pr.range <= 0xffffffffull)
+	else if (s.all_in_range && pr.range <= 0xffffffffull && ((uintptr_t)s.keys & 31u) == 0)
 		MDB_LAUNCH(ctx, k_radix_partition_fast, grid, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
 	else
 		MDB_LAUNCH(ctx, k_radix_partition<false>, grid, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);

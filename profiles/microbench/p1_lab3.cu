@@ -1,0 +1,94 @@
+// Pass-1 laboratory, part 3: the PRODUCTION kernel (mdb_radix_pass1.cuh) run in isolation on the bench workload,
+// so variants can be timed without the rest of the library.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -I../../include -I../../midoridb_b200/csrc -o p1_lab3 p1_lab3.cu
+#include "mdb_common.cuh"
+#include "mdb_radix_types.cuh"
+#include "mdb_radix_pass1.cuh"
+
+#include <cstdio>
+#include <cstdlib>
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
+
+__global__ void k_gen(int64_t *k, uint64_t n, uint64_t domain)
+{
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+		uint64_t x = i * 0x9E3779B97F4A7C15ull + 0x1234567;
+		x ^= x >> 31; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 29; x *= 0x94D049BB133111EBull; x ^= x >> 32;
+		k[i] = (int64_t)(x % domain);
+	}
+}
+
+int main(int argc, char **argv)
+{
+	const int lg = argc > 1 ? atoi(argv[1]) : 28;
+	const uint64_t n = 1ull << lg;
+	int sms;
+	CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+	int64_t *keys;
+	CK(cudaMalloc(&keys, n * 8));
+	k_gen<<<sms * 8, 256>>>(keys, n, n);
+	const uint64_t chunks = (n / RJ_CHUNK + (uint64_t)sms * RJ_MAX_PART) * 3 / 2 + (uint64_t)sms * 8192 + 1024;
+	RJSide s;
+	memset(&s, 0, sizeof(s));
+	s.keys = keys;
+	s.n = n;
+	s.all_in_range = 1;
+	s.world = 1;
+	s.self = 0;
+	s.pool_chunks = (uint32_t)chunks;
+	s.id_batch = 8192;
+	s.id_low = 2048;
+	RJTarget &t = s.dst[0];
+	CK(cudaMalloc(&t.pool, chunks * RJ_CHUNK * 2));
+	CK(cudaMalloc(&t.pool_next, 4));
+	CK(cudaMalloc(&t.chunk_part, chunks * 2));
+	CK(cudaMalloc(&t.chunk_entries, chunks * 2));
+	CK(cudaMalloc(&t.dir_cnt, (RJ_MAX_PART + 1) * 4));
+	uint32_t *flag;
+	CK(cudaMalloc(&flag, 8));
+	CK(cudaMemset(flag, 0, 8));
+	RJParams pr;
+	memset(&pr, 0, sizeof(pr));
+	pr.kmin = 0;
+	pr.range = n;
+	pr.shift = lg - 12;
+	pr.mask = (1u << pr.shift) - 1u;
+	pr.nparts = 4096;
+	pr.part_end = 4096;
+	pr.error_flag = flag;
+	CK(cudaFuncSetAttribute(k_radix_partition_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
+	CK(cudaFuncSetAttribute(k_radix_partition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
+	cudaEvent_t e0, e1;
+	CK(cudaEventCreate(&e0));
+	CK(cudaEventCreate(&e1));
+	printf("n = 2^%d keys, %d SMs, smem %zu\n", lg, sms, sizeof(RJP1Smem));
+	for (int variant = 0; variant < 9; variant++) {
+		s.hints = variant < 8 ? (uint32_t)variant : 0;
+		float total = 0;
+		const int reps = 5;
+		for (int i = 0; i < reps + 2; i++) {
+			CK(cudaMemsetAsync(t.pool_next, 0, 4));
+			CK(cudaMemsetAsync(t.chunk_part, 0xff, chunks * 2));
+			CK(cudaMemsetAsync(t.dir_cnt, 0, (RJ_MAX_PART + 1) * 4));
+			CK(cudaEventRecord(e0));
+			if (variant < 8)
+				k_radix_partition_fast<<<sms, RJ_P1_THREADS, sizeof(RJP1Smem)>>>(s, pr);
+			else
+				k_radix_partition<false><<<sms, RJ_P1_THREADS, sizeof(RJP1Smem)>>>(s, pr);
+			CK(cudaEventRecord(e1));
+			CK(cudaDeviceSynchronize());
+			float ms;
+			CK(cudaEventElapsedTime(&ms, e0, e1));
+			if (i >= 2)
+				total += ms;
+		}
+		uint32_t h[2], used;
+		CK(cudaMemcpy(h, flag, 8, cudaMemcpyDeviceToHost));
+		CK(cudaMemcpy(&used, t.pool_next, 4, cudaMemcpyDeviceToHost));
+		printf("%s hints %d: %8.3f ms  %7.1f GB/s of keys   (error flags %u, chunk ids used %u of %llu)\n",
+				variant < 8 ? "fast   " : "generic", variant < 8 ? variant : 0, total / reps, 8.0 * n / (total / reps) / 1e6, h[0], used,
+				(unsigned long long)chunks);
+	}
+	return 0;
+}
