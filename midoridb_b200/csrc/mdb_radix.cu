@@ -5,9 +5,9 @@
 // replaces _join_nested_loop_tbl2tbl (src/engine/executor_select.c:1076) + proc_groupby_clause (:1526):
 // result(k) = cntA[k] * cntB[k]; no candidate pair and no joined row is ever materialised.
 //
-//   pass 1  k_radix_partition   streams the 8-byte keys ONCE, writes 2-byte remainders into per-partition
-//                               512-byte chunks (partition = high bits of key - kmin, <= 4096 partitions);
-//   (dir)   k_radix_dir_*       counting sort of chunk ids by partition (a few microseconds);
+//   pass 1  k_radix_partition   streams the 8-byte keys ONCE and appends 2-byte remainders to per-partition
+//                               streams (partition = high bits of key - kmin, <= 4096 partitions);
+//   (ship)  k_radix_ship        multi-GPU plans only: push the streams of the partitions a peer owns over NVLink;
 //   pass 2  k_radix_joincount   per partition: both sides' remainders -> packed 4- or 8-bit counters in shared
 //                               memory, checksum against the number of remainders, multiply, emit groups.
 //
@@ -26,132 +26,50 @@ static bool col_all_present(const mdbcu_table *t, int col)
 }
 
 #include "mdb_radix_pass1.cuh"
-
-
-// exclusive scan of the per-partition chunk counts (single block, nparts <= 4096)
-__global__ void k_radix_dir_scan(RJSide s, int nparts)
-{
-	__shared__ uint64_t warp_tot[33];
-	uint64_t carry = 0;
-	for (int base = 0; base < nparts + 1; base += blockDim.x) {
-		int i = base + threadIdx.x;
-		uint64_t v = i < nparts ? s.dst[s.self].dir_cnt[i] : 0;
-		uint64_t incl = v;
-		int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-		for (int o = 1; o < 32; o <<= 1) {
-			uint64_t n = __shfl_up_sync(0xffffffffu, incl, o);
-			if (lane >= o)
-				incl += n;
-		}
-		if (lane == 31)
-			warp_tot[warp] = incl;
-		__syncthreads();
-		if (warp == 0) {
-			uint64_t w = lane < (blockDim.x >> 5) ? warp_tot[lane] : 0, wi = w;
-			for (int o = 1; o < 32; o <<= 1) {
-				uint64_t n = __shfl_up_sync(0xffffffffu, wi, o);
-				if (lane >= o)
-					wi += n;
-			}
-			warp_tot[lane] = wi - w;
-			if (lane == 31)
-				warp_tot[32] = wi;
-		}
-		__syncthreads();
-		if (i < nparts + 1)
-			s.dir_off[i] = carry + warp_tot[warp] + incl - v;
-		carry += warp_tot[32];
-		__syncthreads();
-	}
-}
-
 #include "mdb_radix_pass2.cuh"
 #include "mdb_radix_dist.cuh"
 
-// chunk-id reservation sizes: a CTA needs at most one fresh chunk per owned partition at start-up
-static void rj_id_policy(int world, uint32_t *batch, uint32_t *low)
+// entries one partition's main stream can hold: twice the average (uniform keys fill half of it; a partition that
+// receives more than twice its share sets RJ_ERR_STREAM and the general operators take over)
+static uint32_t rj_stream_cap(uint64_t rows, int nparts)
 {
-	*batch = world == 1 ? 8192u : std::max(1024u, 2u * RJ_MAX_PART / (uint32_t)world);
-	*low = *batch / 4;
+	uint64_t cap = 2 * (rows / (uint64_t)nparts) + 2048;
+	cap = (cap + 63) & ~63ull; // whole 128-byte lines
+	return (uint32_t)std::min<uint64_t>(cap, 0x7fffffc0ull);
 }
 
-// chunks one owner's pool must hold: data chunks (with slack for imbalance) + one ragged chunk per
-// (source CTA, owned partition) + ids abandoned at refills + one reserve per (source CTA, owner)
-static uint64_t rj_pool_chunks(uint64_t rows_for_owner, int world, int grid)
-{
-	uint32_t batch, low;
-	rj_id_policy(world, &batch, &low);
-	uint64_t chunks = rows_for_owner / RJ_CHUNK + (uint64_t)grid * RJ_MAX_PART;
-	chunks += chunks / 2 + (uint64_t)world * grid * batch + 1024;
-	return chunks;
-}
-
-// byte layout of one side inside an exchange arena (identical on every rank)
-struct RJArenaLayout {
-	size_t pool, chunk_part, chunk_entries, dir_cnt, pool_next, bytes;
-};
-
-static RJArenaLayout rj_arena_layout(uint64_t chunks)
-{
-	auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-	RJArenaLayout l;
-	l.pool = 0;
-	l.chunk_part = up(l.pool + chunks * RJ_CHUNK * sizeof(uint16_t));
-	l.chunk_entries = up(l.chunk_part + chunks * sizeof(uint16_t));
-	l.dir_cnt = up(l.chunk_entries + chunks * sizeof(uint16_t));
-	l.pool_next = up(l.dir_cnt + (RJ_MAX_PART + 1) * sizeof(uint32_t));
-	l.bytes = up(l.pool_next + 256);
-	return l;
-}
-
-static void rj_target_at(RJTarget *t, void *base, const RJArenaLayout &l)
-{
-	char *b = (char*)base;
-	t->pool = (uint16_t*)(b + l.pool);
-	t->chunk_part = (uint16_t*)(b + l.chunk_part);
-	t->chunk_entries = (uint16_t*)(b + l.chunk_entries);
-	t->dir_cnt = (uint32_t*)(b + l.dir_cnt);
-	t->pool_next = (uint32_t*)(b + l.pool_next);
-}
-
-// arena_bases == nullptr: all chunks stay on this GPU (single-GPU plan, or NCCL exchange afterwards);
-// otherwise dst[r] points into rank r's arena (at byte offset arena_off) and pass 1 writes over NVLink
-static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_table *t, int col, int grid, uint64_t chunks,
-		void *const *arena_bases, size_t arena_off)
+static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_table *t, int col, int grid, int nparts, uint32_t cap)
 {
 	memset(s, 0, sizeof(*s));
 	s->keys = t->cols[col].data;
 	s->present = col_all_present(t, col) ? nullptr : t->cols[col].present;
 	s->n = t->n_slots;
-	if (chunks >= (1ull << 27))
-		return MDBCU_EUNSUPPORTED;
-	s->pool_chunks = (uint32_t)chunks;
-	s->world = arena_bases ? ctx->world : 1;
-	s->self = arena_bases ? ctx->rank : 0;
-	rj_id_policy(s->world, &s->id_batch, &s->id_low);
 	static const uint32_t hints = getenv("MDBCU_P1_HINTS") ? (uint32_t)atoi(getenv("MDBCU_P1_HINTS")) : RJ_HINT_DEFAULT;
 	s->hints = hints;
-	RJTarget &own = s->dst[s->self];
-	if (arena_bases) {
-		const RJArenaLayout l = rj_arena_layout(chunks);
-		for (int r = 0; r < ctx->world; r++)
-			rj_target_at(&s->dst[r], (char*)arena_bases[r] + arena_off, l);
-	} else {
-		MDB_TRY(tmp.alloc(&own.pool, chunks * RJ_CHUNK));
-		MDB_TRY(tmp.alloc(&own.pool_next, 1));
-		MDB_TRY(tmp.alloc(&own.chunk_part, chunks));
-		MDB_TRY(tmp.alloc(&own.chunk_entries, chunks));
-		MDB_TRY(tmp.alloc(&own.dir_cnt, RJ_MAX_PART + 1));
-	}
-	s->pool = own.pool;
-	MDB_TRY(tmp.alloc(&s->dir_fill, RJ_MAX_PART + 1));
-	MDB_TRY(tmp.alloc(&s->dir_off, RJ_MAX_PART + 2));
-	MDB_TRY(tmp.alloc(&s->dir, chunks));
-	CUDA_TRY(ctx, cudaMemsetAsync(own.pool_next, 0, sizeof(uint32_t), ctx->stream));
-	CUDA_TRY(ctx, cudaMemsetAsync(own.chunk_part, 0xff, chunks * sizeof(uint16_t), ctx->stream)); // 0xffff = never allocated
-	CUDA_TRY(ctx, cudaMemsetAsync(own.dir_cnt, 0, (RJ_MAX_PART + 1) * sizeof(uint32_t), ctx->stream));
-	CUDA_TRY(ctx, cudaMemsetAsync(s->dir_fill, 0, (RJ_MAX_PART + 1) * sizeof(uint32_t), ctx->stream));
+	s->cap = cap;
+	s->tail_cap = (uint32_t)grid * RJ_FLUSH; // every CTA leaves at most 15 remainders per partition
+	if ((uint64_t)nparts * cap >= (1ull << 40))
+		return MDBCU_EUNSUPPORTED;
+	MDB_TRY(tmp.alloc(&s->stream, (size_t)nparts * cap));
+	MDB_TRY(tmp.alloc(&s->tail, (size_t)nparts * s->tail_cap));
+	MDB_TRY(tmp.alloc(&s->cursor, 2 * RJ_MAX_PART));
+	s->tail_cursor = s->cursor + RJ_MAX_PART;
+	CUDA_TRY(ctx, cudaMemsetAsync(s->cursor, 0, 2 * RJ_MAX_PART * sizeof(uint32_t), ctx->stream));
 	return MDBCU_OK;
+}
+
+// pass 2 input of a single-GPU plan: the local streams
+static void rj_runs_local(RJRuns *r, const RJSide &s)
+{
+	memset(r, 0, sizeof(*r));
+	r->nsrc = 1;
+	r->cap = s.cap;
+	r->tail_cap = s.tail_cap;
+	r->stream[0] = s.stream;
+	r->tail[0] = s.tail;
+	r->cursor[0] = s.cursor;
+	r->tail_cursor[0] = s.tail_cursor;
+	r->first[0] = 0;
 }
 
 static void launch_partition(mdbcu_ctx *ctx, int grid, const RJSide &s, const RJParams &pr)
@@ -184,7 +102,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		return MDBCU_EUNSUPPORTED;
 	if (dist) {
 		// every rank must take the same decisions: use the bounds over ALL shards
-		if (!ca.gstats_ok || !cb.gstats_ok)
+		if (!ca.gstats_ok || !cb.gstats_ok || !ta->global_slots || !tb->global_slots)
 			return mdb_fail(ctx, MDBCU_EERROR, "distributed plan: call mdbcu_table_sync_stats on every sharded table first");
 		ca.imin = ca.gmin;
 		ca.imax = ca.gmax;
@@ -235,26 +153,14 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	PhaseClock clock(ctx);
 	DevTemp tmp(ctx);
 	const int grid1 = ctx->num_sms;
+	const int W = dist ? ctx->world : 1, me = dist ? ctx->rank : 0;
 	RJSide sa, sb;
 	RJParams pr;
-	// multi-GPU plans: pass 1 writes every chunk straight into the owner GPU's arena over NVLink (CUDA IPC);
-	// MDBCU_EXCHANGE=nccl selects the staged variant instead (partition locally, then a grouped send/recv)
-	static const bool use_nccl_exchange = getenv("MDBCU_EXCHANGE") && strcmp(getenv("MDBCU_EXCHANGE"), "nccl") == 0;
-	const bool p2p = dist && !use_nccl_exchange;
-	if (p2p) {
-		if (!ta->global_slots || !tb->global_slots)
-			return mdb_fail(ctx, MDBCU_EERROR, "distributed plan: call mdbcu_table_sync_stats on every sharded table first");
-		const uint64_t ca_chunks = rj_pool_chunks(ta->global_slots / ctx->world + 1, ctx->world, grid1);
-		const uint64_t cb_chunks = rj_pool_chunks(tb->global_slots / ctx->world + 1, ctx->world, grid1);
-		const RJArenaLayout la = rj_arena_layout(ca_chunks), lb = rj_arena_layout(cb_chunks);
-		void *bases[MDB_MAX_RANKS];
-		MDB_TRY(mdb_comm_arena(ctx, la.bytes + lb.bytes, bases));
-		MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, ca_chunks, bases, 0));
-		MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, cb_chunks, bases, la.bytes));
-	} else {
-		MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, rj_pool_chunks(ta->n_slots, 1, grid1), nullptr, 0));
-		MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, rj_pool_chunks(tb->n_slots, 1, grid1), nullptr, 0));
-	}
+	// stream capacities must be identical on every rank (the arena slots mirror the local layout)
+	const uint32_t cap_a = rj_stream_cap(dist ? (ta->global_slots + W - 1) / W : ta->n_slots, nparts);
+	const uint32_t cap_b = rj_stream_cap(dist ? (tb->global_slots + W - 1) / W : tb->n_slots, nparts);
+	MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, nparts, cap_a));
+	MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, nparts, cap_b));
 	sa.all_in_range = ca.imin >= kmin && ca.imax <= kmax;
 	sb.all_in_range = cb.imin >= kmin && cb.imax <= kmax;
 	pr.kmin = kmin;
@@ -262,19 +168,62 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	pr.shift = shift;
 	pr.mask = (1u << shift) - 1u;
 	pr.nparts = nparts;
-	pr.part_first = 0;
-	pr.part_end = nparts;
-	if (dist) {
-		pr.part_first = (int)((uint64_t)ctx->rank * nparts / ctx->world);
-		pr.part_end = (int)((uint64_t)(ctx->rank + 1) * nparts / ctx->world);
-	}
+	pr.part_first = (int)((uint64_t)me * nparts / W);
+	pr.part_end = (int)((uint64_t)(me + 1) * nparts / W);
 	uint32_t *d_flags; // [0] error flags, [1] partition counter
-	unsigned long long *d_cursor;
+	unsigned long long *d_cursor; // [0] groups emitted, [1] bytes pushed to peers
 	MDB_TRY(tmp.alloc(&d_flags, 2));
-	MDB_TRY(tmp.alloc(&d_cursor, 1));
+	MDB_TRY(tmp.alloc(&d_cursor, 2));
 	CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint32_t), ctx->stream));
-	CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
 	pr.error_flag = d_flags;
+
+	RJRuns ra, rb;
+	rj_runs_local(&ra, sa);
+	rj_runs_local(&rb, sb);
+	RJShip ship_a, ship_b;
+	if (dist && W > 1) {
+		// arena of every rank: [side A: W slots][side B: W slots]; slot s receives what rank s pushes
+		const uint32_t pown = (uint32_t)((nparts + W - 1) / W) + 1;
+		const RJSlotLayout la = rj_slot_layout(pown, sa.cap, sa.tail_cap), lb = rj_slot_layout(pown, sb.cap, sb.tail_cap);
+		void *bases[MDB_MAX_RANKS];
+		MDB_TRY(mdb_comm_arena(ctx, (la.bytes + lb.bytes) * (size_t)W, bases));
+		auto fill = [&](RJShip *sh, RJRuns *r, const RJSlotLayout &l, size_t side_off) {
+			memset(sh, 0, sizeof(*sh));
+			sh->world = W;
+			sh->self = me;
+			sh->nparts = nparts;
+			sh->shipped_bytes = d_cursor + 1;
+			const uint16_t *own_stream = r->stream[0], *own_tail = r->tail[0]; // rj_runs_local put them at index 0
+			const uint32_t *own_cursor = r->cursor[0], *own_tail_cursor = r->tail_cursor[0];
+			r->nsrc = W;
+			for (int o = 0; o < W; o++) {
+				// slot [me] of rank o's arena: where this rank pushes to
+				char *dst = (char*)bases[o] + side_off + (size_t)me * l.bytes;
+				sh->main[o] = (uint16_t*)(dst + l.main);
+				sh->tail[o] = (uint16_t*)(dst + l.tail);
+				sh->cursor[o] = (uint32_t*)(dst + l.cursor);
+				sh->tail_cursor[o] = (uint32_t*)(dst + l.tail_cursor);
+				if (o == me) { // source `me` of pass 2 = the local streams, indexed by p
+					r->stream[o] = own_stream;
+					r->tail[o] = own_tail;
+					r->cursor[o] = own_cursor;
+					r->tail_cursor[o] = own_tail_cursor;
+					r->first[o] = 0;
+					continue;
+				}
+				// slot [o] of this rank's arena: what rank o pushed here
+				const char *src = (const char*)bases[me] + side_off + (size_t)o * l.bytes;
+				r->stream[o] = (const uint16_t*)(src + l.main);
+				r->tail[o] = (const uint16_t*)(src + l.tail);
+				r->cursor[o] = (const uint32_t*)(src + l.cursor);
+				r->tail_cursor[o] = (const uint32_t*)(src + l.tail_cursor);
+				r->first[o] = (uint32_t)pr.part_first;
+			}
+		};
+		fill(&ship_a, &ra, la, 0);
+		fill(&ship_b, &rb, lb, la.bytes * (size_t)W);
+	}
 
 	// upper bound of groups this rank can emit: one per key of the partitions it owns
 	uint64_t cap_groups = std::min<uint64_t>((uint64_t)(pr.part_end - pr.part_first) << shift, range);
@@ -301,64 +250,53 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
-		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 2 * RJ_DESC_CAP * (int)sizeof(RJDesc)));
-		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536 + 2 * RJ_DESC_CAP * (int)sizeof(RJDesc)));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
 		attr_done = true;
 	}
 
-	if (p2p) {
-		// every rank's arena must be reset before any peer starts writing into it
-		clock.begin(6);
-		MDB_TRY(mdb_comm_barrier_or(ctx, d_flags, nullptr));
-	}
 	clock.begin(1);
 	launch_partition(ctx, grid1, sa, pr);
 	launch_partition(ctx, grid1, sb, pr);
-	if (p2p) {
-		// all remote stores have landed once every rank's pass 1 has completed; error flags are shared so that
-		// every rank takes the same exit
+	if (dist && W > 1) {
+		// every rank must be done reading its arena (previous query) before any peer pushes into it
 		clock.begin(6);
+		MDB_TRY(mdb_comm_barrier_or(ctx, d_flags, nullptr));
+		MDB_LAUNCH(ctx, k_radix_ship, ctx->num_sms * 2, 512, 0, sa, ship_a);
+		MDB_LAUNCH(ctx, k_radix_ship, ctx->num_sms * 2, 512, 0, sb, ship_b);
+		// all pushes have landed once every rank's ship kernels have completed; error flags are shared so that every
+		// rank takes the same exit
 		uint32_t any = 0;
 		MDB_TRY(mdb_comm_barrier_or(ctx, d_flags, &any));
 		if (any)
 			return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "distributed radix join: pass 1 failed on some rank (flags %u: "
-					"1 = chunk pool exhausted, 4 = extreme skew)", any);
-	}
-	clock.begin(7);
-	MDB_LAUNCH(ctx, k_radix_dir_scan, 1, 1024, 0, sa, nparts);
-	MDB_LAUNCH(ctx, k_radix_dir_scan, 1, 1024, 0, sb, nparts);
-	MDB_LAUNCH(ctx, k_radix_dir_fill, ctx->num_sms * 4, 256, 0, sa);
-	MDB_LAUNCH(ctx, k_radix_dir_fill, ctx->num_sms * 4, 256, 0, sb);
-	uint64_t exchanged = 0;
-	if (dist && !p2p) {
-		clock.begin(6);
-		RJSide *both[2] = {&sa, &sb};
-		MDB_TRY(rj_exchange(ctx, tmp, &pr, both, &exchanged));
+					"1 = a partition received more than twice its share of the keys, 4 = extreme skew)", any);
 	}
 	clock.begin(2);
 
 	// 4-bit counters (two CTAs per SM) when keys are mostly unique per side, 8-bit otherwise; a wrapped
 	// counter is detected by the checksum and the pass is repeated one width up before giving up
 	const uint64_t D = 1ull << shift;
-	bool try4 = std::max(ta->n_slots, tb->n_slots) <= 2 * range;
+	const uint64_t rows_a = dist ? ta->global_slots : ta->n_slots, rows_b = dist ? tb->global_slots : tb->n_slots;
+	bool try4 = std::max(rows_a, rows_b) <= 2 * range;
 	uint64_t ngroups = 0;
 	uint32_t flags = 0;
 	for (int attempt = try4 ? 0 : 1; attempt < 2; attempt++) {
 		const int bitsw = attempt == 0 ? 4 : 8;
-		const size_t smem2 = 2 * (size_t)std::max<uint64_t>(1, D * bitsw / 32) * sizeof(uint32_t) + 2 * RJ_DESC_CAP * sizeof(RJDesc);
+		const size_t smem2 = 2 * (size_t)std::max<uint64_t>(1, D * bitsw / 32) * sizeof(uint32_t);
 		const int grid2 = std::max(1, std::min(pr.part_end - pr.part_first, ctx->num_sms * (bitsw == 4 ? 2 : 1)));
 		if (bitsw == 4)
-			MDB_LAUNCH(ctx, (k_radix_joincount<4, 512>), grid2, 512, smem2, sa, sb, pr, out, d_flags + 1);
+			MDB_LAUNCH(ctx, (k_radix_joincount<4, 512>), grid2, 512, smem2, ra, rb, pr, out, d_flags + 1);
 		else
-			MDB_LAUNCH(ctx, (k_radix_joincount<8, 1024>), grid2, 1024, smem2, sa, sb, pr, out, d_flags + 1);
+			MDB_LAUNCH(ctx, (k_radix_joincount<8, 1024>), grid2, 1024, smem2, ra, rb, pr, out, d_flags + 1);
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess)
 			return mdb_fail(ctx, MDBCU_ECUDA, "radix join launch failed: %s", cudaGetErrorString(e));
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar, d_cursor, sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar + 1, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar, d_cursor, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar + 2, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 		ngroups = ctx->h_scalar[0];
-		flags = (uint32_t)(ctx->h_scalar[1] & 0xffffffffu);
+		flags = (uint32_t)(ctx->h_scalar[2] & 0xffffffffu);
 		if (flags != RJ_ERR_COUNTER || attempt == 1)
 			break;
 		// a 4-bit counter wrapped: repeat pass 2 with 8-bit counters (the partitioned remainders are still valid)
@@ -370,10 +308,10 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		if (dist)
 			return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "distributed radix join: key multiplicity or skew beyond the counter width "
 					"(flags %u); the general operators are single-GPU only", flags);
-		return MDBCU_EUNSUPPORTED; // heavy duplicates / skew / pool exhaustion: the general operators redo the query
+		return MDBCU_EUNSUPPORTED; // heavy duplicates / skew / stream overflow: the general operators redo the query
 	}
 	res->nrows = ngroups;
-	ctx->stats.exchange_bytes = exchanged;
+	ctx->stats.exchange_bytes = ctx->h_scalar[1];
 
 	ctx->stats.algorithmic_bytes = 8ull * (ta->n_slots + tb->n_slots) + 8ull * plan->n_out * ngroups;
 	ctx->stats.dominant_ms = ctx->stats.phase_ms[1] + ctx->stats.phase_ms[2];

@@ -1,22 +1,21 @@
-// mdb_radix_pass1.cuh - pass 1 of the radix join: stream the keys once, scatter 2-byte remainders into
-// per-partition 512-byte chunks.  Included by mdb_radix.cu (structs RJSide/RJParams/RJTarget are defined there).
+// mdb_radix_pass1.cuh - pass 1 of the radix join: stream the keys once, append their 2-byte remainders to the
+// per-partition streams (mdb_radix_types.cuh).  Included by mdb_radix.cu.
 //
 // One persistent 1024-thread CTA per SM.  Per round every thread takes 8 keys:
 //   insert   partition = (key - kmin) >> shift; ONE shared-memory atomic hands out a slot of the partition's
 //            40-byte staging row, ONE 2-byte shared store writes the remainder.  The lane that fills slot 16 puts
 //            the partition on ITS WARP's worklist (position from a ballot: no atomics, no CTA-wide queue);
 //   barrier  (all remainders of the queued rows are in shared memory)
-//   flush    every warp flushes its own worklist, one lane per row: the first 16 remainders leave as ONE
-//            256-bit store = one aligned 32-byte sector of the CTA's current chunk of that partition; fresh chunk
-//            ids are handed out warp-wide (one shared-memory atomic per warp, ids reserved in bulk by thread 0);
+//   flush    every warp flushes its own worklist, one lane per row: one global atomic on the partition's cursor
+//            gives the position, the first 16 remainders leave as ONE 256-bit store = one aligned 32-byte sector;
 //   barrier
-// What the measurements behind this shape say (profiles/microbench/p1_lab*.cu, B200, 2^28 keys): 256-bit key loads
-// stream at 6.4 TB/s where 128-bit loads reach 4.7; slot atomics + stores cost 0.05 ms on top of the loads;
-// a CTA-wide worklist fed by same-address atomics costs 0.15 ms more than ballots; scattered sector stores 0.2 ms.
-
-#ifndef RJ_LAB
-#define RJ_LAB 0                   // profiles/microbench/p1_lab3.cu sets bits to knock out parts of the kernel (timing only)
-#endif
+// Measurements behind this shape (profiles/microbench/p1_lab*.cu and profiles/p1_lab_*.txt, B200, 2^28 keys):
+//   * 256-bit key loads stream at 6.4 TB/s where 128-bit loads reach 4.7;
+//   * a CTA that needs more than 195 KiB of shared memory pushes the SM into its largest carve-out, the L1 that
+//     is left cannot hold the key loads in flight and the whole kernel loses 25%;
+//   * slot atomics + 2-byte stores cost 0.05 ms on top of the loads; a CTA-wide worklist fed by same-address
+//     atomics costs 0.15 ms more than ballots; stores that complete whole 128-byte lines are 0.13 ms cheaper than
+//     scattered 32-byte sectors (hence shared per-partition streams instead of per-CTA chunks).
 
 #define RJ_P1_WARPS (RJ_P1_THREADS / 32)
 #define RJ_P1_KEYS 8               // keys per thread per round
@@ -26,28 +25,17 @@
 #define RJ_HINT_PREFETCH 1u        // prefetch.global.L2 two tiles ahead
 #define RJ_HINT_LOAD_EVICT_FIRST 2u
 #define RJ_HINT_STORE_EVICT_LAST 4u
-#define RJ_HINT_DEFAULT 0u         // (MDBCU_P1_HINTS overrides; see profiles/ for the sweep)
+#define RJ_HINT_DEFAULT 0u         // (MDBCU_P1_HINTS overrides; none of them pays once the L1 is large enough)
 
 struct RJP1Smem {
 	uint16_t stage[RJ_MAX_PART * RJ_CAP];     // 160 KiB: 20 two-byte slots per partition
-	uint32_t fill[RJ_MAX_PART / 2];           // slots handed out since the last flush (may overshoot RJ_CAP): 16 bits per partition
-	uint32_t chunk[RJ_MAX_PART];              // current chunk of this CTA: chunk id * 32 + sectors used, or RJ_NONE
+	uint32_t fill[RJ_MAX_PART];               // slots handed out since the last flush (may overshoot RJ_CAP)
 	uint16_t worklist[RJ_P1_WARPS][RJ_WL_CAP]; // per warp: partitions whose 16th slot it filled this round
 	uint32_t ovf[2][RJ_OVF_CAP];              // (partition << 16 | remainder) waiting for the next round
 	uint32_t ovf_count[2];
-	uint32_t local_next[RJ_MAX_RANKS];        // chunk ids reserved by this CTA in each owner's pool
-	uint32_t local_end[RJ_MAX_RANKS];         // (refilled in bulk by thread 0)
 };
 
-// Measured (profiles/microbench/p1_lab4.cu, PAD sweep): a CTA that needs more than 195 KiB pushes the SM into its
-// largest shared-memory carve-out, the L1 that remains cannot hold the key loads in flight and the kernel loses 25%.
 static_assert(sizeof(RJP1Smem) <= 195 * 1024, "pass-1 shared memory must stay inside the 196 KiB carve-out");
-
-// slot counters: two partitions share a 32-bit word
-__device__ __forceinline__ uint32_t rj_fill_get(const RJP1Smem *sm, uint32_t p)
-{
-	return (sm->fill[p >> 1] >> ((p & 1u) << 4)) & 0xffffu;
-}
 
 // plain shared-memory atomic: kept in PTX so the compiler does not expand it into warp-aggregation code
 __device__ __forceinline__ uint32_t rj_smem_add(uint32_t *p, uint32_t v)
@@ -57,27 +45,10 @@ __device__ __forceinline__ uint32_t rj_smem_add(uint32_t *p, uint32_t v)
 	return old;
 }
 
-__device__ __forceinline__ uint32_t rj_smem_inc(uint32_t *p)
-{
-	return rj_smem_add(p, 1u);
-}
-
 // hand out the next slot of partition p's staging row
 __device__ __forceinline__ uint32_t rj_fill_claim(RJP1Smem *sm, uint32_t p)
 {
-	const uint32_t sh = (p & 1u) << 4;
-	return (rj_smem_add(&sm->fill[p >> 1], 1u << sh) >> sh) & 0xffffu;
-}
-
-// after a flush: the count drops from `have` to `keep` (atomic: the neighbour's half of the word may change concurrently)
-__device__ __forceinline__ void rj_fill_drop(RJP1Smem *sm, uint32_t p, uint32_t have, uint32_t keep)
-{
-	rj_smem_add(&sm->fill[p >> 1], (keep - have) << ((p & 1u) << 4));
-}
-
-__device__ __forceinline__ void rj_global_red_inc(uint32_t *p)
-{
-	asm volatile("red.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
+	return rj_smem_add(&sm->fill[p], 1u);
 }
 
 __device__ __forceinline__ uint32_t rj_lanemask_lt()
@@ -120,59 +91,10 @@ __device__ __forceinline__ void rj_load_keys256(const void *p, uint32_t *lo, boo
 	lo[3] = t[6];
 }
 
-// rank that owns partition p: ranks own the contiguous blocks [r*P/W, (r+1)*P/W)
-__device__ __forceinline__ int rj_owner(const RJSide &s, const RJParams &pr, uint32_t p)
-{
-	return s.world == 1 ? 0 : (int)(((p + 1) * (uint32_t)s.world - 1) / (uint32_t)pr.nparts);
-}
-
-// book-keeping of a freshly allocated chunk `cid` that replaces `old` (chunk id * 32 + 16, or RJ_NONE) for partition p
-__device__ __forceinline__ bool rj_open_chunk(const RJSide &s, const RJParams &pr, const RJTarget &t, uint32_t p, uint32_t old, uint32_t cid)
-{
-	if (cid >= s.pool_chunks) {
-		atomicOr(pr.error_flag, RJ_ERR_POOL);
-		return false;
-	}
-	if (RJ_LAB & 4)
-		return true;
-	if (old != RJ_NONE)
-		t.chunk_entries[old >> 5] = RJ_CHUNK; // a chunk is only replaced when all its sectors are written
-	t.chunk_part[cid] = (uint16_t)p;
-	rj_global_red_inc(&t.dir_cnt[p]);
-	return true;
-}
-
-// single-thread allocation (drain): ids come from the CTA's reserved range in the owner's pool
-__device__ static inline void rj_new_chunk(const RJSide &s, const RJParams &pr, RJP1Smem *sm, uint32_t p)
-{
-	const int o = rj_owner(s, pr, p);
-	const RJTarget &t = s.dst[o];
-	uint32_t cid = rj_smem_inc(&sm->local_next[o]);
-	if (cid >= sm->local_end[o])
-		cid = atomicAdd(t.pool_next, 1u);
-	if (rj_open_chunk(s, pr, t, p, sm->chunk[p], cid))
-		sm->chunk[p] = cid << 5;
-}
-
-// thread 0 tops the CTA's id ranges up with ONE global (for a remote owner: NVLink) atomic per id_batch chunks
-// while the other threads insert keys, so that no flush waits on L2 or on the link
-__device__ static inline void rj_refill_ids(const RJSide &s, RJP1Smem *sm)
-{
-	for (int o = 0; o < s.world; o++) {
-		if (sm->local_end[o] - min(sm->local_next[o], sm->local_end[o]) < s.id_low) {
-			const uint32_t base = atomicAdd(s.dst[o].pool_next, s.id_batch);
-			sm->local_next[o] = base;
-			sm->local_end[o] = base + s.id_batch; // ids left in the old range stay unused (chunk_part 0xffff)
-		}
-	}
-}
-
 __device__ static inline void rj_park(RJP1Smem *sm, const RJParams &pr, uint32_t item, int par)
 {
 	// staging row full until this round's flush: the key waits one round
-	if (RJ_LAB & 1)
-		return;
-	const uint32_t o = rj_smem_inc(&sm->ovf_count[par]);
+	const uint32_t o = rj_smem_add(&sm->ovf_count[par], 1u);
 	if (o < RJ_OVF_CAP)
 		sm->ovf[par][o] = item;
 	else
@@ -201,14 +123,11 @@ __device__ __forceinline__ void rj_insert_ws(RJP1Smem *sm, const RJParams &pr, u
 		rj_park(sm, pr, item, par);
 }
 
-// start of a round: id ranges are topped up, keys parked by the previous round go first (their rows were flushed since)
-__device__ static inline void rj_round_begin(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par, uint32_t &wl_n)
+// keys parked by the previous round are inserted again (their rows were flushed since)
+__device__ static inline void rj_reinsert_parked(const RJParams &pr, RJP1Smem *sm, int par, uint32_t &wl_n)
 {
 	const uint32_t tid = threadIdx.x;
-	wl_n = 0;
-	if (tid == 0)
-		rj_refill_ids(s, sm);
-	const uint32_t novf = (RJ_LAB & 1) ? 0u : min(sm->ovf_count[par ^ 1], (uint32_t)RJ_OVF_CAP);
+	const uint32_t novf = min(sm->ovf_count[par ^ 1], (uint32_t)RJ_OVF_CAP);
 	for (uint32_t i0 = tid & ~31u; i0 < novf; i0 += RJ_P1_THREADS) { // warp-uniform trip count
 		const uint32_t i = i0 + (tid & 31u);
 		const bool valid = i < novf;
@@ -216,23 +135,26 @@ __device__ static inline void rj_round_begin(const RJSide &s, const RJParams &pr
 	}
 }
 
-// 8 keys per thread whose partition/remainder are already packed as (partition << 16 | remainder); RJ_NONE = no key.
+// 8 keys per thread.  PACKED: item = (partition << 16 | remainder), RJ_NONE = no key (generic kernel);
+// otherwise item = key - kmin and every item is a key (lean kernel).
 // All slot requests of a thread are issued back to back (independent shared-memory atomics), then consumed.
-template <bool ALL_VALID>
+template <bool PACKED>
 __device__ __forceinline__ void rj_insert_items(RJP1Smem *sm, const RJParams &pr, const uint32_t *item, int par, uint32_t &wl_n)
 {
+	constexpr bool ALL_VALID = !PACKED;
+	const int pshift = PACKED ? 16 : pr.shift;
 	uint32_t pos[RJ_P1_KEYS];
 #pragma unroll
 	for (int k = 0; k < RJ_P1_KEYS; k++)
-		pos[k] = (ALL_VALID || item[k] != RJ_NONE) ? rj_fill_claim(sm, item[k] >> 16) : RJ_NONE;
+		pos[k] = (ALL_VALID || item[k] != RJ_NONE) ? rj_fill_claim(sm, item[k] >> pshift) : RJ_NONE;
 	const uint32_t lt = rj_lanemask_lt();
 	uint16_t *wl = sm->worklist[threadIdx.x >> 5];
-	uint32_t park_mask = 0;
+	uint32_t worst = 0; // largest slot handed to this thread (+1 with holes, so that RJ_NONE counts as 0)
 #pragma unroll
 	for (int k = 0; k < RJ_P1_KEYS; k++) {
-		const uint32_t p = item[k] >> 16;
+		const uint32_t p = item[k] >> pshift;
 		if (pos[k] < RJ_CAP)
-			sm->stage[p * RJ_CAP + pos[k]] = (uint16_t)item[k];
+			sm->stage[p * RJ_CAP + pos[k]] = (uint16_t)(PACKED ? item[k] : item[k] & pr.mask);
 		const bool done = pos[k] == RJ_FLUSH - 1;
 		const uint32_t bal = __ballot_sync(0xffffffffu, done);
 		if (done) {
@@ -241,13 +163,13 @@ __device__ __forceinline__ void rj_insert_items(RJP1Smem *sm, const RJParams &pr
 				wl[idx] = (uint16_t)p;
 		}
 		wl_n += __popc(bal);
-		park_mask |= (pos[k] >= RJ_CAP && (ALL_VALID || item[k] != RJ_NONE)) ? (1u << k) : 0u;
+		worst = max(worst, ALL_VALID ? pos[k] : pos[k] + 1u);
 	}
-	if (park_mask) {
+	if (worst >= (ALL_VALID ? RJ_CAP : RJ_CAP + 1u)) { // rare: some row was full
 #pragma unroll
 		for (int k = 0; k < RJ_P1_KEYS; k++)
-			if (park_mask & (1u << k))
-				rj_park(sm, pr, item[k], par);
+			if (pos[k] >= RJ_CAP && (ALL_VALID || item[k] != RJ_NONE))
+				rj_park(sm, pr, PACKED ? item[k] : (((item[k] >> pshift) << 16) | (item[k] & pr.mask)), par);
 	}
 }
 
@@ -258,120 +180,68 @@ __device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, 
 	const uint16_t *wl = sm->worklist[tid >> 5];
 	__syncthreads();
 	if (tid == 0)
-		sm->ovf_count[par ^ 1] = 0; // the other parity's parked keys were re-inserted at the start of this round
+		sm->ovf_count[par ^ 1] = 0; // the other parity's parked keys were re-inserted during this round
 	if (wl_n > RJ_WL_CAP) {
 		if (lane == 0)
 			atomicOr(pr.error_flag, RJ_ERR_SKEW);
 		wl_n = RJ_WL_CAP;
 	}
-	const uint32_t lt = rj_lanemask_lt();
 	const bool evict_last = (s.hints & RJ_HINT_STORE_EVICT_LAST) != 0;
-	for (uint32_t base = 0; base < wl_n; base += 32) { // warp-uniform
-		const bool act = base + lane < wl_n;
-		const uint32_t p = act ? wl[base + lane] : 0u;
-		uint32_t ch = act ? sm->chunk[p] : 0u;
-		if (RJ_LAB & 2) { // no chunk logic: sectors go to a private, hashed position
-			if (act) {
-				uint2 *row = reinterpret_cast<uint2*>(&sm->stage[p * RJ_CAP]);
-				const uint32_t have = rj_fill_get(sm, p);
-				const uint2 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4];
-				const uint32_t sec = (((tid >> 5) << 12) + ((par * 977u + base + lane) & 4095u)) * 40503u & 131071u;
-				if (!(RJ_LAB & 8))
-					rj_store_sector(s.dst[0].pool + ((size_t)blockIdx.x * 131072u + sec) * RJ_FLUSH, a, b, c, d, evict_last);
-				row[0] = e;
-				rj_fill_drop(sm, p, have, min(have, (uint32_t)RJ_CAP) - RJ_FLUSH);
-			}
-			continue;
-		}
-		const bool need = act && (ch == RJ_NONE || (ch & 31u) == RJ_BLOCKS_PER_CHUNK);
-		const int o = rj_owner(s, pr, p);
-		bool ok = act;
-		if (__any_sync(0xffffffffu, need)) {
-			// fresh chunks for the whole warp: one shared-memory atomic per owner
-			uint32_t cid = 0;
-			for (int oo = 0; oo < s.world; oo++) {
-				const uint32_t m = __ballot_sync(0xffffffffu, need && o == oo);
-				if (m == 0)
-					continue;
-				uint32_t first = 0;
-				if (lane == 0)
-					first = rj_smem_add(&sm->local_next[oo], (uint32_t)__popc(m));
-				first = __shfl_sync(0xffffffffu, first, 0);
-				if (need && o == oo)
-					cid = first + __popc(m & lt);
-			}
-			if (need) {
-				if (cid >= sm->local_end[o])
-					cid = atomicAdd(s.dst[o].pool_next, 1u); // the reserve ran dry inside one round (start-up, skew)
-				ok = rj_open_chunk(s, pr, s.dst[o], p, ch, cid);
-				ch = cid << 5;
-			}
-		}
-		if (ok) {
-			uint2 *row = reinterpret_cast<uint2*>(&sm->stage[p * RJ_CAP]); // 40-byte rows are 8-byte aligned
-			const uint32_t have = rj_fill_get(sm, p);
-			const uint2 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4];
-			if (!(RJ_LAB & 8))
-				rj_store_sector(s.dst[o].pool + (size_t)(ch >> 5) * RJ_CHUNK + (ch & 31u) * RJ_FLUSH, a, b, c, d, evict_last);
-			sm->chunk[p] = ch + 1;
-			row[0] = e; // keep the (at most 4) remainders behind the flushed sector
-			rj_fill_drop(sm, p, have, min(have, (uint32_t)RJ_CAP) - RJ_FLUSH);
-		}
+	for (uint32_t w = lane; w < wl_n; w += 32) {
+		const uint32_t p = wl[w];
+		const uint32_t at = atomicAdd(&s.cursor[p], (uint32_t)RJ_FLUSH);
+		uint2 *row = reinterpret_cast<uint2*>(&sm->stage[p * RJ_CAP]); // 40-byte rows are 8-byte aligned
+		const uint32_t have = sm->fill[p];
+		const uint2 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4];
+		row[0] = e; // keep the (at most 4) remainders behind the flushed sector
+		sm->fill[p] = min(have, (uint32_t)RJ_CAP) - RJ_FLUSH;
+		if (at + RJ_FLUSH <= s.cap)
+			rj_store_sector(s.stream + (size_t)p * s.cap + at, a, b, c, d, evict_last);
+		else
+			atomicOr(pr.error_flag, RJ_ERR_STREAM);
 	}
 	__syncthreads();
 }
 
-// every partition's partial sector goes out, chunk entry counts are finalised
+// every partition's partial sector goes to the partition's tail stream
 __device__ static inline void rj_drain(const RJSide &s, const RJParams &pr, RJP1Smem *sm)
 {
 	for (int p = threadIdx.x; p < pr.nparts; p += RJ_P1_THREADS) {
-		const uint32_t f = min(rj_fill_get(sm, p), (uint32_t)RJ_CAP);
-		const RJTarget &t = s.dst[rj_owner(s, pr, p)];
-		uint32_t ch = sm->chunk[p];
-		if (f > 0) {
-			if (ch == RJ_NONE || (ch & 31u) == RJ_BLOCKS_PER_CHUNK) {
-				rj_new_chunk(s, pr, sm, p);
-				ch = sm->chunk[p];
-			}
-			if (ch != RJ_NONE && (ch & 31u) < RJ_BLOCKS_PER_CHUNK) {
-				uint16_t *dst = t.pool + (size_t)(ch >> 5) * RJ_CHUNK + (ch & 31u) * RJ_FLUSH;
-				for (uint32_t i = 0; i < f; i++)
-					dst[i] = sm->stage[p * RJ_CAP + i];
-				t.chunk_entries[ch >> 5] = (uint16_t)((ch & 31u) * RJ_FLUSH + f);
-			}
-		} else if (ch != RJ_NONE) {
-			t.chunk_entries[ch >> 5] = (uint16_t)((ch & 31u) * RJ_FLUSH);
+		const uint32_t f = min(sm->fill[p], (uint32_t)RJ_CAP);
+		if (f == 0)
+			continue;
+		const uint32_t at = atomicAdd(&s.tail_cursor[p], f);
+		if (at + f <= s.tail_cap) {
+			uint16_t *dst = s.tail + (size_t)p * s.tail_cap + at;
+			for (uint32_t i = 0; i < f; i++)
+				dst[i] = sm->stage[p * RJ_CAP + i];
+		} else {
+			atomicOr(pr.error_flag, RJ_ERR_STREAM);
 		}
 	}
-	__threadfence_system(); // remote owners read these chunks after the next cross-rank barrier
 }
 
 __device__ static inline void rj_smem_init(RJP1Smem *sm)
 {
 	const int tid = threadIdx.x;
-	for (int p = tid; p < RJ_MAX_PART; p += RJ_P1_THREADS) {
-		if (p < RJ_MAX_PART / 2)
-			sm->fill[p] = 0;
-		sm->chunk[p] = RJ_NONE;
-	}
+	for (int p = tid; p < RJ_MAX_PART; p += RJ_P1_THREADS)
+		sm->fill[p] = 0;
 	if (tid < 2)
 		sm->ovf_count[tid] = 0;
-	if (tid < RJ_MAX_RANKS)
-		sm->local_next[tid] = sm->local_end[tid] = 0;
 	__syncthreads();
 }
 
 // rounds for the keys still parked after the last tile (bounded: a row that never drains means extreme skew)
 __device__ static inline void rj_finish(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par)
 {
-	uint32_t wl_n;
 	for (int guard = 0; sm->ovf_count[par ^ 1] != 0; guard++) { // block-uniform: written before the last barrier
 		if (guard == RJ_TAIL_ROUNDS) {
 			if (threadIdx.x == 0)
 				atomicOr(pr.error_flag, RJ_ERR_SKEW);
 			break;
 		}
-		rj_round_begin(s, pr, sm, par, wl_n);
+		uint32_t wl_n = 0;
+		rj_reinsert_parked(pr, sm, par, wl_n);
 		rj_round_end(s, pr, sm, par, wl_n);
 		par ^= 1;
 	}
@@ -406,14 +276,12 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSid
 		rj_load_keys256(t + RJ_P1_THREADS * 32u, dst + 4, evict_first);
 	};
 	auto round = [&](const uint32_t *buf) {
-		uint32_t wl_n, item[RJ_P1_KEYS];
-		rj_round_begin(s, pr, sm, par, wl_n);
+		uint32_t wl_n = 0, item[RJ_P1_KEYS];
 #pragma unroll
-		for (int k = 0; k < RJ_P1_KEYS; k++) {
-			const uint32_t d = buf[k] - kmin_lo;
-			item[k] = ((d >> pr.shift) << 16) | (d & pr.mask);
-		}
-		rj_insert_items<true>(sm, pr, item, par, wl_n);
+		for (int k = 0; k < RJ_P1_KEYS; k++)
+			item[k] = buf[k] - kmin_lo;
+		rj_insert_items<false>(sm, pr, item, par, wl_n);
+		rj_reinsert_parked(pr, sm, par, wl_n);
 		rj_round_end(s, pr, sm, par, wl_n);
 		par ^= 1;
 	};
@@ -435,14 +303,14 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSid
 		tile = next;
 	}
 	if (blockIdx.x == 0 && nfull * TILE != s.n) {
-		uint32_t wl_n;
-		rj_round_begin(s, pr, sm, par, wl_n);
+		uint32_t wl_n = 0;
 		for (uint64_t r0 = nfull * TILE + (tid & ~31u); r0 < s.n; r0 += RJ_P1_THREADS) { // warp-uniform trip count
 			const uint64_t r = r0 + (tid & 31u);
 			const bool valid = r < s.n;
 			const uint32_t d = valid ? (uint32_t)(unsigned long long)s.keys[r] - kmin_lo : 0u;
 			rj_insert_ws(sm, pr, ((d >> pr.shift) << 16) | (d & pr.mask), valid, par, wl_n);
 		}
+		rj_reinsert_parked(pr, sm, par, wl_n);
 		rj_round_end(s, pr, sm, par, wl_n);
 		par ^= 1;
 	}
@@ -450,7 +318,6 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSid
 }
 
 // generic tile load: 128-bit loads of whole 64-bit keys (range test needs the high words)
-template <bool HAS_PRESENT>
 __device__ static inline void rj_load_tile(const RJSide &s, uint64_t tile, int4 *dst)
 {
 	constexpr uint32_t TILE = RJ_P1_THREADS * RJ_P1_KEYS;
@@ -504,7 +371,7 @@ __device__ static inline void rj_insert_tile(const RJSide &s, const RJParams &pr
 		item[2 * j] = ok0 ? ((((uint32_t)d0 >> pr.shift) << 16) | ((uint32_t)d0 & pr.mask)) : RJ_NONE;
 		item[2 * j + 1] = ok1 ? ((((uint32_t)d1 >> pr.shift) << 16) | ((uint32_t)d1 & pr.mask)) : RJ_NONE;
 	}
-	rj_insert_items<false>(sm, pr, item, par, wl_n);
+	rj_insert_items<true>(sm, pr, item, par, wl_n);
 }
 
 // Pass 1, generic variant (NULLs / tombstones / keys outside the partitioned range): same rounds as the lean
@@ -523,28 +390,28 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition(RJSide s, 
 	uint64_t tile = blockIdx.x;
 	int par = 0;
 	if (tile < ntiles)
-		rj_load_tile<HAS_PRESENT>(s, tile, buf_a);
+		rj_load_tile(s, tile, buf_a);
 	auto round = [&](const int4 *buf, uint64_t t) {
-		uint32_t wl_n;
-		rj_round_begin(s, pr, sm, par, wl_n);
+		uint32_t wl_n = 0;
 		if (t < nfull)
 			rj_insert_tile<HAS_PRESENT, true>(s, pr, sm, buf, t, par, wl_n);
 		else
 			rj_insert_tile<HAS_PRESENT, false>(s, pr, sm, buf, t, par, wl_n);
+		rj_reinsert_parked(pr, sm, par, wl_n);
 		rj_round_end(s, pr, sm, par, wl_n);
 		par ^= 1;
 	};
 	while (tile < ntiles) {
 		uint64_t next = tile + gridDim.x;
 		if (next < ntiles)
-			rj_load_tile<HAS_PRESENT>(s, next, buf_b);
+			rj_load_tile(s, next, buf_b);
 		round(buf_a, tile);
 		tile = next;
 		if (tile >= ntiles)
 			break;
 		next = tile + gridDim.x;
 		if (next < ntiles)
-			rj_load_tile<HAS_PRESENT>(s, next, buf_a);
+			rj_load_tile(s, next, buf_a);
 		round(buf_b, tile);
 		tile = next;
 	}

@@ -4,32 +4,14 @@
 // the field sums against the number of remainders read (a wrapped counter lowers the sum), then emit every
 // key present on both sides with count cntA * cntB.
 //
-// What bounds it (ncu, profiles/): the remainders are read once (2 B/key) and the groups written once
-// (16 B/group); everything else is shared memory.  Three things keep it off the latency floor:
-//   * the chunk descriptors (chunk id, entries) of a partition are fetched into shared memory up front, so the
-//     only dependent global access per chunk is the 512-byte chunk itself, several chunks in flight per warp;
+// What bounds it: the remainders are read once (2 B/key) and the groups written once (16 B/group); everything
+// else is shared memory.
+//   * a partition's remainders are contiguous per source rank (main stream + tail stream, mdb_radix_types.cuh):
+//     256-bit loads, a warp covers 1 KiB per instruction, two loads in flight per lane;
 //   * groups are written with warp-ballot compaction: for one counter position at a time the matching lanes
 //     write to consecutive output rows, so every store instruction covers a contiguous run;
 //   * with 4-bit counters two CTAs share an SM: one emits while the other loads.
 #pragma once
-
-#define RJ_DESC_CAP 1024 // chunk descriptors staged per side and batch
-
-__global__ void k_radix_dir_fill(RJSide s)
-{
-	const RJTarget &t = s.dst[s.self];
-	uint32_t nchunks = min(*t.pool_next, s.pool_chunks);
-	for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nchunks; c += gridDim.x * blockDim.x) {
-		uint32_t p = t.chunk_part[c];
-		if (p == 0xffffu)
-			continue; // id reserved by a CTA but never used
-		uint32_t pos = atomicAdd(&s.dir_fill[p], 1u);
-		RJDesc d;
-		d.off16 = c * (RJ_CHUNK / 8);
-		d.ne = t.chunk_entries[c];
-		s.dir[s.dir_off[p] + pos] = d;
-	}
-}
 
 struct RJOut {
 	int nout;
@@ -64,53 +46,72 @@ __device__ __forceinline__ uint32_t rj_field_sum(uint32_t x)
 	return __dp4a(x, 0x01010101u, 0u);
 }
 
-// count the remainders of chunks [0, n) described in shared memory into cnt; returns (per warp) entries seen
-template <int BITS, int THREADS>
-__device__ __forceinline__ uint32_t rj_histogram(const uint16_t *__restrict__ pool, const RJDesc *descs, uint32_t n, uint32_t *cnt)
+__device__ __forceinline__ void rj_load256(const void *p, uint32_t *w)
 {
-	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	constexpr int NWARPS = THREADS / 32;
-	constexpr int MLP = 4; // chunks in flight per warp
-	uint32_t seen = 0;
-	for (uint32_t c = warp * MLP; c < n; c += NWARPS * MLP) {
-		int4 v[MLP];
-		uint32_t ne[MLP];
+	asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+			: "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+}
+
+// count the `ne` remainders starting at `run` (32-byte aligned; reading up to the next 32-byte boundary is safe)
+template <int BITS, int THREADS>
+__device__ __forceinline__ void rj_histogram_run(const uint16_t *__restrict__ run, uint32_t ne, uint32_t *cnt)
+{
+	constexpr int MLP = 2; // 32-byte vectors in flight per thread
+	const uint32_t nvec = (ne + 15u) / 16u;
+	for (uint32_t v0 = threadIdx.x; v0 < nvec; v0 += THREADS * MLP) {
+		uint32_t w[MLP][8];
+#pragma unroll
+		for (int u = 0; u < MLP; u++) // unconditional (address clamped): keeps the vectors in registers
+			rj_load256(run + (size_t)min(v0 + u * THREADS, nvec - 1u) * 16u, w[u]);
 #pragma unroll
 		for (int u = 0; u < MLP; u++) {
-			ne[u] = 0;
-			v[u] = make_int4(0, 0, 0, 0);
-			if (c + u < n) {
-				const RJDesc d = descs[c + u];
-				ne[u] = d.ne;
-				if ((uint32_t)lane * 8 < d.ne) // partially filled chunks: only touch the sectors that hold data
-					v[u] = mdb_ldg_stream(reinterpret_cast<const int4*>(pool) + (size_t)d.off16 + lane);
-			}
-		}
+			const uint32_t v = v0 + u * THREADS;
+			if (v >= nvec)
+				continue;
+			const uint32_t valid = min(16u, ne - v * 16u);
+			if (valid == 16u) {
 #pragma unroll
-		for (int u = 0; u < MLP; u++) {
-			const uint32_t w[4] = {(uint32_t)v[u].x, (uint32_t)v[u].y, (uint32_t)v[u].z, (uint32_t)v[u].w};
-			const uint32_t first = (uint32_t)lane * 8;
-			if (first + 8 <= ne[u]) {
-#pragma unroll
-				for (int j = 0; j < 4; j++) {
-					rj_count<BITS>(cnt, w[j] & 0xffffu);
-					rj_count<BITS>(cnt, w[j] >> 16);
+				for (int j = 0; j < 8; j++) {
+					rj_count<BITS>(cnt, w[u][j] & 0xffffu);
+					rj_count<BITS>(cnt, w[u][j] >> 16);
 				}
-			} else if (first < ne[u]) {
-				// the one lane holding the ragged tail of a drained chunk
-				for (uint32_t j = 0; first + j < ne[u]; j++)
-					rj_count<BITS>(cnt, (w[j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+			} else {
+				// ragged last vector of a stream
+#pragma unroll
+				for (int j = 0; j < 16; j++)
+					if ((uint32_t)j < valid)
+						rj_count<BITS>(cnt, (w[u][j >> 1] >> ((j & 1) * 16)) & 0xffffu);
 			}
-			seen += ne[u];
 		}
 	}
-	return seen;
+}
+
+// all streams of partition p on one side; returns the number of remainders (identical in every thread)
+template <int BITS, int THREADS>
+__device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, uint32_t p, uint32_t *cnt)
+{
+	uint32_t total = 0;
+	for (int s = 0; s < r.nsrc; s++) {
+		const uint32_t q = p - r.first[s];
+		const uint32_t n_main = min(r.cursor[s][q], r.cap), n_tail = min(r.tail_cursor[s][q], r.tail_cap);
+		rj_histogram_run<BITS, THREADS>(r.stream[s] + (size_t)q * r.cap, n_main, cnt);
+		rj_histogram_run<BITS, THREADS>(r.tail[s] + (size_t)q * r.tail_cap, n_tail, cnt);
+		total += n_main + n_tail;
+	}
+	return total;
 }
 
 template <int BITS, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
-k_radix_joincount(RJSide a, RJSide b, RJParams pr, RJOut out, uint32_t *__restrict__ part_counter)
+k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32_t *__restrict__ part_counter)
 {
+	// the per-source arrays are indexed at run time: keep them in shared memory, not in a local copy of the parameters
+	__shared__ RJRuns s_runs[2];
+	for (uint32_t i = threadIdx.x; i < sizeof(RJRuns) / 4; i += THREADS) {
+		reinterpret_cast<uint32_t*>(&s_runs[0])[i] = reinterpret_cast<const uint32_t*>(&a_param)[i];
+		reinterpret_cast<uint32_t*>(&s_runs[1])[i] = reinterpret_cast<const uint32_t*>(&b_param)[i];
+	}
+	const RJRuns &a = s_runs[0], &b = s_runs[1];
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	constexpr int KPW = 32 / BITS;
 	constexpr int NWARPS = THREADS / 32;
@@ -119,9 +120,7 @@ k_radix_joincount(RJSide a, RJSide b, RJParams pr, RJOut out, uint32_t *__restri
 	const int words = D >= KPW ? D / KPW : 1;
 	uint32_t *cntA = reinterpret_cast<uint32_t*>(smem_raw);
 	uint32_t *cntB = cntA + words;
-	RJDesc *descA = reinterpret_cast<RJDesc*>(cntB + words);
-	RJDesc *descB = descA + RJ_DESC_CAP;
-	__shared__ uint32_t s_part, s_totA, s_totB, s_sumA, s_sumB;
+	__shared__ uint32_t s_part, s_sumA, s_sumB;
 	__shared__ uint32_t s_warp[NWARPS + 1];
 	__shared__ unsigned long long s_base;
 	const int tid = threadIdx.x;
@@ -131,36 +130,19 @@ k_radix_joincount(RJSide a, RJSide b, RJParams pr, RJOut out, uint32_t *__restri
 	while (true) {
 		if (tid == 0) {
 			s_part = (uint32_t)pr.part_first + atomicAdd(part_counter, 1u);
-			s_totA = s_totB = s_sumA = s_sumB = 0;
+			s_sumA = s_sumB = 0;
 		}
+		for (int w = tid; w < words * 2; w += THREADS)
+			cntA[w] = 0; // cntB follows cntA
 		__syncthreads();
 		const uint32_t p = s_part;
 		if (p >= (uint32_t)pr.part_end) // this rank owns partitions [part_first, part_end)
 			break;
 
-		// ---- count both sides (descriptor batches of RJ_DESC_CAP chunks per side; one batch is the common case)
-		const uint64_t a0 = a.dir_off[p], a1 = a.dir_off[p + 1], b0 = b.dir_off[p], b1 = b.dir_off[p + 1];
-		for (int w = tid; w < words * 2; w += THREADS)
-			cntA[w] = 0; // cntB follows cntA
-		uint32_t seenA = 0, seenB = 0;
-		for (uint64_t off = 0; a0 + off < a1 || b0 + off < b1; off += RJ_DESC_CAP) {
-			const uint32_t na = a0 + off < a1 ? (uint32_t)min((uint64_t)RJ_DESC_CAP, a1 - a0 - off) : 0u;
-			const uint32_t nb = b0 + off < b1 ? (uint32_t)min((uint64_t)RJ_DESC_CAP, b1 - b0 - off) : 0u;
-			for (uint32_t i = tid; i < na; i += THREADS)
-				descA[i] = a.dir[a0 + off + i];
-			for (uint32_t i = tid; i < nb; i += THREADS)
-				descB[i] = b.dir[b0 + off + i];
-			__syncthreads();
-			seenA += rj_histogram<BITS, THREADS>(a.pool, descA, na, cntA);
-			seenB += rj_histogram<BITS, THREADS>(b.pool, descB, nb, cntB);
-			__syncthreads();
-		}
-		if (lane == 0) {
-			if (seenA)
-				atomicAdd(&s_totA, seenA);
-			if (seenB)
-				atomicAdd(&s_totB, seenB);
-		}
+		// ---- count both sides
+		const uint32_t totA = rj_histogram_side<BITS, THREADS>(a, p, cntA);
+		const uint32_t totB = rj_histogram_side<BITS, THREADS>(b, p, cntB);
+		__syncthreads();
 
 		// ---- checksum + number of groups of this partition
 		uint32_t sumA = 0, sumB = 0, matches = 0;
@@ -195,7 +177,7 @@ k_radix_joincount(RJSide a, RJSide b, RJParams pr, RJOut out, uint32_t *__restri
 			if (lane == 31) {
 				s_base = incl ? atomicAdd(out.cursor, (unsigned long long)incl) : 0ull;
 				s_warp[NWARPS] = incl;
-				if (s_sumA != s_totA || s_sumB != s_totB)
+				if (s_sumA != totA || s_sumB != totB)
 					atomicOr(pr.error_flag, RJ_ERR_COUNTER);
 			}
 		}

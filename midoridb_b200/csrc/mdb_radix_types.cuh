@@ -6,48 +6,45 @@
 #define RJ_MAX_SHIFT 16            // remainder bits: 2-byte remainders
 #define RJ_CAP 20                  // staging slots per partition in shared memory
 #define RJ_FLUSH 16                // a partition is flushed when 16 remainders (= one 32-byte sector) are staged
-#define RJ_CHUNK 256               // remainders per chunk (512 bytes = one warp-wide 128-bit load)
-#define RJ_BLOCKS_PER_CHUNK (RJ_CHUNK / RJ_FLUSH)
 #define RJ_P1_THREADS 1024
 #define RJ_OVF_CAP 512             // keys per round that may find their staging row full and wait one round
 #define RJ_NONE 0xffffffffu
+#define RJ_MAX_RANKS 8
 
-#define RJ_ERR_POOL 1u             // chunk pool exhausted
+#define RJ_ERR_STREAM 1u           // a partition's stream is full (its keys are far more frequent than the average)
 #define RJ_ERR_COUNTER 2u          // a packed counter wrapped (too many equal keys for the counter width)
 #define RJ_ERR_SKEW 4u             // more than RJ_OVF_CAP keys per round hit full staging rows
 
-// one run of <= RJ_CHUNK remainders: 16-byte aligned offset into a remainder buffer, valid entries
-struct RJDesc {
-	uint32_t off16; // in units of 16 bytes (8 remainders)
-	uint32_t ne;
-};
-
-#define RJ_MAX_RANKS 8
-
-// where the chunks of the partitions owned by one rank are written: this GPU's own arrays, or - in a
-// multi-GPU plan - the owner's arena mapped over NVLink (CUDA IPC), so pass 1 IS the exchange
-struct RJTarget {
-	uint16_t *pool;            // pool_chunks * RJ_CHUNK remainders
-	uint32_t *pool_next;       // allocation cursor
-	uint16_t *chunk_part;      // partition of each chunk
-	uint16_t *chunk_entries;   // valid remainders in each chunk
-	uint32_t *dir_cnt;         // chunks per partition
-};
-
+// One side of the join on this GPU.  Pass 1 appends the 2-byte remainders of partition p to p's stream:
+//   main  stream + p * cap,       cursor[p] entries      whole 32-byte sectors, appended by every CTA (position =
+//                                                         one global atomic per sector: consecutive sectors of a
+//                                                         128-byte line are written within about a microsecond by
+//                                                         different CTAs and merge in L2 on their way to DRAM)
+//   tail  tail + p * tail_cap,    tail_cursor[p] entries  the partial sectors left in the CTAs' staging rows at the end
 struct RJSide {
 	const int64_t *keys;
 	const uint32_t *present;
 	uint64_t n;
 	int all_in_range;          // every key of the column lies in [kmin, kmin + range): no per-key range test
 	uint32_t hints;            // RJ_HINT_* cache-hint switches of pass 1
-	int world, self;           // owner ranks; index of this GPU in dst[]
-	uint32_t pool_chunks;      // capacity of every target's pool
-	uint32_t id_batch, id_low; // chunk ids a CTA reserves per owner at a time / refill threshold
-	RJTarget dst[RJ_MAX_RANKS];
-	uint16_t *pool;            // pass 2 reads remainders from here (dst[self].pool unless an NCCL exchange staged them)
-	RJDesc *dir;               // (offset, entries) of this GPU's chunks grouped by partition
-	uint64_t *dir_off;         // exclusive offsets into dir
-	uint32_t *dir_fill;
+	uint16_t *stream;
+	uint32_t *cursor;
+	uint16_t *tail;
+	uint32_t *tail_cursor;
+	uint32_t cap, tail_cap;    // entries per partition (multiples of 16)
+};
+
+// What pass 2 reads for one side: for every source rank the streams of the partitions this GPU owns.  Source
+// `self` is this GPU's own RJSide (indexed by p); the others are the arena slots the peers pushed into over
+// NVLink (indexed by p - first).
+struct RJRuns {
+	int nsrc;
+	uint32_t cap, tail_cap;
+	const uint16_t *stream[RJ_MAX_RANKS];
+	const uint16_t *tail[RJ_MAX_RANKS];
+	const uint32_t *cursor[RJ_MAX_RANKS];
+	const uint32_t *tail_cursor[RJ_MAX_RANKS];
+	uint32_t first[RJ_MAX_RANKS];
 };
 
 struct RJParams {
@@ -59,4 +56,3 @@ struct RJParams {
 	int part_first, part_end;  // pass 2 handles partitions [part_first, part_end) (all of them on one GPU)
 	uint32_t *error_flag;
 };
-
