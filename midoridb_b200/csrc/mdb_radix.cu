@@ -250,8 +250,12 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
-		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
 		attr_done = true;
 	}
 
@@ -285,10 +289,25 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		const int bitsw = attempt == 0 ? 4 : 8;
 		const size_t smem2 = 2 * (size_t)std::max<uint64_t>(1, D * bitsw / 32) * sizeof(uint32_t);
 		const int grid2 = std::max(1, std::min(pr.part_end - pr.part_first, ctx->num_sms * (bitsw == 4 ? 2 : 1)));
-		if (bitsw == 4)
-			MDB_LAUNCH(ctx, (k_radix_joincount<4, 512>), grid2, 512, smem2, ra, rb, pr, out, d_flags + 1);
-		else
-			MDB_LAUNCH(ctx, (k_radix_joincount<8, 1024>), grid2, 1024, smem2, ra, rb, pr, out, d_flags + 1);
+		// result layout known at compile time for the two common shapes: [key, count] and [count, key]
+		const int layout = out.nout != 2 ? 0 : (!out.is_count[0] && out.is_count[1]) ? 1 : (out.is_count[0] && !out.is_count[1]) ? 2 : 0;
+#define RJ_LAUNCH2(B, T, L) MDB_LAUNCH(ctx, (k_radix_joincount<B, T, L>), grid2, T, smem2, ra, rb, pr, out, d_flags + 1)
+		if (bitsw == 4) {
+			if (layout == 1)
+				RJ_LAUNCH2(4, 512, 1);
+			else if (layout == 2)
+				RJ_LAUNCH2(4, 512, 2);
+			else
+				RJ_LAUNCH2(4, 512, 0);
+		} else {
+			if (layout == 1)
+				RJ_LAUNCH2(8, 1024, 1);
+			else if (layout == 2)
+				RJ_LAUNCH2(8, 1024, 2);
+			else
+				RJ_LAUNCH2(8, 1024, 0);
+		}
+#undef RJ_LAUNCH2
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess)
 			return mdb_fail(ctx, MDBCU_ECUDA, "radix join launch failed: %s", cudaGetErrorString(e));
@@ -305,6 +324,9 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	}
 	clock.finish();
 	if (flags || ngroups > cap_groups) {
+		if (getenv("MDBCU_TRACE"))
+			fprintf(stderr, "[mdbcu] radix join gives up: flags %u (1 stream full, 2 counter wrapped, 4 skew), groups %llu of %llu\n",
+					flags, (unsigned long long)ngroups, (unsigned long long)cap_groups);
 		if (dist)
 			return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "distributed radix join: key multiplicity or skew beyond the counter width "
 					"(flags %u); the general operators are single-GPU only", flags);

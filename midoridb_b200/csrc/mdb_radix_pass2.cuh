@@ -101,7 +101,9 @@ __device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, uint32_t 
 	return total;
 }
 
-template <int BITS, int THREADS>
+// LAYOUT fixes the result columns at compile time (the emit loop is the largest part of this kernel's instruction
+// stream): 0 = read RJOut at run time, 1 = [key, count], 2 = [count, key]
+template <int BITS, int THREADS, int LAYOUT>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32_t *__restrict__ part_counter)
 {
@@ -185,9 +187,11 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 
 		// ---- emit: one counter position at a time, matching lanes write consecutive rows (coalesced runs)
 		const uint32_t total = s_warp[NWARPS];
-		unsigned long long pos = s_base + s_warp[warp];
 		if (total && s_base + total <= out.cap) {
 			const long long key_base = pr.kmin + (long long)((unsigned long long)p << pr.shift);
+			const unsigned long long row0 = s_base + s_warp[warp];
+			int64_t *const key_col = out.cells[LAYOUT == 2 ? 1 : 0] + row0, *const cnt_col = out.cells[LAYOUT == 2 ? 0 : 1] + row0;
+			uint32_t pos = 0; // rows this warp has written for this partition
 			for (int w0 = 0; w0 < words; w0 += THREADS) {
 				const int w = w0 + tid;
 				uint32_t x = 0, y = 0;
@@ -198,18 +202,24 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 				const uint32_t m = rj_nonzero_mask<BITS>(x) & rj_nonzero_mask<BITS>(y);
 				if (__ballot_sync(0xffffffffu, m != 0) == 0)
 					continue;
+				const long long key_w = key_base + (long long)w * KPW;
 #pragma unroll
 				for (int f = 0; f < KPW; f++) {
-					const bool has = (m >> (f * BITS + BITS - 1)) & 1u;
+					const bool has = (m & (1u << (f * BITS + BITS - 1))) != 0;
 					const uint32_t bal = __ballot_sync(0xffffffffu, has);
 					if (has) {
-						const unsigned long long row = pos + __popc(bal & lt_mask);
-						const long long key = key_base + (long long)w * KPW + f;
-						const long long cnt = (long long)((x >> (f * BITS)) & FIELD) * (long long)((y >> (f * BITS)) & FIELD);
+						const uint32_t r = pos + __popc(bal & lt_mask);
+						const long long key = key_w + f;
+						const long long cnt = (long long)(((x >> (f * BITS)) & FIELD) * ((y >> (f * BITS)) & FIELD));
+						if (LAYOUT != 0) {
+							key_col[r] = key;
+							cnt_col[r] = cnt;
+						} else {
 #pragma unroll
-						for (int o = 0; o < 4; o++)
-							if (o < out.nout)
-								out.cells[o][row] = out.is_count[o] ? cnt : key;
+							for (int o = 0; o < 4; o++)
+								if (o < out.nout)
+									out.cells[o][row0 + r] = out.is_count[o] ? cnt : key;
+						}
 					}
 					pos += __popc(bal);
 				}

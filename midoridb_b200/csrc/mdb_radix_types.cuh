@@ -7,7 +7,7 @@
 #define RJ_CAP 20                  // staging slots per partition in shared memory
 #define RJ_FLUSH 16                // a partition is flushed when 16 remainders (= one 32-byte sector) are staged
 #define RJ_P1_THREADS 1024
-#define RJ_OVF_CAP 512             // keys per round that may find their staging row full and wait one round
+#define RJ_OVF_CAP 1024            // keys per round that may find their staging row full and wait one round (about 200 expected)
 #define RJ_NONE 0xffffffffu
 #define RJ_MAX_RANKS 8
 
