@@ -3,11 +3,13 @@
 //
 // One persistent 1024-thread CTA per SM.  Per round every thread takes 8 keys:
 //   insert   partition = (key - kmin) >> shift; ONE shared-memory atomic hands out a slot of the partition's
-//            40-byte staging row, ONE 2-byte shared store writes the remainder.  The lane that fills slot 16 puts
-//            the partition on ITS WARP's worklist (position from a ballot: no atomics, no CTA-wide queue);
-//   barrier  (all remainders of the queued rows are in shared memory)
-//   flush    every warp flushes its own worklist, one lane per row: one global atomic on the partition's cursor
-//            gives the position, the first 16 remainders leave as ONE 256-bit store = one aligned 32-byte sector;
+//            40-byte staging row, ONE 2-byte shared store writes the remainder - nothing else per key.  A key that
+//            finds its row full (about 7 of 8192 per round) is put on a small CTA-wide spill list;
+//   barrier  (all remainders handed out this round are in shared memory)
+//   flush    every warp owns 128 partitions: one 128-bit read of four slot counters per lane finds the rows that hold
+//            a whole sector, ballots compact them so that every lane gets one row; one global atomic on the
+//            partition's cursor gives the position, the first 16 remainders leave as ONE 256-bit store = one aligned
+//            32-byte sector; spilled keys are appended one by one to their partition's tail stream;
 //   barrier
 // Measurements behind this shape (profiles/microbench/p1_lab*.cu and profiles/p1_lab_*.txt, B200, 2^28 keys):
 //   * 256-bit key loads stream at 6.4 TB/s where 128-bit loads reach 4.7;
@@ -15,12 +17,22 @@
 //     is left cannot hold the key loads in flight and the whole kernel loses 25%;
 //   * slot atomics + 2-byte stores cost 0.05 ms on top of the loads; a CTA-wide worklist fed by same-address
 //     atomics costs 0.15 ms more than ballots; stores that complete whole 128-byte lines are 0.13 ms cheaper than
-//     scattered 32-byte sectors (hence shared per-partition streams instead of per-CTA chunks).
+//     scattered 32-byte sectors (hence shared per-partition streams instead of per-CTA chunks);
+//   * the kernel is bound by instruction issue and shared-memory latency, not by DRAM: noticing "row complete" per
+//     key (compare, ballot, rank, queue) was a third of all executed instructions - hence the scan after the barrier;
+//   * re-inserting overflowing keys in the next round cost 0.07 ms (the re-insert sits on one warp's critical path
+//     before the barrier) and appending them to the tail stream right away cost 0.08 ms (a global atomic's latency
+//     in the insert phase): they wait on a list until the flush, whose atomics are in flight anyway;
+//   * two tiles per flush halve the barriers but overflow 25x more often: slower.
+
+#ifndef RJ_LAB
+#define RJ_LAB 0                   // profiles/microbench/p1_lab3.cu knocks parts of the kernel out (timing experiments only):
+#endif                             // 1 drop overflowing keys, 2 no cursor atomic (fake positions), 4 no sector store
 
 #define RJ_P1_WARPS (RJ_P1_THREADS / 32)
 #define RJ_P1_KEYS 8               // keys per thread per round
-#define RJ_WL_CAP 128              // rows one warp may complete per round (16 expected, four times that while all rows fill in step at start-up)
-#define RJ_TAIL_ROUNDS 64          // rounds spent on parked keys after the last tile before giving up (skew)
+#define RJ_SPILL_CAP 512           // keys per round that may find their staging row full (about 7 expected)
+#define RJ_WARP_PARTS (RJ_MAX_PART / RJ_P1_WARPS) // partitions whose staging rows one warp flushes
 
 #define RJ_HINT_PREFETCH 1u        // prefetch.global.L2 two tiles ahead
 #define RJ_HINT_LOAD_EVICT_FIRST 2u
@@ -30,12 +42,13 @@
 struct RJP1Smem {
 	uint16_t stage[RJ_MAX_PART * RJ_CAP];     // 160 KiB: 20 two-byte slots per partition
 	uint32_t fill[RJ_MAX_PART];               // slots handed out since the last flush (may overshoot RJ_CAP)
-	uint16_t worklist[RJ_P1_WARPS][RJ_WL_CAP]; // per warp: partitions whose 16th slot it filled this round
-	uint32_t ovf[2][RJ_OVF_CAP];              // (partition << 16 | remainder) waiting for the next round
-	uint32_t ovf_count[2];
+	uint16_t worklist[RJ_P1_WARPS][RJ_WARP_PARTS]; // per warp: those of its partitions that hold a whole sector this round
+	uint32_t spill[RJ_SPILL_CAP];             // (partition << 16 | remainder) of keys whose row was full this round
+	uint32_t spill_n[2];                      // by round parity
 };
 
 static_assert(sizeof(RJP1Smem) <= 195 * 1024, "pass-1 shared memory must stay inside the 196 KiB carve-out");
+static_assert(RJ_WARP_PARTS == 128, "the flush scan reads four slot counters per lane");
 
 // plain shared-memory atomic: kept in PTX so the compiler does not expand it into warp-aggregation code
 __device__ __forceinline__ uint32_t rj_smem_add(uint32_t *p, uint32_t v)
@@ -91,110 +104,104 @@ __device__ __forceinline__ void rj_load_keys256(const void *p, uint32_t *lo, boo
 	lo[3] = t[6];
 }
 
-__device__ static inline void rj_park(RJP1Smem *sm, const RJParams &pr, uint32_t item, int par)
+// the staging row of partition p is full until this round's flush: the key waits on the CTA's spill list
+__device__ static inline void rj_spill(RJP1Smem *sm, const RJParams &pr, uint32_t p, uint32_t rem, int par)
 {
-	// staging row full until this round's flush: the key waits one round
-	const uint32_t o = rj_smem_add(&sm->ovf_count[par], 1u);
-	if (o < RJ_OVF_CAP)
-		sm->ovf[par][o] = item;
+	if (RJ_LAB & 1)
+		return;
+	const uint32_t o = rj_smem_add(&sm->spill_n[par], 1u);
+	if (o < RJ_SPILL_CAP)
+		sm->spill[o] = (p << 16) | rem;
 	else
 		atomicOr(pr.error_flag, RJ_ERR_SKEW);
 }
 
-// Warp-synchronous insert of one item per lane (lanes without a key pass valid = false): slot, store, and - for
-// the lane that completed a sector - a place on the warp's worklist.
-__device__ __forceinline__ void rj_insert_ws(RJP1Smem *sm, const RJParams &pr, uint32_t item, bool valid, int par, uint32_t &wl_n)
+// insert of one item = (partition << 16 | remainder): slot, store
+__device__ __forceinline__ void rj_insert_one(RJP1Smem *sm, const RJParams &pr, uint32_t item, int par)
 {
 	const uint32_t p = item >> 16;
-	uint32_t pos = RJ_NONE;
-	if (valid)
-		pos = rj_fill_claim(sm, p);
+	const uint32_t pos = rj_fill_claim(sm, p);
 	if (pos < RJ_CAP)
 		sm->stage[p * RJ_CAP + pos] = (uint16_t)item;
-	const bool done = pos == RJ_FLUSH - 1;
-	const uint32_t bal = __ballot_sync(0xffffffffu, done);
-	if (done) {
-		const uint32_t idx = wl_n + __popc(bal & rj_lanemask_lt());
-		if (idx < RJ_WL_CAP)
-			sm->worklist[threadIdx.x >> 5][idx] = (uint16_t)p;
-	}
-	wl_n += __popc(bal);
-	if (valid && pos >= RJ_CAP)
-		rj_park(sm, pr, item, par);
-}
-
-// keys parked by the previous round are inserted again (their rows were flushed since)
-__device__ static inline void rj_reinsert_parked(const RJParams &pr, RJP1Smem *sm, int par, uint32_t &wl_n)
-{
-	const uint32_t tid = threadIdx.x;
-	const uint32_t novf = min(sm->ovf_count[par ^ 1], (uint32_t)RJ_OVF_CAP);
-	for (uint32_t i0 = tid & ~31u; i0 < novf; i0 += RJ_P1_THREADS) { // warp-uniform trip count
-		const uint32_t i = i0 + (tid & 31u);
-		const bool valid = i < novf;
-		rj_insert_ws(sm, pr, valid ? sm->ovf[par ^ 1][i] : 0u, valid, par, wl_n);
-	}
+	else
+		rj_spill(sm, pr, p, item & 0xffffu, par);
 }
 
 // 8 keys per thread.  PACKED: item = (partition << 16 | remainder), RJ_NONE = no key (generic kernel);
 // otherwise item = key - kmin and every item is a key (lean kernel).
 // All slot requests of a thread are issued back to back (independent shared-memory atomics), then consumed.
 template <bool PACKED>
-__device__ __forceinline__ void rj_insert_items(RJP1Smem *sm, const RJParams &pr, const uint32_t *item, int par, uint32_t &wl_n)
+__device__ __forceinline__ void rj_insert_items(RJP1Smem *sm, const RJParams &pr, const uint32_t *item, int par)
 {
 	constexpr bool ALL_VALID = !PACKED;
 	const int pshift = PACKED ? 16 : pr.shift;
+	const uint32_t rmask = PACKED ? 0xffffu : pr.mask;
 	uint32_t pos[RJ_P1_KEYS];
 #pragma unroll
 	for (int k = 0; k < RJ_P1_KEYS; k++)
 		pos[k] = (ALL_VALID || item[k] != RJ_NONE) ? rj_fill_claim(sm, item[k] >> pshift) : RJ_NONE;
-	const uint32_t lt = rj_lanemask_lt();
-	uint16_t *wl = sm->worklist[threadIdx.x >> 5];
 	uint32_t worst = 0; // largest slot handed to this thread (+1 with holes, so that RJ_NONE counts as 0)
 #pragma unroll
 	for (int k = 0; k < RJ_P1_KEYS; k++) {
 		const uint32_t p = item[k] >> pshift;
 		if (pos[k] < RJ_CAP)
-			sm->stage[p * RJ_CAP + pos[k]] = (uint16_t)(PACKED ? item[k] : item[k] & pr.mask);
-		const bool done = pos[k] == RJ_FLUSH - 1;
-		const uint32_t bal = __ballot_sync(0xffffffffu, done);
-		if (done) {
-			const uint32_t idx = wl_n + __popc(bal & lt);
-			if (idx < RJ_WL_CAP)
-				wl[idx] = (uint16_t)p;
-		}
-		wl_n += __popc(bal);
+			sm->stage[p * RJ_CAP + pos[k]] = (uint16_t)(item[k] & rmask);
 		worst = max(worst, ALL_VALID ? pos[k] : pos[k] + 1u);
 	}
 	if (worst >= (ALL_VALID ? RJ_CAP : RJ_CAP + 1u)) { // rare: some row was full
 #pragma unroll
 		for (int k = 0; k < RJ_P1_KEYS; k++)
 			if (pos[k] >= RJ_CAP && (ALL_VALID || item[k] != RJ_NONE))
-				rj_park(sm, pr, PACKED ? item[k] : (((item[k] >> pshift) << 16) | (item[k] & pr.mask)), par);
+				rj_spill(sm, pr, item[k] >> pshift, item[k] & rmask, par);
 	}
 }
 
-// barrier, every warp flushes the rows on its own worklist, barrier
-__device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par, uint32_t wl_n)
+// barrier, every warp flushes the full rows among ITS 128 partitions, spilled keys go to the tail streams, barrier
+__device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par)
 {
-	const uint32_t tid = threadIdx.x, lane = tid & 31u;
-	const uint16_t *wl = sm->worklist[tid >> 5];
+	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+	uint16_t *wl = sm->worklist[warp];
 	__syncthreads();
+	// spilled keys: one global atomic + one 2-byte store each, issued together with the flush's atomics
+	const uint32_t nspill = min(sm->spill_n[par], (uint32_t)RJ_SPILL_CAP);
 	if (tid == 0)
-		sm->ovf_count[par ^ 1] = 0; // the other parity's parked keys were re-inserted during this round
-	if (wl_n > RJ_WL_CAP) {
-		if (lane == 0)
-			atomicOr(pr.error_flag, RJ_ERR_SKEW);
-		wl_n = RJ_WL_CAP;
+		sm->spill_n[par ^ 1] = 0; // (read by every thread before the previous round's second barrier)
+	for (uint32_t i = tid; i < nspill; i += RJ_P1_THREADS) {
+		const uint32_t item = sm->spill[i], p = item >> 16;
+		const uint32_t at = atomicAdd(&s.tail_cursor[p], 1u);
+		if (at < s.tail_cap)
+			s.tail[(size_t)p * s.tail_cap + at] = (uint16_t)item;
+		else
+			atomicOr(pr.error_flag, RJ_ERR_STREAM);
+	}
+	// which of this warp's rows hold a whole sector?  (the insert loop itself never looks at "row complete")
+	uint32_t wl_n = 0;
+	{
+		const uint32_t first = warp * RJ_WARP_PARTS + lane * 4u;
+		const uint4 f = *reinterpret_cast<const uint4*>(&sm->fill[first]);
+		const uint32_t cnt[4] = {f.x, f.y, f.z, f.w};
+		const uint32_t lt = rj_lanemask_lt();
+#pragma unroll
+		for (int j = 0; j < 4; j++) {
+			const bool full = cnt[j] >= RJ_FLUSH;
+			const uint32_t bal = __ballot_sync(0xffffffffu, full);
+			if (full)
+				wl[wl_n + __popc(bal & lt)] = (uint16_t)(first + j);
+			wl_n += __popc(bal);
+		}
+		__syncwarp();
 	}
 	const bool evict_last = (s.hints & RJ_HINT_STORE_EVICT_LAST) != 0;
 	for (uint32_t w = lane; w < wl_n; w += 32) {
 		const uint32_t p = wl[w];
-		const uint32_t at = atomicAdd(&s.cursor[p], (uint32_t)RJ_FLUSH);
+		const uint32_t at = (RJ_LAB & 2) ? ((warp * 997u + w * 16u) & 0xfff0u) : atomicAdd(&s.cursor[p], (uint32_t)RJ_FLUSH);
 		uint2 *row = reinterpret_cast<uint2*>(&sm->stage[p * RJ_CAP]); // 40-byte rows are 8-byte aligned
 		const uint32_t have = sm->fill[p];
 		const uint2 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4];
 		row[0] = e; // keep the (at most 4) remainders behind the flushed sector
 		sm->fill[p] = min(have, (uint32_t)RJ_CAP) - RJ_FLUSH;
+		if (RJ_LAB & 4)
+			continue;
 		if (at + RJ_FLUSH <= s.cap)
 			rj_store_sector(s.stream + (size_t)p * s.cap + at, a, b, c, d, evict_last);
 		else
@@ -223,29 +230,11 @@ __device__ static inline void rj_drain(const RJSide &s, const RJParams &pr, RJP1
 
 __device__ static inline void rj_smem_init(RJP1Smem *sm)
 {
-	const int tid = threadIdx.x;
-	for (int p = tid; p < RJ_MAX_PART; p += RJ_P1_THREADS)
+	for (int p = threadIdx.x; p < RJ_MAX_PART; p += RJ_P1_THREADS)
 		sm->fill[p] = 0;
-	if (tid < 2)
-		sm->ovf_count[tid] = 0;
+	if (threadIdx.x < 2)
+		sm->spill_n[threadIdx.x] = 0;
 	__syncthreads();
-}
-
-// rounds for the keys still parked after the last tile (bounded: a row that never drains means extreme skew)
-__device__ static inline void rj_finish(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par)
-{
-	for (int guard = 0; sm->ovf_count[par ^ 1] != 0; guard++) { // block-uniform: written before the last barrier
-		if (guard == RJ_TAIL_ROUNDS) {
-			if (threadIdx.x == 0)
-				atomicOr(pr.error_flag, RJ_ERR_SKEW);
-			break;
-		}
-		uint32_t wl_n = 0;
-		rj_reinsert_parked(pr, sm, par, wl_n);
-		rj_round_end(s, pr, sm, par, wl_n);
-		par ^= 1;
-	}
-	rj_drain(s, pr, sm);
 }
 
 // Pass 1, lean variant: column without NULLs/tombstones whose [min, max] lies inside the partitioned range and
@@ -275,21 +264,14 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSid
 		rj_load_keys256(t, dst, evict_first);
 		rj_load_keys256(t + RJ_P1_THREADS * 32u, dst + 4, evict_first);
 	};
-	// a round = one tile (8 keys per thread) and one flush.  (Two tiles per flush halve the barriers but park 25x
-	// more keys: measured 4% slower.)
-	uint32_t wl_n = 0;
-	auto insert = [&](const uint32_t *buf) {
+	auto round = [&](const uint32_t *buf) {
 		uint32_t item[RJ_P1_KEYS];
 #pragma unroll
 		for (int k = 0; k < RJ_P1_KEYS; k++)
 			item[k] = buf[k] - kmin_lo;
-		rj_insert_items<false>(sm, pr, item, par, wl_n);
-	};
-	auto end_round = [&]() {
-		rj_reinsert_parked(pr, sm, par, wl_n);
-		rj_round_end(s, pr, sm, par, wl_n);
+		rj_insert_items<false>(sm, pr, item, par);
+		rj_round_end(s, pr, sm, par);
 		par ^= 1;
-		wl_n = 0;
 	};
 	uint64_t tile = blockIdx.x;
 	if (tile < nfull)
@@ -298,30 +280,24 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSid
 		uint64_t next = tile + gridDim.x;
 		if (next < nfull)
 			load(next, buf_b);
-		insert(buf_a);
-		end_round();
+		round(buf_a);
 		tile = next;
 		if (tile >= nfull)
 			break;
 		next = tile + gridDim.x;
 		if (next < nfull)
 			load(next, buf_a);
-		insert(buf_b);
-		end_round();
+		round(buf_b);
 		tile = next;
 	}
 	if (blockIdx.x == 0 && nfull * TILE != s.n) {
-		for (uint64_t r0 = nfull * TILE + (tid & ~31u); r0 < s.n; r0 += RJ_P1_THREADS) { // warp-uniform trip count
-			const uint64_t r = r0 + (tid & 31u);
-			const bool valid = r < s.n;
-			const uint32_t d = valid ? (uint32_t)(unsigned long long)s.keys[r] - kmin_lo : 0u;
-			rj_insert_ws(sm, pr, ((d >> pr.shift) << 16) | (d & pr.mask), valid, par, wl_n);
+		for (uint64_t r = nfull * TILE + tid; r < s.n; r += RJ_P1_THREADS) {
+			const uint32_t d = (uint32_t)(unsigned long long)s.keys[r] - kmin_lo;
+			rj_insert_one(sm, pr, ((d >> pr.shift) << 16) | (d & pr.mask), par);
 		}
-		rj_reinsert_parked(pr, sm, par, wl_n);
-		rj_round_end(s, pr, sm, par, wl_n);
-		par ^= 1;
+		rj_round_end(s, pr, sm, par);
 	}
-	rj_finish(s, pr, sm, par);
+	rj_drain(s, pr, sm);
 }
 
 // generic tile load: 128-bit loads of whole 64-bit keys (range test needs the high words)
@@ -353,8 +329,7 @@ __device__ static inline void rj_load_tile(const RJSide &s, uint64_t tile, int4 
 
 // generic insert phase: range test, NULL/tombstone bitmap, ragged last tile.  FULL: every row of the tile exists
 template <bool HAS_PRESENT, bool FULL>
-__device__ static inline void rj_insert_tile(const RJSide &s, const RJParams &pr, RJP1Smem *sm, const int4 *buf, uint64_t tile,
-		int par, uint32_t &wl_n)
+__device__ static inline void rj_insert_tile(const RJSide &s, const RJParams &pr, RJP1Smem *sm, const int4 *buf, uint64_t tile, int par)
 {
 	constexpr uint32_t TILE = RJ_P1_THREADS * RJ_P1_KEYS;
 	const uint64_t base_pair = tile * (TILE / 2);
@@ -378,7 +353,7 @@ __device__ static inline void rj_insert_tile(const RJSide &s, const RJParams &pr
 		item[2 * j] = ok0 ? ((((uint32_t)d0 >> pr.shift) << 16) | ((uint32_t)d0 & pr.mask)) : RJ_NONE;
 		item[2 * j + 1] = ok1 ? ((((uint32_t)d1 >> pr.shift) << 16) | ((uint32_t)d1 & pr.mask)) : RJ_NONE;
 	}
-	rj_insert_items<true>(sm, pr, item, par, wl_n);
+	rj_insert_items<true>(sm, pr, item, par);
 }
 
 // Pass 1, generic variant (NULLs / tombstones / keys outside the partitioned range): same rounds as the lean
@@ -399,13 +374,11 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition(RJSide s, 
 	if (tile < ntiles)
 		rj_load_tile(s, tile, buf_a);
 	auto round = [&](const int4 *buf, uint64_t t) {
-		uint32_t wl_n = 0;
 		if (t < nfull)
-			rj_insert_tile<HAS_PRESENT, true>(s, pr, sm, buf, t, par, wl_n);
+			rj_insert_tile<HAS_PRESENT, true>(s, pr, sm, buf, t, par);
 		else
-			rj_insert_tile<HAS_PRESENT, false>(s, pr, sm, buf, t, par, wl_n);
-		rj_reinsert_parked(pr, sm, par, wl_n);
-		rj_round_end(s, pr, sm, par, wl_n);
+			rj_insert_tile<HAS_PRESENT, false>(s, pr, sm, buf, t, par);
+		rj_round_end(s, pr, sm, par);
 		par ^= 1;
 	};
 	while (tile < ntiles) {
@@ -422,5 +395,5 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition(RJSide s, 
 		round(buf_b, tile);
 		tile = next;
 	}
-	rj_finish(s, pr, sm, par);
+	rj_drain(s, pr, sm);
 }

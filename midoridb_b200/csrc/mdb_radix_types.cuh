@@ -7,20 +7,20 @@
 #define RJ_CAP 20                  // staging slots per partition in shared memory
 #define RJ_FLUSH 16                // a partition is flushed when 16 remainders (= one 32-byte sector) are staged
 #define RJ_P1_THREADS 1024
-#define RJ_OVF_CAP 1024            // keys per round that may find their staging row full and wait one round (about 200 expected)
 #define RJ_NONE 0xffffffffu
 #define RJ_MAX_RANKS 8
 
 #define RJ_ERR_STREAM 1u           // a partition's stream is full (its keys are far more frequent than the average)
 #define RJ_ERR_COUNTER 2u          // a packed counter wrapped (too many equal keys for the counter width)
-#define RJ_ERR_SKEW 4u             // more than RJ_OVF_CAP keys per round hit full staging rows
+#define RJ_ERR_SKEW 4u             // more than RJ_SPILL_CAP keys of one round found their staging row full (clustered keys)
 
 // One side of the join on this GPU.  Pass 1 appends the 2-byte remainders of partition p to p's stream:
 //   main  stream + p * cap,       cursor[p] entries      whole 32-byte sectors, appended by every CTA (position =
 //                                                         one global atomic per sector: consecutive sectors of a
 //                                                         128-byte line are written within about a microsecond by
 //                                                         different CTAs and merge in L2 on their way to DRAM)
-//   tail  tail + p * tail_cap,    tail_cursor[p] entries  the partial sectors left in the CTAs' staging rows at the end
+//   tail  tail + p * tail_cap,    tail_cursor[p] entries  single remainders: keys that found their staging row full, and
+//                                                         the partial sectors left in the staging rows at the end
 struct RJSide {
 	const int64_t *keys;
 	const uint32_t *present;

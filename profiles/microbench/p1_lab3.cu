@@ -28,23 +28,17 @@ int main(int argc, char **argv)
 	int64_t *keys;
 	CK(cudaMalloc(&keys, n * 8));
 	k_gen<<<sms * 8, 256>>>(keys, n, n);
-	const uint64_t chunks = (n / RJ_CHUNK + (uint64_t)sms * RJ_MAX_PART) * 3 / 2 + (uint64_t)sms * 8192 + 1024;
 	RJSide s;
 	memset(&s, 0, sizeof(s));
 	s.keys = keys;
 	s.n = n;
 	s.all_in_range = 1;
-	s.world = 1;
-	s.self = 0;
-	s.pool_chunks = (uint32_t)chunks;
-	s.id_batch = 8192;
-	s.id_low = 2048;
-	RJTarget &t = s.dst[0];
-	CK(cudaMalloc(&t.pool, chunks * RJ_CHUNK * 2));
-	CK(cudaMalloc(&t.pool_next, 4));
-	CK(cudaMalloc(&t.chunk_part, chunks * 2));
-	CK(cudaMalloc(&t.chunk_entries, chunks * 2));
-	CK(cudaMalloc(&t.dir_cnt, (RJ_MAX_PART + 1) * 4));
+	s.cap = (uint32_t)(2 * (n / 4096) + 2048);
+	s.tail_cap = (sms * RJ_FLUSH + s.cap / 32 + 15u) & ~15u;
+	CK(cudaMalloc(&s.stream, (size_t)4096 * s.cap * 2));
+	CK(cudaMalloc(&s.tail, (size_t)4096 * s.tail_cap * 2));
+	CK(cudaMalloc(&s.cursor, 2 * RJ_MAX_PART * 4));
+	s.tail_cursor = s.cursor + RJ_MAX_PART;
 	uint32_t *flag;
 	CK(cudaMalloc(&flag, 8));
 	CK(cudaMemset(flag, 0, 8));
@@ -63,14 +57,12 @@ int main(int argc, char **argv)
 	CK(cudaEventCreate(&e0));
 	CK(cudaEventCreate(&e1));
 	printf("n = 2^%d keys, %d SMs, smem %zu\n", lg, sms, sizeof(RJP1Smem));
-	for (int variant = 0; variant < 9; variant++) {
+	for (int variant = 0; variant < 9; variant += (variant == 1 ? 7 : 1)) {
 		s.hints = variant < 8 ? (uint32_t)variant : 0;
 		float total = 0;
 		const int reps = 5;
 		for (int i = 0; i < reps + 2; i++) {
-			CK(cudaMemsetAsync(t.pool_next, 0, 4));
-			CK(cudaMemsetAsync(t.chunk_part, 0xff, chunks * 2));
-			CK(cudaMemsetAsync(t.dir_cnt, 0, (RJ_MAX_PART + 1) * 4));
+			CK(cudaMemsetAsync(s.cursor, 0, 2 * RJ_MAX_PART * 4));
 			CK(cudaEventRecord(e0));
 			if (variant < 8)
 				k_radix_partition_fast<<<sms, RJ_P1_THREADS, sizeof(RJP1Smem)>>>(s, pr);
@@ -83,12 +75,16 @@ int main(int argc, char **argv)
 			if (i >= 2)
 				total += ms;
 		}
-		uint32_t h[2], used;
+		uint32_t h[2];
+		static uint32_t cur[2 * RJ_MAX_PART];
 		CK(cudaMemcpy(h, flag, 8, cudaMemcpyDeviceToHost));
-		CK(cudaMemcpy(&used, t.pool_next, 4, cudaMemcpyDeviceToHost));
-		printf("%s hints %d: %8.3f ms  %7.1f GB/s of keys   (error flags %u, chunk ids used %u of %llu)\n",
-				variant < 8 ? "fast   " : "generic", variant < 8 ? variant : 0, total / reps, 8.0 * n / (total / reps) / 1e6, h[0], used,
-				(unsigned long long)chunks);
+		CK(cudaMemcpy(cur, s.cursor, sizeof(cur), cudaMemcpyDeviceToHost));
+		unsigned long long total_entries = 0;
+		for (int i = 0; i < 2 * RJ_MAX_PART; i++)
+			total_entries += cur[i];
+		printf("%s hints %d: %8.3f ms  %7.1f GB/s of keys   (error flags %u, entries in streams %llu of %llu)\n",
+				variant < 8 ? "fast   " : "generic", variant < 8 ? variant : 0, total / reps, 8.0 * n / (total / reps) / 1e6, h[0], total_entries,
+				(unsigned long long)n);
 	}
 	return 0;
 }
