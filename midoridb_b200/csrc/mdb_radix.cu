@@ -54,9 +54,9 @@ static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_ta
 		return MDBCU_EUNSUPPORTED;
 	MDB_TRY(tmp.alloc(&s->stream, (size_t)nparts * cap));
 	MDB_TRY(tmp.alloc(&s->tail, (size_t)nparts * s->tail_cap));
-	MDB_TRY(tmp.alloc(&s->cursor, 2 * RJ_MAX_PART));
-	s->tail_cursor = s->cursor + RJ_MAX_PART;
-	CUDA_TRY(ctx, cudaMemsetAsync(s->cursor, 0, 2 * RJ_MAX_PART * sizeof(uint32_t), ctx->stream));
+	MDB_TRY(tmp.alloc(&s->cursor, (size_t)RJ_MAX_PART * RJ_CUR_STRIDE));
+	s->tail_cursor = s->cursor + 1;
+	CUDA_TRY(ctx, cudaMemsetAsync(s->cursor, 0, (size_t)RJ_MAX_PART * RJ_CUR_STRIDE * sizeof(uint32_t), ctx->stream));
 	return MDBCU_OK;
 }
 
@@ -72,6 +72,7 @@ static void rj_runs_local(RJRuns *r, const RJSide &s)
 	r->cursor[0] = s.cursor;
 	r->tail_cursor[0] = s.tail_cursor;
 	r->first[0] = 0;
+	r->cur_stride[0] = RJ_CUR_STRIDE;
 }
 
 static void launch_partition(mdbcu_ctx *ctx, int grid, const RJSide &s, const RJParams &pr)
@@ -212,6 +213,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 					r->cursor[o] = own_cursor;
 					r->tail_cursor[o] = own_tail_cursor;
 					r->first[o] = 0;
+					r->cur_stride[o] = RJ_CUR_STRIDE;
 					continue;
 				}
 				// slot [o] of this rank's arena: what rank o pushed here
@@ -221,6 +223,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 				r->cursor[o] = (const uint32_t*)(src + l.cursor);
 				r->tail_cursor[o] = (const uint32_t*)(src + l.tail_cursor);
 				r->first[o] = (uint32_t)pr.part_first;
+				r->cur_stride[o] = 1;
 			}
 		};
 		fill(&ship_a, &ra, la, 0);

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(512) k_radix_ship(RJSide s, RJShip sh)
 		if (o == sh.self)
 			continue;
 		const uint32_t q = (uint32_t)p - (uint32_t)((uint64_t)o * sh.nparts / sh.world);
-		const uint32_t n_main = min(s.cursor[p], s.cap), n_tail = min(s.tail_cursor[p], s.tail_cap);
+		const uint32_t n_main = min(s.cursor[p * RJ_CUR_STRIDE], s.cap), n_tail = min(s.tail_cursor[p * RJ_CUR_STRIDE], s.tail_cap);
 		const char *src = reinterpret_cast<const char*>(s.stream + (size_t)p * s.cap);
 		char *dst = reinterpret_cast<char*>(sh.main[o] + (size_t)q * s.cap);
 		for (uint32_t v = threadIdx.x; v < n_main / 16u; v += blockDim.x)

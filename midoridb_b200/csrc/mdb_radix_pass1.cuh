@@ -29,6 +29,15 @@
 #define RJ_LAB 0                   // profiles/microbench/p1_lab3.cu knocks parts of the kernel out (timing experiments only):
 #endif                             // 1 drop overflowing keys, 2 no cursor atomic (fake positions), 4 no sector store
 
+#if RJ_LAB & 8
+// timeline of one warp of CTA 0 (p1_lab3): cycles spent in [insert | wait barrier 1 | flush | wait barrier 2], summed over rounds
+__device__ unsigned long long rj_timeline[4][8];
+#define RJ_STAMP(i) do { if ((RJ_LAB & 8) && blockIdx.x == 0 && (threadIdx.x & 31u) == 0 && (threadIdx.x >> 5) % 10 == 0) { \
+	const long long now_ = clock64(); atomicAdd(&rj_timeline[(threadIdx.x >> 5) / 10][i], (unsigned long long)(now_ - rj_t_)); rj_t_ = now_; } } while (0)
+#else
+#define RJ_STAMP(i) do { } while (0)
+#endif
+
 #define RJ_P1_WARPS (RJ_P1_THREADS / 32)
 #define RJ_P1_KEYS 8               // keys per thread per round
 #define RJ_SPILL_CAP 512           // keys per round that may find their staging row full (about 7 expected)
@@ -157,18 +166,20 @@ __device__ __forceinline__ void rj_insert_items(RJP1Smem *sm, const RJParams &pr
 }
 
 // barrier, every warp flushes the full rows among ITS 128 partitions, spilled keys go to the tail streams, barrier
-__device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par)
+__device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par, long long &rj_t_)
 {
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	uint16_t *wl = sm->worklist[warp];
+	RJ_STAMP(0);
 	__syncthreads();
+	RJ_STAMP(1);
 	// spilled keys: one global atomic + one 2-byte store each, issued together with the flush's atomics
 	const uint32_t nspill = min(sm->spill_n[par], (uint32_t)RJ_SPILL_CAP);
 	if (tid == 0)
 		sm->spill_n[par ^ 1] = 0; // (read by every thread before the previous round's second barrier)
 	for (uint32_t i = tid; i < nspill; i += RJ_P1_THREADS) {
 		const uint32_t item = sm->spill[i], p = item >> 16;
-		const uint32_t at = atomicAdd(&s.tail_cursor[p], 1u);
+		const uint32_t at = atomicAdd(&s.tail_cursor[p * RJ_CUR_STRIDE], 1u);
 		if (at < s.tail_cap)
 			s.tail[(size_t)p * s.tail_cap + at] = (uint16_t)item;
 		else
@@ -191,10 +202,11 @@ __device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, 
 		}
 		__syncwarp();
 	}
+	RJ_STAMP(4);
 	const bool evict_last = (s.hints & RJ_HINT_STORE_EVICT_LAST) != 0;
 	for (uint32_t w = lane; w < wl_n; w += 32) {
 		const uint32_t p = wl[w];
-		const uint32_t at = (RJ_LAB & 2) ? ((warp * 997u + w * 16u) & 0xfff0u) : atomicAdd(&s.cursor[p], (uint32_t)RJ_FLUSH);
+		const uint32_t at = (RJ_LAB & 2) ? ((warp * 997u + w * 16u) & 0xfff0u) : atomicAdd(&s.cursor[p * RJ_CUR_STRIDE], (uint32_t)RJ_FLUSH);
 		uint2 *row = reinterpret_cast<uint2*>(&sm->stage[p * RJ_CAP]); // 40-byte rows are 8-byte aligned
 		const uint32_t have = sm->fill[p];
 		const uint2 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4];
@@ -207,7 +219,9 @@ __device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, 
 		else
 			atomicOr(pr.error_flag, RJ_ERR_STREAM);
 	}
+	RJ_STAMP(2);
 	__syncthreads();
+	RJ_STAMP(3);
 }
 
 // every partition's partial sector goes to the partition's tail stream
@@ -217,7 +231,7 @@ __device__ static inline void rj_drain(const RJSide &s, const RJParams &pr, RJP1
 		const uint32_t f = min(sm->fill[p], (uint32_t)RJ_CAP);
 		if (f == 0)
 			continue;
-		const uint32_t at = atomicAdd(&s.tail_cursor[p], f);
+		const uint32_t at = atomicAdd(&s.tail_cursor[p * RJ_CUR_STRIDE], f);
 		if (at + f <= s.tail_cap) {
 			uint16_t *dst = s.tail + (size_t)p * s.tail_cap + at;
 			for (uint32_t i = 0; i < f; i++)
@@ -253,6 +267,7 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSid
 	const bool pf = (s.hints & RJ_HINT_PREFETCH) != 0, evict_first = (s.hints & RJ_HINT_LOAD_EVICT_FIRST) != 0;
 	uint32_t buf_a[RJ_P1_KEYS], buf_b[RJ_P1_KEYS];
 	int par = 0;
+	long long rj_t_ = (RJ_LAB & 8) ? clock64() : 0; // (timeline experiments only)
 	auto load = [&](uint64_t tile, uint32_t *dst) {
 		if (pf) {
 			// pull the tile this CTA will load two rounds from now into L2 (one 128-byte line per thread)
@@ -270,7 +285,7 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSid
 		for (int k = 0; k < RJ_P1_KEYS; k++)
 			item[k] = buf[k] - kmin_lo;
 		rj_insert_items<false>(sm, pr, item, par);
-		rj_round_end(s, pr, sm, par);
+		rj_round_end(s, pr, sm, par, rj_t_);
 		par ^= 1;
 	};
 	uint64_t tile = blockIdx.x;
@@ -295,7 +310,7 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSid
 			const uint32_t d = (uint32_t)(unsigned long long)s.keys[r] - kmin_lo;
 			rj_insert_one(sm, pr, ((d >> pr.shift) << 16) | (d & pr.mask), par);
 		}
-		rj_round_end(s, pr, sm, par);
+		rj_round_end(s, pr, sm, par, rj_t_);
 	}
 	rj_drain(s, pr, sm);
 }
@@ -371,6 +386,7 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition(RJSide s, 
 	int4 buf_a[RJ_P1_KEYS / 2], buf_b[RJ_P1_KEYS / 2];
 	uint64_t tile = blockIdx.x;
 	int par = 0;
+	long long rj_t_ = (RJ_LAB & 8) ? clock64() : 0; // (timeline experiments only)
 	if (tile < ntiles)
 		rj_load_tile(s, tile, buf_a);
 	auto round = [&](const int4 *buf, uint64_t t) {
@@ -378,7 +394,7 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition(RJSide s, 
 			rj_insert_tile<HAS_PRESENT, true>(s, pr, sm, buf, t, par);
 		else
 			rj_insert_tile<HAS_PRESENT, false>(s, pr, sm, buf, t, par);
-		rj_round_end(s, pr, sm, par);
+		rj_round_end(s, pr, sm, par, rj_t_);
 		par ^= 1;
 	};
 	while (tile < ntiles) {

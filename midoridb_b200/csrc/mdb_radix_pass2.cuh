@@ -93,7 +93,7 @@ __device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, uint32_t 
 	uint32_t total = 0;
 	for (int s = 0; s < r.nsrc; s++) {
 		const uint32_t q = p - r.first[s];
-		const uint32_t n_main = min(r.cursor[s][q], r.cap), n_tail = min(r.tail_cursor[s][q], r.tail_cap);
+		const uint32_t n_main = min(r.cursor[s][q * r.cur_stride[s]], r.cap), n_tail = min(r.tail_cursor[s][q * r.cur_stride[s]], r.tail_cap);
 		rj_histogram_run<BITS, THREADS>(r.stream[s] + (size_t)q * r.cap, n_main, cnt);
 		rj_histogram_run<BITS, THREADS>(r.tail[s] + (size_t)q * r.tail_cap, n_tail, cnt);
 		total += n_main + n_tail;

@@ -37,8 +37,8 @@ int main(int argc, char **argv)
 	s.tail_cap = (sms * RJ_FLUSH + s.cap / 32 + 15u) & ~15u;
 	CK(cudaMalloc(&s.stream, (size_t)4096 * s.cap * 2));
 	CK(cudaMalloc(&s.tail, (size_t)4096 * s.tail_cap * 2));
-	CK(cudaMalloc(&s.cursor, 2 * RJ_MAX_PART * 4));
-	s.tail_cursor = s.cursor + RJ_MAX_PART;
+	CK(cudaMalloc(&s.cursor, (size_t)RJ_MAX_PART * RJ_CUR_STRIDE * 4));
+	s.tail_cursor = s.cursor + 1;
 	uint32_t *flag;
 	CK(cudaMalloc(&flag, 8));
 	CK(cudaMemset(flag, 0, 8));
@@ -57,12 +57,12 @@ int main(int argc, char **argv)
 	CK(cudaEventCreate(&e0));
 	CK(cudaEventCreate(&e1));
 	printf("n = 2^%d keys, %d SMs, smem %zu\n", lg, sms, sizeof(RJP1Smem));
-	for (int variant = 0; variant < 9; variant += (variant == 1 ? 7 : 1)) {
+	for (int variant = 0; variant < ((RJ_LAB & 8) ? 1 : 9); variant += (variant == 1 ? 7 : 1)) {
 		s.hints = variant < 8 ? (uint32_t)variant : 0;
 		float total = 0;
 		const int reps = 5;
 		for (int i = 0; i < reps + 2; i++) {
-			CK(cudaMemsetAsync(s.cursor, 0, 2 * RJ_MAX_PART * 4));
+			CK(cudaMemsetAsync(s.cursor, 0, (size_t)RJ_MAX_PART * RJ_CUR_STRIDE * 4));
 			CK(cudaEventRecord(e0));
 			if (variant < 8)
 				k_radix_partition_fast<<<sms, RJ_P1_THREADS, sizeof(RJP1Smem)>>>(s, pr);
@@ -76,15 +76,30 @@ int main(int argc, char **argv)
 				total += ms;
 		}
 		uint32_t h[2];
-		static uint32_t cur[2 * RJ_MAX_PART];
+		static uint32_t cur[RJ_MAX_PART * RJ_CUR_STRIDE];
 		CK(cudaMemcpy(h, flag, 8, cudaMemcpyDeviceToHost));
 		CK(cudaMemcpy(cur, s.cursor, sizeof(cur), cudaMemcpyDeviceToHost));
 		unsigned long long total_entries = 0;
-		for (int i = 0; i < 2 * RJ_MAX_PART; i++)
+		for (int i = 0; i < RJ_MAX_PART * RJ_CUR_STRIDE; i++)
 			total_entries += cur[i];
 		printf("%s hints %d: %8.3f ms  %7.1f GB/s of keys   (error flags %u, entries in streams %llu of %llu)\n",
 				variant < 8 ? "fast   " : "generic", variant < 8 ? variant : 0, total / reps, 8.0 * n / (total / reps) / 1e6, h[0], total_entries,
 				(unsigned long long)n);
 	}
+#if RJ_LAB & 8
+	unsigned long long tl[4][8];
+	CK(cudaMemcpyFromSymbol(tl, rj_timeline, sizeof(tl)));
+	const char *names[5] = {"insert", "wait barrier 1", "flush rows (atomic, store)", "wait barrier 2", "spill + scan counters"};
+	const int order[5] = {0, 1, 4, 2, 3};
+	for (int w = 0; w < 4; w++) {
+		unsigned long long sum = 0;
+		for (int i = 0; i < 5; i++)
+			sum += tl[w][i];
+		printf("warp %2d of CTA 0:", w * 10);
+		for (int k = 0; k < 5; k++)
+			printf("  %s %4.1f%%", names[order[k]], 100.0 * tl[w][order[k]] / (double)sum);
+		printf("   (cycles per launch %.0f)\n", sum / 7.0);
+	}
+#endif
 	return 0;
 }
