@@ -316,7 +316,7 @@ def main():
     step_gbs = alg_bytes / (ms_per_step / 1000.0) / 1e9
     roofline_step = {"bound": "hbm", "what": "whole step: (8|A| + 8|B| + 16 G) bytes / step device time", "achieved": step_gbs,
                      "peak": peak * world, "unit": "GB/s", "frac": step_gbs / (peak * world), "algorithmic_bytes_per_step": alg_bytes,
-                     "phase_ms": {"partition": phase[1], "directory": phase[7], "histogram_join_emit": phase[2], "exchange": phase[6]}}
+                     "phase_ms": {"partition": phase[1], "histogram_join_emit": phase[2], "exchange_push": phase[6], "barriers_and_other": phase[7]}}
 
     # ---- e2e: the same query through the C ABI from HOST page images (reference row format, pinned memory)
     e2e = None

@@ -32,6 +32,7 @@ struct mdbcu_ctx {
 	void *arena_local = nullptr;
 	size_t arena_bytes = 0;
 	void *arena_peer[MDB_MAX_RANKS] = {};
+	uint32_t arena_epoch = 0;  // barriers passed on the arena's flag words (mdb_comm_arena_barrier)
 	// reusable scratch: pinned host word for small D2H reads
 	uint64_t *h_scalar = nullptr; // pinned, 64 entries
 	uint64_t *d_scalar = nullptr; // device, 64 entries
@@ -243,8 +244,10 @@ int mdb_comm_group_end(mdbcu_ctx *ctx);
 int mdb_comm_send(mdbcu_ctx *ctx, const void *p, size_t bytes, int peer);
 int mdb_comm_recv(mdbcu_ctx *ctx, void *p, size_t bytes, int peer);
 int mdb_comm_arena(mdbcu_ctx *ctx, size_t bytes, void **bases);
+int mdb_comm_arena_barrier(mdbcu_ctx *ctx, const uint32_t *d_err, uint32_t *d_all);
 void mdb_comm_arena_destroy(mdbcu_ctx *ctx);
 int mdb_comm_barrier_or(mdbcu_ctx *ctx, uint32_t *d_flag, uint32_t *h_or_out);
+int mdb_comm_barrier_gather(mdbcu_ctx *ctx, uint32_t *d_flag, uint32_t *d_all);
 int mdb_comm_allgather_u64(mdbcu_ctx *ctx, const uint64_t *send, uint64_t *recv, size_t count);
 
 // phase clock: events are only recorded while the query runs; one synchronise at the end

@@ -180,6 +180,15 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint32_t), ctx->stream));
 	CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
 	pr.error_flag = d_flags;
+	pr.peer_flags = nullptr;
+	pr.n_peer_flags = 0;
+	uint32_t *d_peer_flags = nullptr;
+	if (dist && W > 1) {
+		MDB_TRY(tmp.alloc(&d_peer_flags, MDB_MAX_RANKS));
+		CUDA_TRY(ctx, cudaMemsetAsync(d_peer_flags, 0, MDB_MAX_RANKS * sizeof(uint32_t), ctx->stream));
+		pr.peer_flags = d_peer_flags;
+		pr.n_peer_flags = W;
+	}
 
 	RJRuns ra, rb;
 	rj_runs_local(&ra, sa);
@@ -269,17 +278,15 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	launch_partition(ctx, grid1, sb, pr);
 	if (dist && W > 1) {
 		// every rank must be done reading its arena (previous query) before any peer pushes into it
+		clock.begin(7);
+		MDB_TRY(mdb_comm_arena_barrier(ctx, d_flags, d_peer_flags));
 		clock.begin(6);
-		MDB_TRY(mdb_comm_barrier_or(ctx, d_flags, nullptr));
 		MDB_LAUNCH(ctx, k_radix_ship, ctx->num_sms * 2, 512, 0, sa, ship_a);
 		MDB_LAUNCH(ctx, k_radix_ship, ctx->num_sms * 2, 512, 0, sb, ship_b);
-		// all pushes have landed once every rank's ship kernels have completed; error flags are shared so that every
-		// rank takes the same exit
-		uint32_t any = 0;
-		MDB_TRY(mdb_comm_barrier_or(ctx, d_flags, &any));
-		if (any)
-			return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "distributed radix join: pass 1 failed on some rank (flags %u: "
-					"1 = a partition received more than twice its share of the keys, 4 = extreme skew)", any);
+		// all pushes have landed once every rank's ship kernels have completed.  The error flags travel with this
+		// barrier and stay on the device: pass 2 checks them itself, the host reads them with the result count
+		clock.begin(7);
+		MDB_TRY(mdb_comm_arena_barrier(ctx, d_flags, d_peer_flags));
 	}
 	clock.begin(2);
 
@@ -318,9 +325,19 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 			return mdb_fail(ctx, MDBCU_ECUDA, "radix join launch failed: %s", cudaGetErrorString(e));
 		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar, d_cursor, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar + 2, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		if (d_peer_flags)
+			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar + 3, d_peer_flags, MDB_MAX_RANKS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 		ngroups = ctx->h_scalar[0];
 		flags = (uint32_t)(ctx->h_scalar[2] & 0xffffffffu);
+		if (d_peer_flags) {
+			uint32_t any = 0;
+			for (int r = 0; r < W; r++)
+				any |= reinterpret_cast<const uint32_t*>(ctx->h_scalar + 3)[r];
+			if (any)
+				return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "distributed radix join: pass 1 failed on some rank (flags %u: "
+						"1 = a partition received more than twice its share of the keys, 4 = extreme skew)", any);
+		}
 		if (flags != RJ_ERR_COUNTER || attempt == 1)
 			break;
 		// a 4-bit counter wrapped: repeat pass 2 with 8-bit counters (the partitioned remainders are still valid)

@@ -114,6 +114,9 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 		reinterpret_cast<uint32_t*>(&s_runs[1])[i] = reinterpret_cast<const uint32_t*>(&b_param)[i];
 	}
 	const RJRuns &a = s_runs[0], &b = s_runs[1];
+	for (int r = 0; r < pr.n_peer_flags; r++)
+		if (pr.peer_flags[r] != 0)
+			return; // pass 1 failed on some rank: every rank skips pass 2 and reports it
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	constexpr int KPW = 32 / BITS;
 	constexpr int NWARPS = THREADS / 32;

@@ -58,4 +58,6 @@ struct RJParams {
 	int nparts;
 	int part_first, part_end;  // pass 2 handles partitions [part_first, part_end) (all of them on one GPU)
 	uint32_t *error_flag;
+	const uint32_t *peer_flags; // multi-GPU: every rank's error flags after the exchange (pass 2 does nothing if any is set)
+	int n_peer_flags;
 };
