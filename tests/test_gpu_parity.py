@@ -246,6 +246,27 @@ def test_radix_joincount_fastpath(be, shape):
         t.drop()
 
 
+@pytest.mark.parametrize("order", ["ascending", "clustered"])
+def test_radix_joincount_ordered_keys(be, order):
+    """auto-increment style ids (all keys of a tile fall into one or two partitions): whichever path runs - the radix
+    path or, after its skew flag, the general operators - the result equals the oracle's"""
+    rng = np.random.default_rng(43)
+    n = 1 << 20
+    if order == "ascending":
+        a, b = np.arange(n, dtype=np.int64), np.arange(n, dtype=np.int64)[::-1].copy()
+    else:
+        a = np.sort(rng.integers(0, 1 << 21, n))
+        b = rng.integers(0, 1 << 21, n)
+    ga, oa = both_tables(be, [I], [a])
+    gb, ob = both_tables(be, [I], [b])
+    grows, orows, _, st = run_both(be, [ga, gb], [oa, ob], joins=[((0, 0), (1, 0))], group=[(0, 0)],
+                                   out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)])
+    assert st.path in (capi.PATH_RADIX_JOINCOUNT, capi.PATH_GENERAL)
+    assert helpers.canon(grows) == helpers.canon(orows)
+    for t in (ga, gb):
+        t.drop()
+
+
 def test_radix_joincount_heavy_key_falls_back(be):
     """more than 255 equal keys wrap a byte counter: detected by the checksum, redone by the general operators"""
     rng = np.random.default_rng(41)
