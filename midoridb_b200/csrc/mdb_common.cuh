@@ -33,6 +33,9 @@ struct mdbcu_ctx {
 	size_t arena_bytes = 0;
 	void *arena_peer[MDB_MAX_RANKS] = {};
 	uint32_t arena_epoch = 0;  // barriers passed on the arena's flag words (mdb_comm_arena_barrier)
+	cudaStream_t side_stream = nullptr; // multi-GPU: the push of one join side runs here while pass 1 of the other side runs
+	cudaEvent_t side_ev[2] = {};
+	uint32_t arena_queries = 0; // distributed queries so far: alternate queries use alternate halves of the arena
 	// reusable scratch: pinned host word for small D2H reads
 	uint64_t *h_scalar = nullptr; // pinned, 64 entries
 	uint64_t *d_scalar = nullptr; // device, 64 entries

@@ -29,6 +29,10 @@ static bool col_all_present(const mdbcu_table *t, int col)
 #include "mdb_radix_pass2.cuh"
 #include "mdb_radix_dist.cuh"
 
+// dynamic shared memory the side-stream push asks for: it is not used, it makes a push CTA own its SM so that the
+// push takes push_sms SMs and pass 1 of the other side gets all the others
+#define RJ_SHIP_SMEM (160 * 1024)
+
 // entries one partition's main stream can hold: twice the average (uniform keys fill half of it; a partition that
 // receives more than twice its share sets RJ_ERR_STREAM and the general operators take over)
 static uint32_t rj_stream_cap(uint64_t rows, int nparts)
@@ -198,8 +202,12 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		// arena of every rank: [side A: W slots][side B: W slots]; slot s receives what rank s pushes
 		const uint32_t pown = (uint32_t)((nparts + W - 1) / W) + 1;
 		const RJSlotLayout la = rj_slot_layout(pown, sa.cap, sa.tail_cap), lb = rj_slot_layout(pown, sb.cap, sb.tail_cap);
+		// two halves used by alternate queries: a peer that is already pushing for the next query writes into the
+		// half this rank is NOT reading, so one cross-rank barrier per query (after the push) is enough
 		void *bases[MDB_MAX_RANKS];
-		MDB_TRY(mdb_comm_arena(ctx, (la.bytes + lb.bytes) * (size_t)W, bases));
+		const size_t half_bytes = (la.bytes + lb.bytes) * (size_t)W;
+		MDB_TRY(mdb_comm_arena(ctx, 2 * half_bytes, bases));
+		const size_t half_off = (ctx->arena_queries++ & 1u) ? half_bytes : 0;
 		auto fill = [&](RJShip *sh, RJRuns *r, const RJSlotLayout &l, size_t side_off) {
 			memset(sh, 0, sizeof(*sh));
 			sh->world = W;
@@ -235,8 +243,8 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 				r->cur_stride[o] = 1;
 			}
 		};
-		fill(&ship_a, &ra, la, 0);
-		fill(&ship_b, &rb, lb, la.bytes * (size_t)W);
+		fill(&ship_a, &ra, la, half_off);
+		fill(&ship_b, &rb, lb, half_off + la.bytes * (size_t)W);
 	}
 
 	// upper bound of groups this rank can emit: one per key of the partitions it owns
@@ -270,23 +278,37 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
 		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
 		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_ship, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_SHIP_SMEM));
 		attr_done = true;
 	}
 
 	clock.begin(1);
 	launch_partition(ctx, grid1, sa, pr);
-	launch_partition(ctx, grid1, sb, pr);
 	if (dist && W > 1) {
-		// every rank must be done reading its arena (previous query) before any peer pushes into it
-		clock.begin(7);
-		MDB_TRY(mdb_comm_arena_barrier(ctx, d_flags, d_peer_flags));
+		// Side A's streams are pushed to their owners by a few SMs WHILE pass 1 of side B runs on the others (pass 1
+		// is bound by shared memory, not by the SM count: giving up 1/9 of the SMs costs it 12 %, the push of A is free)
+		if (!ctx->side_stream) {
+			CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
+			CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->side_ev[0], cudaEventDisableTiming));
+			CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->side_ev[1], cudaEventDisableTiming));
+		}
+		const int push_sms = std::max(4, ctx->num_sms / 9);
+		CUDA_TRY(ctx, cudaEventRecord(ctx->side_ev[0], ctx->stream));
+		CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_ev[0], 0));
+		k_radix_ship<<<push_sms, 1024, RJ_SHIP_SMEM, ctx->side_stream>>>(sa, ship_a); // one CTA per SM (see RJ_SHIP_SMEM)
+		ctx->stats.kernel_launches++;
+		ctx->total_launches++;
+		CUDA_TRY(ctx, cudaEventRecord(ctx->side_ev[1], ctx->side_stream));
+		launch_partition(ctx, grid1 - push_sms, sb, pr);
 		clock.begin(6);
-		MDB_LAUNCH(ctx, k_radix_ship, ctx->num_sms * 2, 512, 0, sa, ship_a);
-		MDB_LAUNCH(ctx, k_radix_ship, ctx->num_sms * 2, 512, 0, sb, ship_b);
+		MDB_LAUNCH(ctx, k_radix_ship, ctx->num_sms * 2, 1024, 0, sb, ship_b);
+		CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->side_ev[1], 0));
 		// all pushes have landed once every rank's ship kernels have completed.  The error flags travel with this
 		// barrier and stay on the device: pass 2 checks them itself, the host reads them with the result count
 		clock.begin(7);
 		MDB_TRY(mdb_comm_arena_barrier(ctx, d_flags, d_peer_flags));
+	} else {
+		launch_partition(ctx, grid1, sb, pr);
 	}
 	clock.begin(2);
 

@@ -44,17 +44,33 @@ struct RJShip {
 	unsigned long long *shipped_bytes; // statistics
 };
 
-__device__ __forceinline__ void rj_copy32(void *dst, const void *src)
+// copy nvec 32-byte vectors with the whole CTA, four loads in flight per thread before the four stores
+__device__ __forceinline__ void rj_copy_vectors(char *dst, const char *src, uint32_t nvec)
 {
-	uint32_t w[8];
-	asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-			: "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(src));
-	asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]),
-			"r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+	constexpr int U = 4;
+	for (uint32_t v0 = threadIdx.x; v0 < nvec; v0 += blockDim.x * U) {
+		uint32_t w[U][8];
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const uint32_t v = min(v0 + u * blockDim.x, nvec - 1u); // clamped: keeps the vectors in registers
+			asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+					: "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]), "=r"(w[u][4]), "=r"(w[u][5]), "=r"(w[u][6]), "=r"(w[u][7])
+					: "l"(src + (size_t)v * 32u));
+		}
+#pragma unroll
+		for (int u = 0; u < U; u++) {
+			const uint32_t v = v0 + u * blockDim.x;
+			if (v < nvec)
+				asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + (size_t)v * 32u), "r"(w[u][0]), "r"(w[u][1]),
+						"r"(w[u][2]), "r"(w[u][3]), "r"(w[u][4]), "r"(w[u][5]), "r"(w[u][6]), "r"(w[u][7]) : "memory");
+		}
+	}
 }
 
-// one CTA per partition owned by a peer (grid-stride): push its main and tail stream and their counts
-__global__ void __launch_bounds__(512) k_radix_ship(RJSide s, RJShip sh)
+// one CTA per partition owned by a peer (grid-stride): push its main and tail stream and their counts.
+// Launched either over the whole GPU or - with enough dynamic shared memory to own an SM - on a handful of SMs
+// next to pass 1 of the other join side.
+__global__ void __launch_bounds__(1024) k_radix_ship(RJSide s, RJShip sh)
 {
 	for (int p = blockIdx.x; p < sh.nparts; p += gridDim.x) {
 		const int o = (int)(((uint32_t)(p + 1) * (uint32_t)sh.world - 1u) / (uint32_t)sh.nparts); // owner of p
@@ -62,14 +78,10 @@ __global__ void __launch_bounds__(512) k_radix_ship(RJSide s, RJShip sh)
 			continue;
 		const uint32_t q = (uint32_t)p - (uint32_t)((uint64_t)o * sh.nparts / sh.world);
 		const uint32_t n_main = min(s.cursor[p * RJ_CUR_STRIDE], s.cap), n_tail = min(s.tail_cursor[p * RJ_CUR_STRIDE], s.tail_cap);
-		const char *src = reinterpret_cast<const char*>(s.stream + (size_t)p * s.cap);
-		char *dst = reinterpret_cast<char*>(sh.main[o] + (size_t)q * s.cap);
-		for (uint32_t v = threadIdx.x; v < n_main / 16u; v += blockDim.x)
-			rj_copy32(dst + (size_t)v * 32u, src + (size_t)v * 32u);
-		src = reinterpret_cast<const char*>(s.tail + (size_t)p * s.tail_cap);
-		dst = reinterpret_cast<char*>(sh.tail[o] + (size_t)q * s.tail_cap);
-		for (uint32_t v = threadIdx.x; v < (n_tail + 15u) / 16u; v += blockDim.x)
-			rj_copy32(dst + (size_t)v * 32u, src + (size_t)v * 32u);
+		rj_copy_vectors(reinterpret_cast<char*>(sh.main[o] + (size_t)q * s.cap), reinterpret_cast<const char*>(s.stream + (size_t)p * s.cap),
+				n_main / 16u);
+		rj_copy_vectors(reinterpret_cast<char*>(sh.tail[o] + (size_t)q * s.tail_cap),
+				reinterpret_cast<const char*>(s.tail + (size_t)p * s.tail_cap), (n_tail + 15u) / 16u);
 		if (threadIdx.x == 0) {
 			sh.cursor[o][q] = n_main;
 			sh.tail_cursor[o][q] = n_tail;
