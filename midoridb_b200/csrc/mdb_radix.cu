@@ -79,14 +79,15 @@ static void rj_runs_local(RJRuns *r, const RJSide &s)
 	r->cur_stride[0] = RJ_CUR_STRIDE;
 }
 
+// grid = SMs to use: RJ_SPLIT CTAs are launched for each (together they fill one SM's shared memory and registers)
 static void launch_partition(mdbcu_ctx *ctx, int grid, const RJSide &s, const RJParams &pr)
 {
 	if (s.present)
-		MDB_LAUNCH(ctx, k_radix_partition<true>, grid, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
+		MDB_LAUNCH(ctx, k_radix_partition<true>, grid * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
 	else if (s.all_in_range && pr.range <= 0xffffffffull && ((uintptr_t)s.keys & 31u) == 0)
-		MDB_LAUNCH(ctx, k_radix_partition_fast, grid, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
+		MDB_LAUNCH(ctx, k_radix_partition_fast, grid * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
 	else
-		MDB_LAUNCH(ctx, k_radix_partition<false>, grid, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
+		MDB_LAUNCH(ctx, k_radix_partition<false>, grid * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
 }
 
 int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res)

@@ -32,8 +32,8 @@
 #if RJ_LAB & 8
 // timeline of one warp of CTA 0 (p1_lab3): cycles spent in [insert | wait barrier 1 | flush | wait barrier 2], summed over rounds
 __device__ unsigned long long rj_timeline[4][8];
-#define RJ_STAMP(i) do { if ((RJ_LAB & 8) && blockIdx.x == 0 && (threadIdx.x & 31u) == 0 && (threadIdx.x >> 5) % 10 == 0) { \
-	const long long now_ = clock64(); atomicAdd(&rj_timeline[(threadIdx.x >> 5) / 10][i], (unsigned long long)(now_ - rj_t_)); rj_t_ = now_; } } while (0)
+#define RJ_STAMP(i) do { if ((RJ_LAB & 8) && blockIdx.x == 0 && (threadIdx.x & 31u) == 0 && (threadIdx.x >> 5) % (RJ_P1_THREADS / 96) == 0) { \
+	const long long now_ = clock64(); atomicAdd(&rj_timeline[(threadIdx.x >> 5) / (RJ_P1_THREADS / 96)][i], (unsigned long long)(now_ - rj_t_)); rj_t_ = now_; } } while (0)
 #else
 #define RJ_STAMP(i) do { } while (0)
 #endif
@@ -41,7 +41,7 @@ __device__ unsigned long long rj_timeline[4][8];
 #define RJ_P1_WARPS (RJ_P1_THREADS / 32)
 #define RJ_P1_KEYS 8               // keys per thread per round
 #define RJ_SPILL_CAP 512           // keys per round that may find their staging row full (about 7 expected)
-#define RJ_WARP_PARTS (RJ_MAX_PART / RJ_P1_WARPS) // partitions whose staging rows one warp flushes
+#define RJ_WARP_PARTS (RJ_ROWS / RJ_P1_WARPS) // staging rows one warp flushes
 
 #define RJ_HINT_PREFETCH 1u        // prefetch.global.L2 two tiles ahead
 #define RJ_HINT_LOAD_EVICT_FIRST 2u
@@ -49,14 +49,14 @@ __device__ unsigned long long rj_timeline[4][8];
 #define RJ_HINT_DEFAULT 0u         // (MDBCU_P1_HINTS overrides; none of them pays once the L1 is large enough)
 
 struct RJP1Smem {
-	uint16_t stage[RJ_MAX_PART * RJ_CAP];     // 160 KiB: 20 two-byte slots per partition
-	uint32_t fill[RJ_MAX_PART];               // slots handed out since the last flush (may overshoot RJ_CAP)
+	uint16_t stage[RJ_ROWS * RJ_CAP];         // 20 two-byte slots per staged partition (row r = partition r * RJ_SPLIT + this CTA's residue)
+	uint32_t fill[RJ_ROWS];                   // slots handed out since the last flush (may overshoot RJ_CAP)
 	uint16_t worklist[RJ_P1_WARPS][RJ_WARP_PARTS]; // per warp: those of its partitions that hold a whole sector this round
 	uint32_t spill[RJ_SPILL_CAP];             // (partition << 16 | remainder) of keys whose row was full this round
 	uint32_t spill_n[2];                      // by round parity
 };
 
-static_assert(sizeof(RJP1Smem) <= 195 * 1024, "pass-1 shared memory must stay inside the 196 KiB carve-out");
+static_assert((sizeof(RJP1Smem) + 1024) * RJ_SPLIT <= 196 * 1024, "pass-1 shared memory of all CTAs of an SM must stay inside the 196 KiB carve-out");
 static_assert(RJ_WARP_PARTS == 128, "the flush scan reads four slot counters per lane");
 
 // plain shared-memory atomic: kept in PTX so the compiler does not expand it into warp-aggregation code
@@ -67,10 +67,10 @@ __device__ __forceinline__ uint32_t rj_smem_add(uint32_t *p, uint32_t v)
 	return old;
 }
 
-// hand out the next slot of partition p's staging row
-__device__ __forceinline__ uint32_t rj_fill_claim(RJP1Smem *sm, uint32_t p)
+// hand out the next slot of staging row r
+__device__ __forceinline__ uint32_t rj_fill_claim(RJP1Smem *sm, uint32_t r)
 {
-	return rj_smem_add(&sm->fill[p], 1u);
+	return rj_smem_add(&sm->fill[r], 1u);
 }
 
 __device__ __forceinline__ uint32_t rj_lanemask_lt()
@@ -125,13 +125,16 @@ __device__ static inline void rj_spill(RJP1Smem *sm, const RJParams &pr, uint32_
 		atomicOr(pr.error_flag, RJ_ERR_SKEW);
 }
 
-// insert of one item = (partition << 16 | remainder): slot, store
-__device__ __forceinline__ void rj_insert_one(RJP1Smem *sm, const RJParams &pr, uint32_t item, int par)
+// insert of one item = (partition << 16 | remainder) if its partition is staged by this CTA: slot, store
+__device__ __forceinline__ void rj_insert_one(RJP1Smem *sm, const RJParams &pr, uint32_t item, int par, uint32_t half)
 {
 	const uint32_t p = item >> 16;
-	const uint32_t pos = rj_fill_claim(sm, p);
+	if (RJ_SPLIT > 1 && p % RJ_SPLIT != half)
+		return;
+	const uint32_t r = p / RJ_SPLIT;
+	const uint32_t pos = rj_fill_claim(sm, r);
 	if (pos < RJ_CAP)
-		sm->stage[p * RJ_CAP + pos] = (uint16_t)item;
+		sm->stage[r * RJ_CAP + pos] = (uint16_t)item;
 	else
 		rj_spill(sm, pr, p, item & 0xffffu, par);
 }
@@ -140,33 +143,36 @@ __device__ __forceinline__ void rj_insert_one(RJP1Smem *sm, const RJParams &pr, 
 // otherwise item = key - kmin and every item is a key (lean kernel).
 // All slot requests of a thread are issued back to back (independent shared-memory atomics), then consumed.
 template <bool PACKED>
-__device__ __forceinline__ void rj_insert_items(RJP1Smem *sm, const RJParams &pr, const uint32_t *item, int par)
+__device__ __forceinline__ void rj_insert_items(RJP1Smem *sm, const RJParams &pr, const uint32_t *item, int par, uint32_t half)
 {
-	constexpr bool ALL_VALID = !PACKED;
+	constexpr bool ALL_MINE = !PACKED && RJ_SPLIT == 1; // every item is a key of a partition this CTA stages
 	const int pshift = PACKED ? 16 : pr.shift;
 	const uint32_t rmask = PACKED ? 0xffffu : pr.mask;
 	uint32_t pos[RJ_P1_KEYS];
 #pragma unroll
-	for (int k = 0; k < RJ_P1_KEYS; k++)
-		pos[k] = (ALL_VALID || item[k] != RJ_NONE) ? rj_fill_claim(sm, item[k] >> pshift) : RJ_NONE;
-	uint32_t worst = 0; // largest slot handed to this thread (+1 with holes, so that RJ_NONE counts as 0)
-#pragma unroll
 	for (int k = 0; k < RJ_P1_KEYS; k++) {
 		const uint32_t p = item[k] >> pshift;
-		if (pos[k] < RJ_CAP)
-			sm->stage[p * RJ_CAP + pos[k]] = (uint16_t)(item[k] & rmask);
-		worst = max(worst, ALL_VALID ? pos[k] : pos[k] + 1u);
+		const bool mine = (!PACKED || item[k] != RJ_NONE) && (RJ_SPLIT == 1 || p % RJ_SPLIT == half);
+		pos[k] = mine ? rj_fill_claim(sm, p / RJ_SPLIT) : RJ_NONE;
 	}
-	if (worst >= (ALL_VALID ? RJ_CAP : RJ_CAP + 1u)) { // rare: some row was full
+	uint32_t worst = 0; // largest slot handed to this thread (+1 unless ALL_MINE, so that RJ_NONE counts as 0)
+#pragma unroll
+	for (int k = 0; k < RJ_P1_KEYS; k++) {
+		const uint32_t r = (item[k] >> pshift) / RJ_SPLIT;
+		if (pos[k] < RJ_CAP)
+			sm->stage[r * RJ_CAP + pos[k]] = (uint16_t)(item[k] & rmask);
+		worst = max(worst, ALL_MINE ? pos[k] : pos[k] + 1u);
+	}
+	if (worst >= (ALL_MINE ? RJ_CAP : RJ_CAP + 1u)) { // rare: some row was full
 #pragma unroll
 		for (int k = 0; k < RJ_P1_KEYS; k++)
-			if (pos[k] >= RJ_CAP && (ALL_VALID || item[k] != RJ_NONE))
+			if (pos[k] >= RJ_CAP && pos[k] != RJ_NONE)
 				rj_spill(sm, pr, item[k] >> pshift, item[k] & rmask, par);
 	}
 }
 
 // barrier, every warp flushes the full rows among ITS 128 partitions, spilled keys go to the tail streams, barrier
-__device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par, long long &rj_t_)
+__device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par, uint32_t half, long long &rj_t_)
 {
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	uint16_t *wl = sm->worklist[warp];
@@ -205,13 +211,13 @@ __device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, 
 	RJ_STAMP(4);
 	const bool evict_last = (s.hints & RJ_HINT_STORE_EVICT_LAST) != 0;
 	for (uint32_t w = lane; w < wl_n; w += 32) {
-		const uint32_t p = wl[w];
+		const uint32_t r = wl[w], p = r * RJ_SPLIT + half;
 		const uint32_t at = (RJ_LAB & 2) ? ((warp * 997u + w * 16u) & 0xfff0u) : atomicAdd(&s.cursor[p * RJ_CUR_STRIDE], (uint32_t)RJ_FLUSH);
-		uint2 *row = reinterpret_cast<uint2*>(&sm->stage[p * RJ_CAP]); // 40-byte rows are 8-byte aligned
-		const uint32_t have = sm->fill[p];
+		uint2 *row = reinterpret_cast<uint2*>(&sm->stage[r * RJ_CAP]); // 40-byte rows are 8-byte aligned
+		const uint32_t have = sm->fill[r];
 		const uint2 a = row[0], b = row[1], c = row[2], d = row[3], e = row[4];
 		row[0] = e; // keep the (at most 4) remainders behind the flushed sector
-		sm->fill[p] = min(have, (uint32_t)RJ_CAP) - RJ_FLUSH;
+		sm->fill[r] = min(have, (uint32_t)RJ_CAP) - RJ_FLUSH;
 		if (RJ_LAB & 4)
 			continue;
 		if (at + RJ_FLUSH <= s.cap)
@@ -224,18 +230,19 @@ __device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, 
 	RJ_STAMP(3);
 }
 
-// every partition's partial sector goes to the partition's tail stream
-__device__ static inline void rj_drain(const RJSide &s, const RJParams &pr, RJP1Smem *sm)
+// every staged partition's partial sector goes to the partition's tail stream
+__device__ static inline void rj_drain(const RJSide &s, const RJParams &pr, RJP1Smem *sm, uint32_t half)
 {
-	for (int p = threadIdx.x; p < pr.nparts; p += RJ_P1_THREADS) {
-		const uint32_t f = min(sm->fill[p], (uint32_t)RJ_CAP);
-		if (f == 0)
+	for (uint32_t r = threadIdx.x; r < RJ_ROWS; r += RJ_P1_THREADS) {
+		const uint32_t p = r * RJ_SPLIT + half;
+		const uint32_t f = min(sm->fill[r], (uint32_t)RJ_CAP);
+		if (f == 0 || p >= (uint32_t)pr.nparts)
 			continue;
 		const uint32_t at = atomicAdd(&s.tail_cursor[p * RJ_CUR_STRIDE], f);
 		if (at + f <= s.tail_cap) {
 			uint16_t *dst = s.tail + (size_t)p * s.tail_cap + at;
 			for (uint32_t i = 0; i < f; i++)
-				dst[i] = sm->stage[p * RJ_CAP + i];
+				dst[i] = sm->stage[r * RJ_CAP + i];
 		} else {
 			atomicOr(pr.error_flag, RJ_ERR_STREAM);
 		}
@@ -244,8 +251,8 @@ __device__ static inline void rj_drain(const RJSide &s, const RJParams &pr, RJP1
 
 __device__ static inline void rj_smem_init(RJP1Smem *sm)
 {
-	for (int p = threadIdx.x; p < RJ_MAX_PART; p += RJ_P1_THREADS)
-		sm->fill[p] = 0;
+	for (int r = threadIdx.x; r < RJ_ROWS; r += RJ_P1_THREADS)
+		sm->fill[r] = 0;
 	if (threadIdx.x < 2)
 		sm->spill_n[threadIdx.x] = 0;
 	__syncthreads();
@@ -254,7 +261,7 @@ __device__ static inline void rj_smem_init(RJP1Smem *sm)
 // Pass 1, lean variant: column without NULLs/tombstones whose [min, max] lies inside the partitioned range and
 // key - kmin < 2^32: no per-key validity test, 32-bit arithmetic on the low words, 256-bit key loads
 // (double-buffered in registers: 8 registers per tile in flight).  The ragged tail (< one tile) goes through CTA 0.
-__global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSide s, RJParams pr)
+__global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition_fast(RJSide s, RJParams pr)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	RJP1Smem *sm = reinterpret_cast<RJP1Smem*>(smem_raw);
@@ -262,6 +269,7 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSid
 
 	constexpr uint32_t TILE = RJ_P1_THREADS * RJ_P1_KEYS;
 	const uint32_t tid = threadIdx.x;
+	const uint32_t half = blockIdx.x % RJ_SPLIT, slot = blockIdx.x / RJ_SPLIT, nslots = gridDim.x / RJ_SPLIT; // CTA group = one SM's worth
 	const uint64_t nfull = s.n / TILE;
 	const uint32_t kmin_lo = (uint32_t)(unsigned long long)pr.kmin;
 	const bool pf = (s.hints & RJ_HINT_PREFETCH) != 0, evict_first = (s.hints & RJ_HINT_LOAD_EVICT_FIRST) != 0;
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSid
 	auto load = [&](uint64_t tile, uint32_t *dst) {
 		if (pf) {
 			// pull the tile this CTA will load two rounds from now into L2 (one 128-byte line per thread)
-			const uint64_t pf_first = (tile + 2ull * gridDim.x) * TILE + (uint64_t)tid * 16;
+			const uint64_t pf_first = (tile + 2ull * nslots) * TILE + (uint64_t)tid * 16;
 			if (tid < TILE / 16 && pf_first + 16 <= s.n)
 				asm volatile("prefetch.global.L2 [%0];" ::"l"(s.keys + pf_first));
 		}
@@ -284,35 +292,35 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition_fast(RJSid
 #pragma unroll
 		for (int k = 0; k < RJ_P1_KEYS; k++)
 			item[k] = buf[k] - kmin_lo;
-		rj_insert_items<false>(sm, pr, item, par);
-		rj_round_end(s, pr, sm, par, rj_t_);
+		rj_insert_items<false>(sm, pr, item, par, half);
+		rj_round_end(s, pr, sm, par, half, rj_t_);
 		par ^= 1;
 	};
-	uint64_t tile = blockIdx.x;
+	uint64_t tile = slot;
 	if (tile < nfull)
 		load(tile, buf_a);
 	while (tile < nfull) {
-		uint64_t next = tile + gridDim.x;
+		uint64_t next = tile + nslots;
 		if (next < nfull)
 			load(next, buf_b);
 		round(buf_a);
 		tile = next;
 		if (tile >= nfull)
 			break;
-		next = tile + gridDim.x;
+		next = tile + nslots;
 		if (next < nfull)
 			load(next, buf_a);
 		round(buf_b);
 		tile = next;
 	}
-	if (blockIdx.x == 0 && nfull * TILE != s.n) {
+	if (slot == 0 && nfull * TILE != s.n) {
 		for (uint64_t r = nfull * TILE + tid; r < s.n; r += RJ_P1_THREADS) {
 			const uint32_t d = (uint32_t)(unsigned long long)s.keys[r] - kmin_lo;
-			rj_insert_one(sm, pr, ((d >> pr.shift) << 16) | (d & pr.mask), par);
+			rj_insert_one(sm, pr, ((d >> pr.shift) << 16) | (d & pr.mask), par, half);
 		}
-		rj_round_end(s, pr, sm, par, rj_t_);
+		rj_round_end(s, pr, sm, par, half, rj_t_);
 	}
-	rj_drain(s, pr, sm);
+	rj_drain(s, pr, sm, half);
 }
 
 // generic tile load: 128-bit loads of whole 64-bit keys (range test needs the high words)
@@ -344,7 +352,8 @@ __device__ static inline void rj_load_tile(const RJSide &s, uint64_t tile, int4 
 
 // generic insert phase: range test, NULL/tombstone bitmap, ragged last tile.  FULL: every row of the tile exists
 template <bool HAS_PRESENT, bool FULL>
-__device__ static inline void rj_insert_tile(const RJSide &s, const RJParams &pr, RJP1Smem *sm, const int4 *buf, uint64_t tile, int par)
+__device__ static inline void rj_insert_tile(const RJSide &s, const RJParams &pr, RJP1Smem *sm, const int4 *buf, uint64_t tile, int par,
+		uint32_t half)
 {
 	constexpr uint32_t TILE = RJ_P1_THREADS * RJ_P1_KEYS;
 	const uint64_t base_pair = tile * (TILE / 2);
@@ -368,48 +377,49 @@ __device__ static inline void rj_insert_tile(const RJSide &s, const RJParams &pr
 		item[2 * j] = ok0 ? ((((uint32_t)d0 >> pr.shift) << 16) | ((uint32_t)d0 & pr.mask)) : RJ_NONE;
 		item[2 * j + 1] = ok1 ? ((((uint32_t)d1 >> pr.shift) << 16) | ((uint32_t)d1 & pr.mask)) : RJ_NONE;
 	}
-	rj_insert_items<true>(sm, pr, item, par);
+	rj_insert_items<true>(sm, pr, item, par, half);
 }
 
 // Pass 1, generic variant (NULLs / tombstones / keys outside the partitioned range): same rounds as the lean
 // kernel, whole keys double-buffered in registers (ping-pong, no copies).
 template <bool HAS_PRESENT>
-__global__ void __launch_bounds__(RJ_P1_THREADS, 1) k_radix_partition(RJSide s, RJParams pr)
+__global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition(RJSide s, RJParams pr)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	RJP1Smem *sm = reinterpret_cast<RJP1Smem*>(smem_raw);
 	rj_smem_init(sm);
 
 	constexpr uint32_t TILE = RJ_P1_THREADS * RJ_P1_KEYS;
+	const uint32_t half = blockIdx.x % RJ_SPLIT, slot = blockIdx.x / RJ_SPLIT, nslots = gridDim.x / RJ_SPLIT;
 	const uint64_t ntiles = (s.n + TILE - 1) / TILE;
 	const uint64_t nfull = s.n / TILE; // tiles [0, nfull) are complete
 	int4 buf_a[RJ_P1_KEYS / 2], buf_b[RJ_P1_KEYS / 2];
-	uint64_t tile = blockIdx.x;
+	uint64_t tile = slot;
 	int par = 0;
 	long long rj_t_ = (RJ_LAB & 8) ? clock64() : 0; // (timeline experiments only)
 	if (tile < ntiles)
 		rj_load_tile(s, tile, buf_a);
 	auto round = [&](const int4 *buf, uint64_t t) {
 		if (t < nfull)
-			rj_insert_tile<HAS_PRESENT, true>(s, pr, sm, buf, t, par);
+			rj_insert_tile<HAS_PRESENT, true>(s, pr, sm, buf, t, par, half);
 		else
-			rj_insert_tile<HAS_PRESENT, false>(s, pr, sm, buf, t, par);
-		rj_round_end(s, pr, sm, par, rj_t_);
+			rj_insert_tile<HAS_PRESENT, false>(s, pr, sm, buf, t, par, half);
+		rj_round_end(s, pr, sm, par, half, rj_t_);
 		par ^= 1;
 	};
 	while (tile < ntiles) {
-		uint64_t next = tile + gridDim.x;
+		uint64_t next = tile + nslots;
 		if (next < ntiles)
 			rj_load_tile(s, next, buf_b);
 		round(buf_a, tile);
 		tile = next;
 		if (tile >= ntiles)
 			break;
-		next = tile + gridDim.x;
+		next = tile + nslots;
 		if (next < ntiles)
 			rj_load_tile(s, next, buf_a);
 		round(buf_b, tile);
 		tile = next;
 	}
-	rj_drain(s, pr, sm);
+	rj_drain(s, pr, sm, half);
 }

@@ -6,7 +6,11 @@
 #define RJ_MAX_SHIFT 16            // remainder bits: 2-byte remainders
 #define RJ_CAP 20                  // staging slots per partition in shared memory
 #define RJ_FLUSH 16                // a partition is flushed when 16 remainders (= one 32-byte sector) are staged
-#define RJ_P1_THREADS 1024
+#ifndef RJ_SPLIT
+#define RJ_SPLIT 1                 // pass-1 CTAs per SM: CTA b stages only the partitions p with p % RJ_SPLIT == b % RJ_SPLIT
+#endif                             // (measured with 2: every tile is decoded twice, 1.26 ms against 0.85 ms per launch)
+#define RJ_P1_THREADS (1024 / RJ_SPLIT)
+#define RJ_ROWS (RJ_MAX_PART / RJ_SPLIT) // staging rows per CTA
 #define RJ_NONE 0xffffffffu
 #define RJ_MAX_RANKS 8
 #define RJ_CUR_STRIDE 2            // 32-bit words per partition in the cursor array: [main cursor, tail cursor].  (One 128-byte

@@ -65,9 +65,9 @@ int main(int argc, char **argv)
 			CK(cudaMemsetAsync(s.cursor, 0, (size_t)RJ_MAX_PART * RJ_CUR_STRIDE * 4));
 			CK(cudaEventRecord(e0));
 			if (variant < 8)
-				k_radix_partition_fast<<<sms, RJ_P1_THREADS, sizeof(RJP1Smem)>>>(s, pr);
+				k_radix_partition_fast<<<sms * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem)>>>(s, pr);
 			else
-				k_radix_partition<false><<<sms, RJ_P1_THREADS, sizeof(RJP1Smem)>>>(s, pr);
+				k_radix_partition<false><<<sms * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem)>>>(s, pr);
 			CK(cudaEventRecord(e1));
 			CK(cudaDeviceSynchronize());
 			float ms;
@@ -95,7 +95,7 @@ int main(int argc, char **argv)
 		unsigned long long sum = 0;
 		for (int i = 0; i < 5; i++)
 			sum += tl[w][i];
-		printf("warp %2d of CTA 0:", w * 10);
+		printf("warp %2d of CTA 0:", w * (RJ_P1_THREADS / 96));
 		for (int k = 0; k < 5; k++)
 			printf("  %s %4.1f%%", names[order[k]], 100.0 * tl[w][order[k]] / (double)sum);
 		printf("   (cycles per launch %.0f)\n", sum / 7.0);
