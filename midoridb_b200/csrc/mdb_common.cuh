@@ -51,6 +51,8 @@ struct DevColumn {
 	bool has_nulls = false;
 	bool stats_ok = false;     // imin/imax valid (conservative bounds over present cells)
 	int64_t imin = 0, imax = 0;
+	uint64_t sorted_version = 0; // table version at which `sorted` was computed (0 = never)
+	bool sorted = false;       // cells [0, n_slots) are non-decreasing (checked on demand by the radix join, cached)
 	bool gstats_ok = false;    // gmin/gmax = bounds over ALL ranks' shards (mdbcu_table_sync_stats)
 	int64_t gmin = 0, gmax = 0;
 };
@@ -67,6 +69,7 @@ struct mdbcu_table {
 	bool paged = false;
 	bool all_live = true;      // every slot in [0, n_slots) is live
 	uint64_t global_slots = 0; // sum of n_slots over all ranks' shards (mdbcu_table_sync_stats)
+	uint64_t version = 1;      // bumped by every call that changes the table's contents
 	uint32_t *live = nullptr;  // bitmap
 	std::vector<DevColumn> cols;
 };

@@ -28,6 +28,7 @@ static bool col_all_present(const mdbcu_table *t, int col)
 #include "mdb_radix_pass1.cuh"
 #include "mdb_radix_pass2.cuh"
 #include "mdb_radix_dist.cuh"
+#include "mdb_radix_sorted.cuh"
 
 // dynamic shared memory the side-stream push asks for: it is not used, it makes a push CTA own its SM so that the
 // push takes push_sms SMs and pass 1 of the other side gets all the others
@@ -61,6 +62,35 @@ static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_ta
 	MDB_TRY(tmp.alloc(&s->cursor, (size_t)RJ_MAX_PART * RJ_CUR_STRIDE));
 	s->tail_cursor = s->cursor + 1;
 	CUDA_TRY(ctx, cudaMemsetAsync(s->cursor, 0, (size_t)RJ_MAX_PART * RJ_CUR_STRIDE * sizeof(uint32_t), ctx->stream));
+	return MDBCU_OK;
+}
+
+// Is the key column sorted (non-decreasing, no NULLs, no tombstones)?  Checked once per table version: a cheap look at
+// the first 2^20 rows settles it for unordered data, only a column that passes is read completely.
+static int rj_column_sorted(mdbcu_ctx *ctx, DevTemp &tmp, const mdbcu_table *t, int col, bool *sorted)
+{
+	DevColumn &c = const_cast<mdbcu_table*>(t)->cols[col];
+	if (c.sorted_version == t->version) {
+		*sorted = c.sorted;
+		return MDBCU_OK;
+	}
+	*sorted = false;
+	if (col_all_present(t, col) && t->n_slots >= 2 && t->n_slots < (1ull << 32) && ((uintptr_t)c.data & 31u) == 0) {
+		uint32_t *d_desc;
+		MDB_TRY(tmp.alloc(&d_desc, 1));
+		CUDA_TRY(ctx, cudaMemsetAsync(d_desc, 0, sizeof(uint32_t), ctx->stream));
+		const uint64_t sample = std::min<uint64_t>(t->n_slots, 1ull << 20);
+		for (uint64_t rows : {sample, (uint64_t)t->n_slots}) {
+			MDB_LAUNCH(ctx, k_is_sorted, ctx->num_sms * 8, 256, 0, c.data, rows, d_desc);
+			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar, d_desc, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+			CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+			*sorted = (uint32_t)(ctx->h_scalar[0] & 0xffffffffu) == 0;
+			if (!*sorted || rows == t->n_slots)
+				break;
+		}
+	}
+	c.sorted_version = t->version;
+	c.sorted = *sorted;
 	return MDBCU_OK;
 }
 
@@ -167,8 +197,18 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	// stream capacities must be identical on every rank (the arena slots mirror the local layout)
 	const uint32_t cap_a = rj_stream_cap(dist ? (ta->global_slots + W - 1) / W : ta->n_slots, nparts);
 	const uint32_t cap_b = rj_stream_cap(dist ? (tb->global_slots + W - 1) / W : tb->n_slots, nparts);
-	MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, nparts, cap_a));
-	MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, nparts, cap_b));
+	// a side that is already sorted skips pass 1 (single-GPU plans; sorted shards of a distributed plan are not handled)
+	bool sorted_a = false, sorted_b = false;
+	if (!dist) {
+		MDB_TRY(rj_column_sorted(ctx, tmp, ta, jn.left.col, &sorted_a));
+		MDB_TRY(rj_column_sorted(ctx, tmp, tb, jn.right.col, &sorted_b));
+	}
+	memset(&sa, 0, sizeof(sa));
+	memset(&sb, 0, sizeof(sb));
+	if (!sorted_a)
+		MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, nparts, cap_a));
+	if (!sorted_b)
+		MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, nparts, cap_b));
 	sa.all_in_range = ca.imin >= kmin && ca.imax <= kmax;
 	sb.all_in_range = cb.imin >= kmin && cb.imax <= kmax;
 	pr.kmin = kmin;
@@ -196,8 +236,21 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	}
 
 	RJRuns ra, rb;
-	rj_runs_local(&ra, sa);
-	rj_runs_local(&rb, sb);
+	auto runs_of = [&](RJRuns *r, const RJSide &side, bool sorted, const mdbcu_table *t, int col) -> int {
+		if (!sorted) {
+			rj_runs_local(r, side);
+			return MDBCU_OK;
+		}
+		memset(r, 0, sizeof(*r)); // nsrc = 0: pass 2 reads rows [bnd[p], bnd[p + 1]) of the column itself
+		uint64_t *bnd;
+		MDB_TRY(tmp.alloc(&bnd, (size_t)nparts + 1));
+		MDB_LAUNCH(ctx, k_sorted_bounds, (nparts + 1 + 255) / 256, 256, 0, (const int64_t*)t->cols[col].data, (uint64_t)t->n_slots, pr, bnd);
+		r->sorted_keys = t->cols[col].data;
+		r->sorted_bnd = bnd;
+		return MDBCU_OK;
+	};
+	MDB_TRY(runs_of(&ra, sa, sorted_a, ta, jn.left.col));
+	MDB_TRY(runs_of(&rb, sb, sorted_b, tb, jn.right.col));
 	RJShip ship_a, ship_b;
 	if (dist && W > 1) {
 		// arena of every rank: [side A: W slots][side B: W slots]; slot s receives what rank s pushes
@@ -284,7 +337,8 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	}
 
 	clock.begin(1);
-	launch_partition(ctx, grid1, sa, pr);
+	if (!sorted_a)
+		launch_partition(ctx, grid1, sa, pr);
 	if (dist && W > 1) {
 		// Side A's streams are pushed to their owners by a few SMs WHILE pass 1 of side B runs on the others (pass 1
 		// is bound by shared memory, not by the SM count: giving up 1/9 of the SMs costs it 12 %, the push of A is free)
@@ -308,7 +362,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		// barrier and stay on the device: pass 2 checks them itself, the host reads them with the result count
 		clock.begin(7);
 		MDB_TRY(mdb_comm_arena_barrier(ctx, d_flags, d_peer_flags));
-	} else {
+	} else if (!sorted_b) {
 		launch_partition(ctx, grid1, sb, pr);
 	}
 	clock.begin(2);

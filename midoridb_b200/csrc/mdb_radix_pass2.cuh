@@ -86,10 +86,43 @@ __device__ __forceinline__ void rj_histogram_run(const uint16_t *__restrict__ ru
 	}
 }
 
+// count the keys of rows [lo, hi) of a sorted column (all of them belong to the partition being counted)
+template <int BITS, int THREADS>
+__device__ __forceinline__ void rj_histogram_sorted(const int64_t *__restrict__ keys, uint64_t lo, uint64_t hi, uint32_t kmin_lo,
+		uint32_t mask, uint32_t *cnt)
+{
+	const uint64_t a = min((uint64_t)((lo + 3) & ~3ull), hi), b = max(a, (uint64_t)(hi & ~3ull)); // [a, b): whole 32-byte quads
+	for (uint64_t i = lo + threadIdx.x; i < a; i += THREADS)
+		rj_count<BITS>(cnt, ((uint32_t)(unsigned long long)keys[i] - kmin_lo) & mask);
+	for (uint64_t i = b + threadIdx.x; i < hi; i += THREADS)
+		rj_count<BITS>(cnt, ((uint32_t)(unsigned long long)keys[i] - kmin_lo) & mask);
+	constexpr int MLP = 2;
+	const uint64_t q0 = a / 4, nq = (b - a) / 4;
+	for (uint64_t v0 = threadIdx.x; v0 < nq; v0 += THREADS * MLP) {
+		uint32_t w[MLP][8];
+#pragma unroll
+		for (int u = 0; u < MLP; u++)
+			rj_load256(keys + (q0 + min((uint64_t)(v0 + u * THREADS), nq - 1)) * 4, w[u]);
+#pragma unroll
+		for (int u = 0; u < MLP; u++) {
+			if (v0 + u * THREADS >= nq)
+				continue;
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+				rj_count<BITS>(cnt, (w[u][2 * j] - kmin_lo) & mask);
+		}
+	}
+}
+
 // all streams of partition p on one side; returns the number of remainders (identical in every thread)
 template <int BITS, int THREADS>
-__device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, uint32_t p, uint32_t *cnt)
+__device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, const RJParams &pr, uint32_t p, uint32_t *cnt)
 {
+	if (r.nsrc == 0) {
+		const uint64_t lo = r.sorted_bnd[p], hi = r.sorted_bnd[p + 1];
+		rj_histogram_sorted<BITS, THREADS>(r.sorted_keys, lo, hi, (uint32_t)(unsigned long long)pr.kmin, pr.mask, cnt);
+		return (uint32_t)(hi - lo);
+	}
 	uint32_t total = 0;
 	for (int s = 0; s < r.nsrc; s++) {
 		const uint32_t q = p - r.first[s];
@@ -145,8 +178,8 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 			break;
 
 		// ---- count both sides
-		const uint32_t totA = rj_histogram_side<BITS, THREADS>(a, p, cntA);
-		const uint32_t totB = rj_histogram_side<BITS, THREADS>(b, p, cntB);
+		const uint32_t totA = rj_histogram_side<BITS, THREADS>(a, pr, p, cntA);
+		const uint32_t totB = rj_histogram_side<BITS, THREADS>(b, pr, p, cntB);
 		__syncthreads();
 
 		// ---- checksum + number of groups of this partition

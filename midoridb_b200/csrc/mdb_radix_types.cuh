@@ -44,7 +44,9 @@ struct RJSide {
 // `self` is this GPU's own RJSide (indexed by p); the others are the arena slots the peers pushed into over
 // NVLink (indexed by p - first).
 struct RJRuns {
-	int nsrc;
+	int nsrc;                  // 0: the side is a sorted column, see sorted_keys
+	const int64_t *sorted_keys; // sorted column: partition p = rows [sorted_bnd[p], sorted_bnd[p + 1]) (mdb_radix_sorted.cuh)
+	const uint64_t *sorted_bnd;
 	uint32_t cap, tail_cap;
 	const uint16_t *stream[RJ_MAX_RANKS];
 	const uint16_t *tail[RJ_MAX_RANKS];

@@ -604,6 +604,7 @@ extern "C" int mdbcu_table_append_pages(mdbcu_table *t, const void *pages, size_
 {
 	if (!t)
 		return MDBCU_EERROR;
+	t->version++; // cached per-column facts (sortedness) are stale from here on
 	if ((!pages && n_pages) || page_stride < MDBCU_PAGE_SIZE)
 		return mdb_fail(t->ctx, MDBCU_EERROR, "mdbcu_table_append_pages: bad arguments");
 	return append_pages_common(impl(t), n_pages, pages, page_stride, nullptr);
@@ -613,6 +614,7 @@ extern "C" int mdbcu_table_append_page_ptrs(mdbcu_table *t, const void *const *p
 {
 	if (!t)
 		return MDBCU_EERROR;
+	t->version++; // cached per-column facts (sortedness) are stale from here on
 	if (!page_ptrs && n_pages)
 		return mdb_fail(t->ctx, MDBCU_EERROR, "mdbcu_table_append_page_ptrs: bad arguments");
 	return append_pages_common(impl(t), n_pages, nullptr, 0, page_ptrs);
@@ -622,6 +624,7 @@ extern "C" int mdbcu_table_reload_pages(mdbcu_table *tt, size_t first_page, cons
 {
 	if (!tt)
 		return MDBCU_EERROR;
+	tt->version++; // cached per-column facts (sortedness) are stale from here on
 	TableImpl *t = impl(tt);
 	mdbcu_ctx *ctx = t->ctx;
 	cudaSetDevice(ctx->device);
@@ -669,6 +672,7 @@ extern "C" int mdbcu_table_tombstone(mdbcu_table *tt, const uint64_t *page_idx, 
 {
 	if (!tt)
 		return MDBCU_EERROR;
+	tt->version++; // cached per-column facts (sortedness) are stale from here on
 	TableImpl *t = impl(tt);
 	mdbcu_ctx *ctx = t->ctx;
 	cudaSetDevice(ctx->device);
@@ -786,6 +790,7 @@ extern "C" int mdbcu_table_append_columns(mdbcu_table *tt, size_t n_rows, const 
 {
 	if (!tt)
 		return MDBCU_EERROR;
+	tt->version++; // cached per-column facts (sortedness) are stale from here on
 	TableImpl *t = impl(tt);
 	mdbcu_ctx *ctx = t->ctx;
 	cudaSetDevice(ctx->device);
@@ -892,6 +897,7 @@ extern "C" int mdbcu_table_generate(mdbcu_table *tt, uint64_t n_rows, uint64_t r
 {
 	if (!tt)
 		return MDBCU_EERROR;
+	tt->version++; // cached per-column facts (sortedness) are stale from here on
 	TableImpl *t = impl(tt);
 	mdbcu_ctx *ctx = t->ctx;
 	cudaSetDevice(ctx->device);

@@ -246,23 +246,44 @@ def test_radix_joincount_fastpath(be, shape):
         t.drop()
 
 
-@pytest.mark.parametrize("order", ["ascending", "clustered"])
+@pytest.mark.parametrize("order", ["ascending", "descending", "clustered", "sorted_duplicates", "sorted_with_nulls"])
 def test_radix_joincount_ordered_keys(be, order):
-    """auto-increment style ids (all keys of a tile fall into one or two partitions): whichever path runs - the radix
-    path or, after its skew flag, the general operators - the result equals the oracle's"""
+    """auto-increment style ids (all keys of a tile fall into one or two partitions).  A sorted side without NULLs skips
+    pass 1 and is counted straight from the column; with NULLs it is not eligible and, after the skew flag of pass 1,
+    the general operators answer.  Either way the result equals the oracle's"""
     rng = np.random.default_rng(43)
     n = 1 << 20
+    an = None
     if order == "ascending":
-        a, b = np.arange(n, dtype=np.int64), np.arange(n, dtype=np.int64)[::-1].copy()
-    else:
+        a, b = np.arange(n, dtype=np.int64) + 17, np.arange(n, dtype=np.int64) * 2
+    elif order == "descending":  # only non-decreasing columns skip pass 1
+        a, b = np.arange(n, dtype=np.int64) + 17, (np.arange(n, dtype=np.int64)[::-1] * 2).copy()
+    elif order == "clustered":
         a = np.sort(rng.integers(0, 1 << 21, n))
         b = rng.integers(0, 1 << 21, n)
-    ga, oa = both_tables(be, [I], [a])
+    elif order == "sorted_duplicates":
+        a = np.sort(rng.integers(-(1 << 19), 1 << 19, n))  # about two rows per key, negative keys
+        b = np.sort(rng.integers(-(1 << 18), 1 << 20, n + 12345))
+    else:
+        a = np.arange(n, dtype=np.int64)
+        b = rng.integers(0, n, n)
+        an = (rng.random(n) < 0.01).astype(np.uint8)
+    ga, oa = both_tables(be, [I], [a], None if an is None else [an])
     gb, ob = both_tables(be, [I], [b])
     grows, orows, _, st = run_both(be, [ga, gb], [oa, ob], joins=[((0, 0), (1, 0))], group=[(0, 0)],
                                    out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)])
-    assert st.path in (capi.PATH_RADIX_JOINCOUNT, capi.PATH_GENERAL)
+    if order in ("sorted_with_nulls", "descending"):
+        assert st.path in (capi.PATH_RADIX_JOINCOUNT, capi.PATH_GENERAL)
+    else:
+        assert st.path == capi.PATH_RADIX_JOINCOUNT
     assert helpers.canon(grows) == helpers.canon(orows)
+    # the table changes: the cached "sorted" verdict must not survive
+    if order == "ascending":
+        ga.append_columns([np.array([5, 3, 1], dtype=np.int64)])
+        oa.append_columns([np.array([5, 3, 1], dtype=np.int64)])
+        grows, orows, _, st = run_both(be, [ga, gb], [oa, ob], joins=[((0, 0), (1, 0))], group=[(0, 0)],
+                                       out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)])
+        assert helpers.canon(grows) == helpers.canon(orows)
     for t in (ga, gb):
         t.drop()
 
