@@ -44,22 +44,23 @@ struct RJShip {
 	unsigned long long *shipped_bytes; // statistics
 };
 
-// copy nvec 32-byte vectors with the whole CTA, four loads in flight per thread before the four stores
+// copy nvec 32-byte vectors with one warp, four loads in flight per lane before the four stores
 __device__ __forceinline__ void rj_copy_vectors(char *dst, const char *src, uint32_t nvec)
 {
 	constexpr int U = 4;
-	for (uint32_t v0 = threadIdx.x; v0 < nvec; v0 += blockDim.x * U) {
+	const uint32_t lane = threadIdx.x & 31u;
+	for (uint32_t v0 = lane; v0 < nvec; v0 += 32 * U) {
 		uint32_t w[U][8];
 #pragma unroll
 		for (int u = 0; u < U; u++) {
-			const uint32_t v = min(v0 + u * blockDim.x, nvec - 1u); // clamped: keeps the vectors in registers
+			const uint32_t v = min(v0 + u * 32u, nvec - 1u); // clamped: keeps the vectors in registers
 			asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
 					: "=r"(w[u][0]), "=r"(w[u][1]), "=r"(w[u][2]), "=r"(w[u][3]), "=r"(w[u][4]), "=r"(w[u][5]), "=r"(w[u][6]), "=r"(w[u][7])
 					: "l"(src + (size_t)v * 32u));
 		}
 #pragma unroll
 		for (int u = 0; u < U; u++) {
-			const uint32_t v = v0 + u * blockDim.x;
+			const uint32_t v = v0 + u * 32u;
 			if (v < nvec)
 				asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + (size_t)v * 32u), "r"(w[u][0]), "r"(w[u][1]),
 						"r"(w[u][2]), "r"(w[u][3]), "r"(w[u][4]), "r"(w[u][5]), "r"(w[u][6]), "r"(w[u][7]) : "memory");
@@ -67,22 +68,23 @@ __device__ __forceinline__ void rj_copy_vectors(char *dst, const char *src, uint
 	}
 }
 
-// one CTA per partition owned by a peer (grid-stride): push its main and tail stream and their counts.
-// Launched either over the whole GPU or - with enough dynamic shared memory to own an SM - on a handful of SMs
-// next to pass 1 of the other join side.
+// one WARP per partition owned by a peer (grid-stride over warps: with 8 GPUs a partition's stream is 16 KiB, a CTA
+// per partition would be latency-bound): push its main and tail stream and their counts.  Launched either over the
+// whole GPU or - with enough dynamic shared memory to own an SM - on a handful of SMs next to pass 1 of the other side.
 __global__ void __launch_bounds__(1024) k_radix_ship(RJSide s, RJShip sh)
 {
-	for (int p = blockIdx.x; p < sh.nparts; p += gridDim.x) {
-		const int o = (int)(((uint32_t)(p + 1) * (uint32_t)sh.world - 1u) / (uint32_t)sh.nparts); // owner of p
+	const uint32_t warps = blockDim.x >> 5, gw = blockIdx.x * warps + (threadIdx.x >> 5), nw = gridDim.x * warps;
+	for (uint32_t p = gw; p < (uint32_t)sh.nparts; p += nw) {
+		const int o = (int)(((p + 1) * (uint32_t)sh.world - 1u) / (uint32_t)sh.nparts); // owner of p
 		if (o == sh.self)
 			continue;
-		const uint32_t q = (uint32_t)p - (uint32_t)((uint64_t)o * sh.nparts / sh.world);
+		const uint32_t q = p - (uint32_t)((uint64_t)o * sh.nparts / sh.world);
 		const uint32_t n_main = min(s.cursor[p * RJ_CUR_STRIDE], s.cap), n_tail = min(s.tail_cursor[p * RJ_CUR_STRIDE], s.tail_cap);
 		rj_copy_vectors(reinterpret_cast<char*>(sh.main[o] + (size_t)q * s.cap), reinterpret_cast<const char*>(s.stream + (size_t)p * s.cap),
 				n_main / 16u);
 		rj_copy_vectors(reinterpret_cast<char*>(sh.tail[o] + (size_t)q * s.tail_cap),
 				reinterpret_cast<const char*>(s.tail + (size_t)p * s.tail_cap), (n_tail + 15u) / 16u);
-		if (threadIdx.x == 0) {
+		if ((threadIdx.x & 31u) == 0) {
 			sh.cursor[o][q] = n_main;
 			sh.tail_cursor[o][q] = n_tail;
 			atomicAdd(sh.shipped_bytes, 2ull * (n_main + n_tail) + 8ull);
