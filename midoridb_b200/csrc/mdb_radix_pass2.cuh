@@ -114,9 +114,11 @@ __device__ __forceinline__ void rj_histogram_sorted(const int64_t *__restrict__ 
 	}
 }
 
-// all streams of partition p on one side; returns the number of remainders (identical in every thread)
+// all streams of partition p on one side; returns the number of remainders (identical in every thread).
+// counts[s] = {main, tail} entries of source s, fetched for all sources at once by rj_fetch_counts.
 template <int BITS, int THREADS>
-__device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, const RJParams &pr, uint32_t p, uint32_t *cnt)
+__device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, const RJParams &pr, uint32_t p, uint32_t *cnt,
+		const uint32_t (*counts)[2])
 {
 	if (r.nsrc == 0) {
 		const uint64_t lo = r.sorted_bnd[p], hi = r.sorted_bnd[p + 1];
@@ -126,12 +128,23 @@ __device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, const RJP
 	uint32_t total = 0;
 	for (int s = 0; s < r.nsrc; s++) {
 		const uint32_t q = p - r.first[s];
-		const uint32_t n_main = min(r.cursor[s][q * r.cur_stride[s]], r.cap), n_tail = min(r.tail_cursor[s][q * r.cur_stride[s]], r.tail_cap);
+		const uint32_t n_main = counts[s][0], n_tail = counts[s][1];
 		rj_histogram_run<BITS, THREADS>(r.stream[s] + (size_t)q * r.cap, n_main, cnt);
 		rj_histogram_run<BITS, THREADS>(r.tail[s] + (size_t)q * r.tail_cap, n_tail, cnt);
 		total += n_main + n_tail;
 	}
 	return total;
+}
+
+// one thread per (source, main | tail): with 8 GPUs a partition has 16 streams per side, and 16 dependent cursor loads
+// in a row would cost more than counting the streams
+__device__ __forceinline__ void rj_fetch_counts(const RJRuns &r, uint32_t p, uint32_t (*counts)[2], uint32_t t)
+{
+	const uint32_t s = t >> 1, which = t & 1u;
+	if ((int)s < r.nsrc) {
+		const uint32_t q = (p - r.first[s]) * r.cur_stride[s];
+		counts[s][which] = which ? min(r.tail_cursor[s][q], r.tail_cap) : min(r.cursor[s][q], r.cap);
+	}
 }
 
 // LAYOUT fixes the result columns at compile time (the emit loop is the largest part of this kernel's instruction
@@ -159,6 +172,7 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 	uint32_t *cntA = reinterpret_cast<uint32_t*>(smem_raw);
 	uint32_t *cntB = cntA + words;
 	__shared__ uint32_t s_part, s_sumA, s_sumB;
+	__shared__ uint32_t s_counts[2][RJ_MAX_RANKS][2]; // [side][source][main | tail] entries of the current partition
 	__shared__ uint32_t s_warp[NWARPS + 1];
 	__shared__ unsigned long long s_base;
 	const int tid = threadIdx.x;
@@ -176,10 +190,15 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 		const uint32_t p = s_part;
 		if (p >= (uint32_t)pr.part_end) // this rank owns partitions [part_first, part_end)
 			break;
+		if (tid < 2 * RJ_MAX_RANKS)
+			rj_fetch_counts(a, p, s_counts[0], tid);
+		else if (tid < 4 * RJ_MAX_RANKS)
+			rj_fetch_counts(b, p, s_counts[1], tid - 2 * RJ_MAX_RANKS);
+		__syncthreads();
 
 		// ---- count both sides
-		const uint32_t totA = rj_histogram_side<BITS, THREADS>(a, pr, p, cntA);
-		const uint32_t totB = rj_histogram_side<BITS, THREADS>(b, pr, p, cntB);
+		const uint32_t totA = rj_histogram_side<BITS, THREADS>(a, pr, p, cntA, s_counts[0]);
+		const uint32_t totB = rj_histogram_side<BITS, THREADS>(b, pr, p, cntB, s_counts[1]);
 		__syncthreads();
 
 		// ---- checksum + number of groups of this partition
