@@ -113,24 +113,6 @@ void mdb_comm_destroy(mdbcu_ctx *ctx)
 	ctx->nccl_comm = nullptr;
 }
 
-// byte-granular all-to-all: rank r receives send[send_off[r] .. send_off[r+1]) of every peer at recv_off[peer]
-int mdb_comm_alltoallv_bytes(mdbcu_ctx *ctx, const void *send, const uint64_t *send_off, void *recv, const uint64_t *recv_off)
-{
-	if (!ctx->nccl_comm)
-		return mdb_fail(ctx, MDBCU_EERROR, "distributed plan without mdbcu_comm_init");
-	ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
-	NCCL_TRY(ctx, g_nccl.GroupStart());
-	for (int p = 0; p < ctx->world; p++) {
-		uint64_t sb = send_off[p + 1] - send_off[p], rb = recv_off[p + 1] - recv_off[p];
-		if (sb)
-			NCCL_TRY(ctx, g_nccl.Send((const char*)send + send_off[p], sb, NCCL_UINT8, p, comm, ctx->stream));
-		if (rb)
-			NCCL_TRY(ctx, g_nccl.Recv((char*)recv + recv_off[p], rb, NCCL_UINT8, p, comm, ctx->stream));
-	}
-	NCCL_TRY(ctx, g_nccl.GroupEnd());
-	return MDBCU_OK;
-}
-
 int mdb_comm_allgather_u64(mdbcu_ctx *ctx, const uint64_t *send, uint64_t *recv, size_t count)
 {
 	if (!ctx->nccl_comm)
@@ -139,41 +121,13 @@ int mdb_comm_allgather_u64(mdbcu_ctx *ctx, const uint64_t *send, uint64_t *recv,
 	return MDBCU_OK;
 }
 
-// ---- thin wrappers used by the distributed radix join (mdb_radix_dist.cuh)
+// ---- NCCL is plumbing here (statistics, IPC handles); the join's data moves through the arena below
 
 int mdb_comm_allgather_bytes(mdbcu_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank)
 {
 	if (!ctx->nccl_comm)
 		return mdb_fail(ctx, MDBCU_EERROR, "distributed plan without mdbcu_comm_init");
 	NCCL_TRY(ctx, g_nccl.AllGather(send, recv, bytes_per_rank, NCCL_UINT8, (ncclComm_t)ctx->nccl_comm, ctx->stream));
-	return MDBCU_OK;
-}
-
-int mdb_comm_group_begin(mdbcu_ctx *ctx)
-{
-	if (!ctx->nccl_comm)
-		return mdb_fail(ctx, MDBCU_EERROR, "distributed plan without mdbcu_comm_init");
-	NCCL_TRY(ctx, g_nccl.GroupStart());
-	return MDBCU_OK;
-}
-
-int mdb_comm_group_end(mdbcu_ctx *ctx)
-{
-	NCCL_TRY(ctx, g_nccl.GroupEnd());
-	return MDBCU_OK;
-}
-
-int mdb_comm_send(mdbcu_ctx *ctx, const void *p, size_t bytes, int peer)
-{
-	if (bytes)
-		NCCL_TRY(ctx, g_nccl.Send(p, bytes, NCCL_UINT8, peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
-	return MDBCU_OK;
-}
-
-int mdb_comm_recv(mdbcu_ctx *ctx, void *p, size_t bytes, int peer)
-{
-	if (bytes)
-		NCCL_TRY(ctx, g_nccl.Recv(p, bytes, NCCL_UINT8, peer, (ncclComm_t)ctx->nccl_comm, ctx->stream));
 	return MDBCU_OK;
 }
 
@@ -287,29 +241,3 @@ int mdb_comm_arena_barrier(mdbcu_ctx *ctx, const uint32_t *d_err, uint32_t *d_al
 	return MDBCU_OK;
 }
 
-// cross-rank barrier on the context's stream that leaves every rank's 32-bit flag word in d_all[0 .. world)
-// (no host synchronisation: kernels launched afterwards read the flags on the device)
-int mdb_comm_barrier_gather(mdbcu_ctx *ctx, uint32_t *d_flag, uint32_t *d_all)
-{
-	return mdb_comm_allgather_bytes(ctx, d_flag, d_all, sizeof(uint32_t));
-}
-
-// cross-rank barrier on the context's stream that also ORs a 32-bit flag word over all ranks
-int mdb_comm_barrier_or(mdbcu_ctx *ctx, uint32_t *d_flag, uint32_t *h_or_out)
-{
-	const int W = ctx->world;
-	DevTemp tmp(ctx);
-	uint32_t *d_all;
-	MDB_TRY(tmp.alloc(&d_all, W));
-	MDB_TRY(mdb_comm_allgather_bytes(ctx, d_flag, d_all, sizeof(uint32_t)));
-	if (h_or_out) {
-		std::vector<uint32_t> h(W);
-		CUDA_TRY(ctx, cudaMemcpyAsync(h.data(), d_all, sizeof(uint32_t) * W, cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-		uint32_t v = 0;
-		for (int r = 0; r < W; r++)
-			v |= h[r];
-		*h_or_out = v;
-	}
-	return MDBCU_OK;
-}

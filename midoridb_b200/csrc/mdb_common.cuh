@@ -241,19 +241,11 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res);
 
 // multi-GPU exchange used by the radix join path (mdb_comm.cu)
-int mdb_comm_alltoallv_bytes(mdbcu_ctx *ctx, const void *send, const uint64_t *send_off, void *recv,
-		const uint64_t *recv_off);
 void mdb_comm_destroy(mdbcu_ctx *ctx);
 int mdb_comm_allgather_bytes(mdbcu_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
-int mdb_comm_group_begin(mdbcu_ctx *ctx);
-int mdb_comm_group_end(mdbcu_ctx *ctx);
-int mdb_comm_send(mdbcu_ctx *ctx, const void *p, size_t bytes, int peer);
-int mdb_comm_recv(mdbcu_ctx *ctx, void *p, size_t bytes, int peer);
 int mdb_comm_arena(mdbcu_ctx *ctx, size_t bytes, void **bases);
 int mdb_comm_arena_barrier(mdbcu_ctx *ctx, const uint32_t *d_err, uint32_t *d_all);
 void mdb_comm_arena_destroy(mdbcu_ctx *ctx);
-int mdb_comm_barrier_or(mdbcu_ctx *ctx, uint32_t *d_flag, uint32_t *h_or_out);
-int mdb_comm_barrier_gather(mdbcu_ctx *ctx, uint32_t *d_flag, uint32_t *d_all);
 int mdb_comm_allgather_u64(mdbcu_ctx *ctx, const uint64_t *send, uint64_t *recv, size_t count);
 
 // phase clock: events are only recorded while the query runs; one synchronise at the end

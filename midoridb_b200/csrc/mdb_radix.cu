@@ -160,6 +160,8 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	}
 	if (!dist && ta->n_slots + tb->n_slots < (1ull << 20))
 		return MDBCU_EUNSUPPORTED; // small inputs: general operators (they also return the reference's row order)
+	if (ta->n_slots >= (1ull << 32) || tb->n_slots >= (1ull << 32))
+		return MDBCU_EUNSUPPORTED; // stream positions and per-partition totals are 32-bit
 
 	// only keys inside both columns' [min, max] (zone-map statistics kept by the mirror) can ever match
 	long long kmin = std::max(ca.imin, cb.imin), kmax = std::min(ca.imax, cb.imax);

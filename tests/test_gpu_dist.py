@@ -1,6 +1,6 @@
-"""GPU tests (-m gpu) of the multi-GPU code path on ONE device: a world of size 1 still runs the whole
-partition -> all-gather of chunk counts -> grouped send/recv -> remote directory -> owned-partition pass 2
-pipeline (the peer is the rank itself), so its result must equal the single-GPU path and the oracle.
+"""GPU tests (-m gpu) of the multi-GPU code path on ONE device: a world of size 1 takes the distributed plan's
+decisions (global statistics mandatory, ownership of all partitions, no peer to push to), so its result must equal
+the single-GPU path and the oracle.
 Real 2/4/8-GPU runs use tests/dist_check.py under torchrun (gpurun --gpus N)."""
 import numpy as np
 import pytest
