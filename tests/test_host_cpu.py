@@ -19,6 +19,18 @@ def test_api_symbols_exported():
         assert hasattr(L, name), name
 
 
+def test_every_function_declared_in_the_public_header_is_exported():
+    import os
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "midoridb.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = re.findall(r"^\s*(?:struct\s+\w+\s*\*|[A-Za-z_][\w ]*?[\s\*])\s*(\w+)\s*\([^;{]*\)\s*;", hdr, flags=re.M)
+    assert set(API) <= set(declared)
+    L = mdb.load_library()
+    for name in declared:
+        assert hasattr(L, name), name
+
+
 def test_struct_layouts_match_reference_abi():
     # include/primitive/column.h:30-49, table.h:23-42, datablock.h:9-13, query.h:24-40 on x86-64
     assert C.sizeof(mdb.Column) == 144
