@@ -43,7 +43,9 @@ static uint32_t rj_stream_cap(uint64_t rows, int nparts)
 	return (uint32_t)std::min<uint64_t>(cap, 0x7fffffc0ull);
 }
 
-static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_table *t, int col, int grid, int nparts, uint32_t cap)
+// cursors: RJ_MAX_PART * RJ_CUR_STRIDE zeroed words inside the query's control block
+static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_table *t, int col, int grid, int nparts, uint32_t cap,
+		uint32_t *cursors)
 {
 	memset(s, 0, sizeof(*s));
 	s->keys = t->cols[col].data;
@@ -59,9 +61,8 @@ static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_ta
 		return MDBCU_EUNSUPPORTED;
 	MDB_TRY(tmp.alloc(&s->stream, (size_t)nparts * cap));
 	MDB_TRY(tmp.alloc(&s->tail, (size_t)nparts * s->tail_cap));
-	MDB_TRY(tmp.alloc(&s->cursor, (size_t)RJ_MAX_PART * RJ_CUR_STRIDE));
+	s->cursor = cursors;
 	s->tail_cursor = s->cursor + 1;
-	CUDA_TRY(ctx, cudaMemsetAsync(s->cursor, 0, (size_t)RJ_MAX_PART * RJ_CUR_STRIDE * sizeof(uint32_t), ctx->stream));
 	return MDBCU_OK;
 }
 
@@ -205,12 +206,19 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		MDB_TRY(rj_column_sorted(ctx, tmp, ta, jn.left.col, &sorted_a));
 		MDB_TRY(rj_column_sorted(ctx, tmp, tb, jn.right.col, &sorted_b));
 	}
+	// control block of the query: ONE allocation, ONE memset, ONE read-back
+	//   bytes  0..15  groups emitted, bytes pushed to peers (u64 each)      16..23  error flags, partition counter (u32 each)
+	//   bytes 32..63  every rank's error flags after the exchange (u32 x 8)  64..     cursors of side A, then of side B
+	const size_t cursor_words = (size_t)RJ_MAX_PART * RJ_CUR_STRIDE;
+	uint32_t *ctl;
+	MDB_TRY(tmp.alloc(&ctl, 16 + 2 * cursor_words));
+	CUDA_TRY(ctx, cudaMemsetAsync(ctl, 0, (16 + 2 * cursor_words) * sizeof(uint32_t), ctx->stream));
 	memset(&sa, 0, sizeof(sa));
 	memset(&sb, 0, sizeof(sb));
 	if (!sorted_a)
-		MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, nparts, cap_a));
+		MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, nparts, cap_a, ctl + 16));
 	if (!sorted_b)
-		MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, nparts, cap_b));
+		MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, nparts, cap_b, ctl + 16 + cursor_words));
 	sa.all_in_range = ca.imin >= kmin && ca.imax <= kmax;
 	sb.all_in_range = cb.imin >= kmin && cb.imax <= kmax;
 	pr.kmin = kmin;
@@ -220,19 +228,14 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	pr.nparts = nparts;
 	pr.part_first = (int)((uint64_t)me * nparts / W);
 	pr.part_end = (int)((uint64_t)(me + 1) * nparts / W);
-	uint32_t *d_flags; // [0] error flags, [1] partition counter
-	unsigned long long *d_cursor; // [0] groups emitted, [1] bytes pushed to peers
-	MDB_TRY(tmp.alloc(&d_flags, 2));
-	MDB_TRY(tmp.alloc(&d_cursor, 2));
-	CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint32_t), ctx->stream));
-	CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, 2 * sizeof(unsigned long long), ctx->stream));
+	unsigned long long *d_cursor = reinterpret_cast<unsigned long long*>(ctl); // [0] groups emitted, [1] bytes pushed to peers
+	uint32_t *d_flags = ctl + 4;                                                // [0] error flags, [1] partition counter
 	pr.error_flag = d_flags;
 	pr.peer_flags = nullptr;
 	pr.n_peer_flags = 0;
 	uint32_t *d_peer_flags = nullptr;
 	if (dist && W > 1) {
-		MDB_TRY(tmp.alloc(&d_peer_flags, MDB_MAX_RANKS));
-		CUDA_TRY(ctx, cudaMemsetAsync(d_peer_flags, 0, MDB_MAX_RANKS * sizeof(uint32_t), ctx->stream));
+		d_peer_flags = ctl + 8;
 		pr.peer_flags = d_peer_flags;
 		pr.n_peer_flags = W;
 	}
@@ -303,26 +306,6 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		fill(&ship_b, &rb, lb, half_off + la.bytes * (size_t)W);
 	}
 
-	// upper bound of groups this rank can emit: one per key of the partitions it owns
-	uint64_t cap_groups = std::min<uint64_t>((uint64_t)(pr.part_end - pr.part_first) << shift, range);
-	if (!dist)
-		cap_groups = std::min<uint64_t>(cap_groups, std::min<uint64_t>(ta->n_slots, tb->n_slots));
-	MDB_TRY(mdb_result_alloc(ctx, plan, res, 0, false));
-	RJOut out;
-	memset(&out, 0, sizeof(out));
-	out.nout = plan->n_out;
-	out.cursor = d_cursor;
-	out.cap = cap_groups;
-	for (int o = 0; o < plan->n_out; o++) {
-		mdb_free(ctx, res->cols[o].cells);
-		mdb_free(ctx, res->cols[o].nulls);
-		res->cols[o].nulls = nullptr; // NULL keys never join (executor_select.c:716-738): no NULL cells in this result
-		res->cols[o].cells = nullptr;
-		MDB_TRY(mdb_alloc(ctx, &res->cols[o].cells, cap_groups));
-		out.cells[o] = res->cols[o].cells;
-		out.is_count[o] = plan->out[o].kind == MDBCU_OUT_COUNT_STAR;
-	}
-
 	static bool attr_done = false;
 	if (!attr_done) {
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
@@ -367,6 +350,28 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	} else if (!sorted_b) {
 		launch_partition(ctx, grid1, sb, pr);
 	}
+	// (result columns are allocated here, after pass 1 is on its way, so that the GPU starts the query's first kernel as
+	// early as the host allows)
+	// upper bound of groups this rank can emit: one per key of the partitions it owns
+	uint64_t cap_groups = std::min<uint64_t>((uint64_t)(pr.part_end - pr.part_first) << shift, range);
+	if (!dist)
+		cap_groups = std::min<uint64_t>(cap_groups, std::min<uint64_t>(ta->n_slots, tb->n_slots));
+	MDB_TRY(mdb_result_alloc(ctx, plan, res, 0, false));
+	RJOut out;
+	memset(&out, 0, sizeof(out));
+	out.nout = plan->n_out;
+	out.cursor = d_cursor;
+	out.cap = cap_groups;
+	for (int o = 0; o < plan->n_out; o++) {
+		mdb_free(ctx, res->cols[o].cells);
+		mdb_free(ctx, res->cols[o].nulls);
+		res->cols[o].nulls = nullptr; // NULL keys never join (executor_select.c:716-738): no NULL cells in this result
+		res->cols[o].cells = nullptr;
+		MDB_TRY(mdb_alloc(ctx, &res->cols[o].cells, cap_groups));
+		out.cells[o] = res->cols[o].cells;
+		out.is_count[o] = plan->out[o].kind == MDBCU_OUT_COUNT_STAR;
+	}
+
 	clock.begin(2);
 
 	// 4-bit counters (two CTAs per SM) when keys are mostly unique per side, 8-bit otherwise; a wrapped
@@ -402,17 +407,14 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		cudaError_t e = cudaGetLastError();
 		if (e != cudaSuccess)
 			return mdb_fail(ctx, MDBCU_ECUDA, "radix join launch failed: %s", cudaGetErrorString(e));
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar, d_cursor, 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar + 2, d_flags, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-		if (d_peer_flags)
-			CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar + 3, d_peer_flags, MDB_MAX_RANKS * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar, ctl, 64, cudaMemcpyDeviceToHost, ctx->stream)); // the control block's head
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 		ngroups = ctx->h_scalar[0];
 		flags = (uint32_t)(ctx->h_scalar[2] & 0xffffffffu);
 		if (d_peer_flags) {
 			uint32_t any = 0;
 			for (int r = 0; r < W; r++)
-				any |= reinterpret_cast<const uint32_t*>(ctx->h_scalar + 3)[r];
+				any |= reinterpret_cast<const uint32_t*>(ctx->h_scalar + 4)[r];
 			if (any)
 				return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "distributed radix join: pass 1 failed on some rank (flags %u: "
 						"1 = a partition received more than twice its share of the keys, 4 = extreme skew)", any);

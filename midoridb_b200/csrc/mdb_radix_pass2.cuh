@@ -128,7 +128,14 @@ __device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, const RJP
 	uint32_t total = 0;
 	for (int s = 0; s < r.nsrc; s++) {
 		const uint32_t q = p - r.first[s];
-		const uint32_t n_main = counts[s][0], n_tail = counts[s][1];
+		uint32_t n_main, n_tail;
+		if (counts) {
+			n_main = counts[s][0];
+			n_tail = counts[s][1];
+		} else {
+			n_main = min(r.cursor[s][q * r.cur_stride[s]], r.cap);
+			n_tail = min(r.tail_cursor[s][q * r.cur_stride[s]], r.tail_cap);
+		}
 		rj_histogram_run<BITS, THREADS>(r.stream[s] + (size_t)q * r.cap, n_main, cnt);
 		rj_histogram_run<BITS, THREADS>(r.tail[s] + (size_t)q * r.tail_cap, n_tail, cnt);
 		total += n_main + n_tail;
@@ -190,15 +197,18 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 		const uint32_t p = s_part;
 		if (p >= (uint32_t)pr.part_end) // this rank owns partitions [part_first, part_end)
 			break;
-		if (tid < 2 * RJ_MAX_RANKS)
-			rj_fetch_counts(a, p, s_counts[0], tid);
-		else if (tid < 4 * RJ_MAX_RANKS)
-			rj_fetch_counts(b, p, s_counts[1], tid - 2 * RJ_MAX_RANKS);
-		__syncthreads();
+		const bool many = a.nsrc > 1 || b.nsrc > 1; // multi-GPU plan: fetch all stream counts of the partition at once
+		if (many) {
+			if (tid < 2 * RJ_MAX_RANKS)
+				rj_fetch_counts(a, p, s_counts[0], tid);
+			else if (tid < 4 * RJ_MAX_RANKS)
+				rj_fetch_counts(b, p, s_counts[1], tid - 2 * RJ_MAX_RANKS);
+			__syncthreads();
+		}
 
 		// ---- count both sides
-		const uint32_t totA = rj_histogram_side<BITS, THREADS>(a, pr, p, cntA, s_counts[0]);
-		const uint32_t totB = rj_histogram_side<BITS, THREADS>(b, pr, p, cntB, s_counts[1]);
+		const uint32_t totA = rj_histogram_side<BITS, THREADS>(a, pr, p, cntA, many ? s_counts[0] : nullptr);
+		const uint32_t totB = rj_histogram_side<BITS, THREADS>(b, pr, p, cntB, many ? s_counts[1] : nullptr);
 		__syncthreads();
 
 		// ---- checksum + number of groups of this partition
