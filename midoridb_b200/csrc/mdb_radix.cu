@@ -311,12 +311,18 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
-		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 0>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
-		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 1>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
-		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 2>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
+		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_ship, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_SHIP_SMEM));
 		attr_done = true;
 	}
@@ -387,7 +393,13 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		const int grid2 = std::max(1, std::min(pr.part_end - pr.part_first, ctx->num_sms * (bitsw == 4 ? 2 : 1)));
 		// result layout known at compile time for the two common shapes: [key, count] and [count, key]
 		const int layout = out.nout != 2 ? 0 : (!out.is_count[0] && out.is_count[1]) ? 1 : (out.is_count[0] && !out.is_count[1]) ? 2 : 0;
-#define RJ_LAUNCH2(B, T, L) MDB_LAUNCH(ctx, (k_radix_joincount<B, T, L>), grid2, T, smem2, ra, rb, pr, out, d_flags + 1)
+#define RJ_LAUNCH2(B, T, L)                                                                                   \
+	do {                                                                                                  \
+		if (ra.nsrc > 1 || rb.nsrc > 1)                                                               \
+			MDB_LAUNCH(ctx, (k_radix_joincount<B, T, L, true>), grid2, T, smem2, ra, rb, pr, out, d_flags + 1);  \
+		else                                                                                          \
+			MDB_LAUNCH(ctx, (k_radix_joincount<B, T, L, false>), grid2, T, smem2, ra, rb, pr, out, d_flags + 1); \
+	} while (0)
 		if (bitsw == 4) {
 			if (layout == 1)
 				RJ_LAUNCH2(4, 512, 1);

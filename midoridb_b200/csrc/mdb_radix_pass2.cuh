@@ -116,7 +116,7 @@ __device__ __forceinline__ void rj_histogram_sorted(const int64_t *__restrict__ 
 
 // all streams of partition p on one side; returns the number of remainders (identical in every thread).
 // counts[s] = {main, tail} entries of source s, fetched for all sources at once by rj_fetch_counts.
-template <int BITS, int THREADS>
+template <int BITS, int THREADS, bool MULTI>
 __device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, const RJParams &pr, uint32_t p, uint32_t *cnt,
 		const uint32_t (*counts)[2])
 {
@@ -129,7 +129,7 @@ __device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, const RJP
 	for (int s = 0; s < r.nsrc; s++) {
 		const uint32_t q = p - r.first[s];
 		uint32_t n_main, n_tail;
-		if (counts) {
+		if (MULTI) {
 			n_main = counts[s][0];
 			n_tail = counts[s][1];
 		} else {
@@ -156,7 +156,8 @@ __device__ __forceinline__ void rj_fetch_counts(const RJRuns &r, uint32_t p, uin
 
 // LAYOUT fixes the result columns at compile time (the emit loop is the largest part of this kernel's instruction
 // stream): 0 = read RJOut at run time, 1 = [key, count], 2 = [count, key]
-template <int BITS, int THREADS, int LAYOUT>
+// MULTI: multi-GPU plan (several source streams per partition; their counts are fetched together)
+template <int BITS, int THREADS, int LAYOUT, bool MULTI>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32_t *__restrict__ part_counter)
 {
@@ -197,8 +198,7 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 		const uint32_t p = s_part;
 		if (p >= (uint32_t)pr.part_end) // this rank owns partitions [part_first, part_end)
 			break;
-		const bool many = a.nsrc > 1 || b.nsrc > 1; // multi-GPU plan: fetch all stream counts of the partition at once
-		if (many) {
+		if (MULTI) {
 			if (tid < 2 * RJ_MAX_RANKS)
 				rj_fetch_counts(a, p, s_counts[0], tid);
 			else if (tid < 4 * RJ_MAX_RANKS)
@@ -207,8 +207,8 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 		}
 
 		// ---- count both sides
-		const uint32_t totA = rj_histogram_side<BITS, THREADS>(a, pr, p, cntA, many ? s_counts[0] : nullptr);
-		const uint32_t totB = rj_histogram_side<BITS, THREADS>(b, pr, p, cntB, many ? s_counts[1] : nullptr);
+		const uint32_t totA = rj_histogram_side<BITS, THREADS, MULTI>(a, pr, p, cntA, s_counts[0]);
+		const uint32_t totB = rj_histogram_side<BITS, THREADS, MULTI>(b, pr, p, cntB, s_counts[1]);
 		__syncthreads();
 
 		// ---- checksum + number of groups of this partition
