@@ -318,6 +318,17 @@ def main():
                      "peak": peak * world, "unit": "GB/s", "frac": step_gbs / (peak * world), "algorithmic_bytes_per_step": alg_bytes,
                      "phase_ms": {"partition": phase[1], "histogram_join_emit": phase[2], "exchange_push": phase[6], "barriers_and_other": phase[7]}}
 
+    # multi-GPU: bytes this rank pushed to its peers over NVLink per step, against the nominal NVLink 5 rate per direction.
+    # Only the push of join side B is exposed (phase "exchange_push"); side A's push overlaps pass 1 of side B.
+    nvlink = None
+    if world > 1:
+        sent = dist.max(float(st.exchange_bytes))
+        push_ms = dist.max(phase[6])
+        nvlink = {"bytes_pushed_per_rank_per_step": sent, "exposed_push_ms": push_ms,
+                  "achieved_gbs_exposed_half": (sent / 2.0) / (push_ms / 1000.0) / 1e9 if push_ms > 0 else None,
+                  "peak_gbs_per_direction": 900.0, "peak_source": "nominal NVLink 5 (18 links x 50 GB/s), not measured here",
+                  "what": "2-byte remainders of the partitions owned by peers; 8-byte keys never cross the link"}
+
     # ---- e2e: the same query through the C ABI from HOST page images (reference row format, pinned memory)
     e2e = None
     if not args.no_e2e:
@@ -335,7 +346,7 @@ def main():
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
                 "data": "synthetic", "config": workload_config(args, world), "wall_ms_per_step": wall_ms / args.steps,
                 "result_groups": int(total_groups), "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "roofline_step": roofline_step, "e2e": e2e, "cpu_baseline": cpu_baseline}
+                "roofline_step": roofline_step, "nvlink": nvlink, "e2e": e2e, "cpu_baseline": cpu_baseline}
         print(json.dumps(line))
     dist.close()
 

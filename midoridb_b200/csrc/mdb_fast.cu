@@ -555,13 +555,3 @@ int mdb_select_scan_agg(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *re
 	ctx->stats.dominant_bytes = 8ull * t->n_slots * sp.ncols;
 	return MDBCU_OK;
 }
-
-// ===================================================================================== small-build star join
-
-int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res)
-{
-	(void)ctx;
-	(void)plan;
-	(void)res;
-	return MDBCU_EUNSUPPORTED; // config 5 currently runs on the general operators
-}

@@ -340,3 +340,45 @@ def test_generate_is_sharding_invariant_and_join_properties(be):
     assert np.array_equal(cnts[order], (ca * cb)[want_keys])
     ta.drop()
     tb.drop()
+
+
+@pytest.mark.parametrize("fact_first", [False, True])
+def test_star_join_fastpath(be, fact_first):
+    """BASELINE config 5 shape: small dimension with unique dense keys, large fact table, GROUP BY a dimension column
+    with MIN / MAX / SUM / COUNT over fact columns: direct-addressed star join == oracle (ints bit-exact, DOUBLE SUM 1e-9)"""
+    rng = np.random.default_rng(51)
+    nd, nf = 60000, (1 << 20) + 4321
+    d_id = (rng.permutation(65536)[:nd] + 1000).astype(np.int64)        # unique, some keys of the range missing
+    d_g = rng.integers(-7, 1017, nd)
+    f_fk = rng.integers(900, 1000 + 65536 + 100, nf)                     # some foreign keys match nothing
+    f_m = rng.integers(-(1 << 40), 1 << 40, nf)
+    f_x = rng.random(nf) * 100.0
+    f_fk_null = (rng.random(nf) < 0.01).astype(np.uint8)
+    f_m_null = (rng.random(nf) < 0.05).astype(np.uint8)
+    gd, od = both_tables(be, [I, I], [d_id, d_g])
+    gf, of = both_tables(be, [I, I, D], [f_fk, f_m, f_x], [f_fk_null, f_m_null, None])
+    if fact_first:
+        gt, ot, d, f = [gf, gd], [of, od], 1, 0
+    else:
+        gt, ot, d, f = [gd, gf], [od, of], 0, 1
+    # (the ON operands name the earlier table first: column 0 is the key of both tables)
+    kw = dict(joins=[((0, 0), (1, 0))], group=[(d, 1)],
+              out=[(OUT_COLUMN, d, 1), (OUT_MIN, f, 1), (OUT_MAX, f, 1), (OUT_COUNT_STAR,), (OUT_SUM, f, 2)])
+    grows, orows, _, st = run_both(be, gt, ot, **kw)
+    assert st.path == capi.PATH_DIRECT_STAR
+    assert len(orows) > 1000
+    assert helpers.canon_close(grows, orows, rel=1e-9)
+    # AVG and COUNT(col) through the same kernel
+    kw["out"] = [(OUT_AVG, f, 1), (OUT_COLUMN, d, 1), (OUT_COUNT_COL, f, 1), (OUT_AVG, f, 2)]
+    grows, orows, _, st = run_both(be, gt, ot, **kw)
+    assert st.path == capi.PATH_DIRECT_STAR
+    assert helpers.canon_close(grows, orows, rel=1e-9)
+    # a dimension with a duplicate key is not a star dimension: the general operators answer, same result as the oracle
+    gd.append_columns([d_id[:3].copy(), np.array([1, 2, 3], dtype=np.int64)])
+    od.append_columns([d_id[:3].copy(), np.array([1, 2, 3], dtype=np.int64)])
+    kw["out"] = [(OUT_COLUMN, d, 1), (OUT_MIN, f, 1), (OUT_COUNT_STAR,)]
+    grows, orows, _, st = run_both(be, gt, ot, **kw)
+    assert st.path == capi.PATH_GENERAL
+    assert helpers.canon_close(grows, orows, rel=1e-9)
+    for t in (gd, gf):
+        t.drop()
