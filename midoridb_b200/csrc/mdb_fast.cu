@@ -178,36 +178,89 @@ __global__ void __launch_bounds__(SA_THREADS, (NA >= 4 ? 2 : 3)) k_scan_filter_a
 	const uint64_t stride = (uint64_t)gridDim.x * SA_THREADS;
 	uint64_t quad = (uint64_t)blockIdx.x * SA_THREADS + threadIdx.x;
 
-	constexpr int UNROLL = 2;
+	// Eight rows per thread and iteration (two 256-bit loads per referenced column).  The plan is decoded once per
+	// batch, not once per row: first the rows' verdict as an 8-bit mask (column by column), then aggregate by aggregate.
+	constexpr int UNROLL = 2, ROWS = 4 * UNROLL;
 	for (; quad + (UNROLL - 1) * stride < nquads; quad += UNROLL * stride) {
-		uint32_t raw[UNROLL][NC][8];
-		uint32_t pw[UNROLL][NC];
+		uint32_t raw[NC][UNROLL][8], pbits[NC];
 #pragma unroll
-		for (int u = 0; u < UNROLL; u++) {
-			const uint64_t qi = quad + u * stride;
+		for (int c = 0; c < NC; c++) {
+			pbits[c] = 0;
 #pragma unroll
-			for (int c = 0; c < NC; c++) {
+			for (int u = 0; u < UNROLL; u++) {
+				const uint64_t qi = quad + u * stride;
 				const char *src = reinterpret_cast<const char*>(sp.cols[c].data) + qi * 32;
 				asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-						: "=r"(raw[u][c][0]), "=r"(raw[u][c][1]), "=r"(raw[u][c][2]), "=r"(raw[u][c][3]), "=r"(raw[u][c][4]),
-						  "=r"(raw[u][c][5]), "=r"(raw[u][c][6]), "=r"(raw[u][c][7]) : "l"(src));
-				pw[u][c] = sp.cols[c].present ? sp.cols[c].present[qi >> 3] : 0xffffffffu;
+						: "=r"(raw[c][u][0]), "=r"(raw[c][u][1]), "=r"(raw[c][u][2]), "=r"(raw[c][u][3]), "=r"(raw[c][u][4]),
+						  "=r"(raw[c][u][5]), "=r"(raw[c][u][6]), "=r"(raw[c][u][7]) : "l"(src));
+				const uint32_t pw = sp.cols[c].present ? sp.cols[c].present[qi >> 3] : 0xffffffffu;
+				pbits[c] |= ((pw >> ((qi & 7) * 4)) & 0xfu) << (4 * u);
 			}
 		}
+		uint32_t ok = (1u << ROWS) - 1u;
 #pragma unroll
-		for (int u = 0; u < UNROLL; u++) {
-			const uint64_t qi = quad + u * stride;
-			const int bit = (int)((qi & 7) * 4);
+		for (int c = 0; c < NC; c++) {
+			const SACol &col = sp.cols[c];
+			if (!col.has_range) // uniform
+				continue;
+			uint32_t in = 0;
+			if (col.is_dbl) {
 #pragma unroll
-			for (int k = 0; k < 4; k++) {
-				long long v[NC];
-				bool pr[NC];
-#pragma unroll
-				for (int c = 0; c < NC; c++) {
-					v[c] = (long long)(((unsigned long long)raw[u][c][2 * k + 1] << 32) | raw[u][c][2 * k]);
-					pr[c] = (pw[u][c] >> (bit + k)) & 1;
+				for (int r = 0; r < ROWS; r++) {
+					const double d = __hiloint2double((int)raw[c][r / 4][2 * (r % 4) + 1], (int)raw[c][r / 4][2 * (r % 4)]);
+					const bool lo = col.dlo_incl ? d >= col.dlo : d > col.dlo;
+					const bool hi = col.dhi_incl ? d <= col.dhi : d < col.dhi;
+					in |= (lo && hi) ? (1u << r) : 0u;
 				}
-				sa_row<NC, NA>(sp, st, v, pr);
+			} else {
+#pragma unroll
+				for (int r = 0; r < ROWS; r++) {
+					const long long v = (long long)(((unsigned long long)raw[c][r / 4][2 * (r % 4) + 1] << 32) | raw[c][r / 4][2 * (r % 4)]);
+					in |= (v >= col.ilo && v <= col.ihi) ? (1u << r) : 0u;
+				}
+			}
+			ok &= in & pbits[c];
+		}
+		st.rows += __popc(ok);
+#pragma unroll
+		for (int a = 0; a < NA; a++) {
+			const int kind = sp.aggs[a].kind, ac = sp.aggs[a].col; // uniform
+			if (kind == MDBCU_OUT_COUNT_STAR) {
+				st.nn[a] += __popc(ok);
+				continue;
+			}
+#pragma unroll
+			for (int c = 0; c < NC; c++) {
+				if (ac != c)
+					continue;
+				const uint32_t take = ok & pbits[c];
+				st.nn[a] += __popc(take);
+				const bool dbl = sp.cols[c].is_dbl;
+				if (kind == MDBCU_OUT_SUM || kind == MDBCU_OUT_AVG) {
+					if (dbl) {
+						double sum = __longlong_as_double(st.acc[a]);
+#pragma unroll
+						for (int r = 0; r < ROWS; r++)
+							sum += ((take >> r) & 1u) ? __hiloint2double((int)raw[c][r / 4][2 * (r % 4) + 1], (int)raw[c][r / 4][2 * (r % 4)]) : 0.0;
+						st.acc[a] = __double_as_longlong(sum);
+					} else {
+						unsigned long long sum = (unsigned long long)st.acc[a];
+#pragma unroll
+						for (int r = 0; r < ROWS; r++)
+							sum += ((take >> r) & 1u) ? (((unsigned long long)raw[c][r / 4][2 * (r % 4) + 1] << 32) | raw[c][r / 4][2 * (r % 4)]) : 0ull;
+						st.acc[a] = (long long)sum;
+					}
+				} else if (kind == MDBCU_OUT_MIN || kind == MDBCU_OUT_MAX) {
+					long long best = st.acc[a];
+#pragma unroll
+					for (int r = 0; r < ROWS; r++) {
+						const long long x = (long long)(((unsigned long long)raw[c][r / 4][2 * (r % 4) + 1] << 32) | raw[c][r / 4][2 * (r % 4)]);
+						const long long y = dbl ? mdb_dbl_to_ordered(x) : x;
+						if ((take >> r) & 1u)
+							best = kind == MDBCU_OUT_MIN ? min(best, y) : max(best, y);
+					}
+					st.acc[a] = best;
+				}
 			}
 		}
 	}
