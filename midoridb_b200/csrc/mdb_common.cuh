@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <chrono>
 #include <string>
 #include <vector>
 
@@ -118,6 +120,31 @@ void mdb_set_global_error(const char *msg);
 
 #define CUDA_CHECK_LAUNCH(ctx) CUDA_TRY(ctx, cudaGetLastError())
 
+// MDBCU_TRACE=1: path decisions; 2: also host calls that stall a query (pool growth)
+static inline int mdb_trace_level()
+{
+	static int level = -1;
+	if (level < 0) {
+		const char *e = getenv("MDBCU_TRACE");
+		level = e ? atoi(e) : 0;
+	}
+	return level;
+}
+
+// host wall clock between two points of a query, printed under MDBCU_TRACE=2
+struct HostLap {
+	std::chrono::steady_clock::time_point prev = std::chrono::steady_clock::now();
+	void operator()(const char *where, unsigned long long n = 0)
+	{
+		if (mdb_trace_level() < 2)
+			return;
+		auto t = std::chrono::steady_clock::now();
+		fprintf(stderr, "[mdbcu] %-28s %8.2f ms host  (%llu)\n", where,
+				std::chrono::duration<double, std::milli>(t - prev).count(), n);
+		prev = t;
+	}
+};
+
 // ---------------------------------------------------------------- memory (stream-ordered pool)
 
 template <typename T>
@@ -125,7 +152,13 @@ static inline int mdb_alloc(mdbcu_ctx *ctx, T **out, size_t count)
 {
 	void *p = nullptr;
 	size_t bytes = (count ? count : 1) * sizeof(T);
+	auto t0 = std::chrono::steady_clock::now();
 	cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+	if (mdb_trace_level() >= 2) {
+		double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+		if (ms > 0.2)
+			fprintf(stderr, "[mdbcu] slow allocation: %zu bytes took %.2f ms\n", bytes, ms);
+	}
 	if (e != cudaSuccess) {
 		*out = nullptr;
 		return mdb_fail(ctx, e == cudaErrorMemoryAllocation ? MDBCU_ENOMEM : MDBCU_ECUDA,

@@ -729,6 +729,7 @@ static int join_step(mdbcu_ctx *ctx, const mdbcu_plan *plan, int j, Tuples *ts)
 		return MDBCU_OK;
 	}
 
+	HostLap lap;
 	DevTemp tmp(ctx);
 	uint64_t cap = 1024;
 	while (cap < rt->n_slots * 2)
@@ -745,6 +746,7 @@ static int join_step(mdbcu_ctx *ctx, const mdbcu_plan *plan, int j, Tuples *ts)
 	MDB_TRY(tmp.alloc(&first_row, ts->n));
 	MDB_TRY(tmp.alloc(&out_off, ts->n));
 	MDB_TRY(tmp.alloc(&d_total, 1));
+	lap("join: allocate", cap);
 	MDB_LAUNCH(ctx, k_fill_i64, grid_for(ctx, cap, 256), 256, 0, keys, cap, HT_EMPTY);
 	CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, (cap + 2) * sizeof(uint32_t), ctx->stream));
 	CUDA_TRY(ctx, cudaMemsetAsync(fill, 0, (cap + 2) * sizeof(uint32_t), ctx->stream));
@@ -765,9 +767,12 @@ static int join_step(mdbcu_ctx *ctx, const mdbcu_plan *plan, int j, Tuples *ts)
 	CUDA_CHECK_LAUNCH(ctx);
 	MDB_TRY(mdb_scan_u32_u64(ctx, matches, out_off, ts->n, d_total));
 	uint64_t total = 0;
+	lap("join: launches", ts->n);
 	MDB_TRY(mdb_read_u64(ctx, d_total, &total));
+	lap("join: build+count (sync)", total);
 
 	MDB_TRY(alloc_out_tuples(ctx, &out, ts->ntab + 1, total, &arr));
+	lap("join: allocate output", total);
 	if (total) {
 		MDB_LAUNCH(ctx, k_join_probe_emit, gp, 256, 0, to_dev(*ts), (const uint32_t*)matches, (const uint64_t*)first_row,
 				(const uint64_t*)out_off, (const uint32_t*)rows, arr);
@@ -819,9 +824,59 @@ __device__ static inline unsigned long long pack_rids(const DGroupSpec *sp, cons
 }
 
 // slot layout: [0, cap) hashed keys, cap = key INT64_MIN, cap+1 = NULL group (NULLs collate equal, :1476-1482)
-__global__ void k_group_update(const DGroupSpec *__restrict__ sp, TuplesDev ts, long long *__restrict__ keys, uint64_t cap_mask,
-		unsigned long long *__restrict__ first_key, uint32_t *__restrict__ used)
+//
+// Hot groups (a Zipf foreign key sends 12 % of the rows to one slot) would serialise on one L2 atomic unit, so each
+// CTA keeps a direct-mapped cache of `cache_entries` groups in shared memory: [tag | first row | (acc, nn) per
+// aggregate], E words each. A row whose slot owns (or can claim) its cache line updates shared memory; any other row
+// goes to the global accumulators as before. The cache is merged into the global accumulators once per CTA.
+// cache_entries == 0: no cache (more aggregates than 48 KiB of shared memory hold).
+__device__ static inline long long group_acc_init(int kind)
 {
+	return kind == MDBCU_OUT_MIN ? INT64_MAX : kind == MDBCU_OUT_MAX ? INT64_MIN : 0;
+}
+
+__device__ static inline void group_acc_merge(const DOut &out, long long *acc, long long v)
+{
+	switch (out.kind) {
+	case MDBCU_OUT_SUM: case MDBCU_OUT_AVG:
+		if (out.is_dbl)
+			atomicAdd((double*)acc, __longlong_as_double(v));
+		else
+			atomicAdd((unsigned long long*)acc, (unsigned long long)v);
+		break;
+	case MDBCU_OUT_MIN:
+		atomicMin(acc, v);
+		break;
+	case MDBCU_OUT_MAX:
+		atomicMax(acc, v);
+		break;
+	}
+}
+
+__global__ void k_group_update(const DGroupSpec *__restrict__ sp, TuplesDev ts, long long *__restrict__ keys, uint64_t cap_mask,
+		unsigned long long *__restrict__ first_key, uint32_t *__restrict__ used, uint32_t cache_entries)
+{
+	extern __shared__ unsigned long long s_cache[];
+	const uint32_t E = cache_entries;
+	const unsigned long long NO_TAG = ~0ull;
+
+	if (E) {
+		for (uint32_t e = threadIdx.x; e < 2 * E; e += blockDim.x)
+			s_cache[e] = NO_TAG; // tags, then first rows
+		int a = 0;
+		for (int o = 0; o < sp->n_out; o++) {
+			if (sp->out[o].kind == MDBCU_OUT_COLUMN)
+				continue;
+			long long init = group_acc_init(sp->out[o].kind);
+			for (uint32_t e = threadIdx.x; e < E; e += blockDim.x) {
+				s_cache[(2 + 2 * a) * E + e] = (unsigned long long)init;
+				s_cache[(3 + 2 * a) * E + e] = 0;
+			}
+			a++;
+		}
+		__syncthreads();
+	}
+
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < ts.n; i += (uint64_t)gridDim.x * blockDim.x) {
 		uint64_t slot;
 		if (sp->n_group == 0) {
@@ -850,36 +905,70 @@ __global__ void k_group_update(const DGroupSpec *__restrict__ sp, TuplesDev ts, 
 				slot = ht_insert(keys, cap_mask, key);
 			}
 		}
-		used[slot] = 1;
+
+		// slots are hash positions already: their low bits index the cache
+		bool hit = false;
+		uint32_t e = (uint32_t)slot & (E - 1);
+		if (E) {
+			unsigned long long tag = s_cache[e];
+			if (tag == NO_TAG) {
+				tag = atomicCAS(&s_cache[e], NO_TAG, (unsigned long long)slot);
+				if (tag == NO_TAG)
+					tag = slot;
+			}
+			hit = tag == slot;
+		}
+
+		if (!hit)
+			used[slot] = 1;
 		if (sp->pack_ok)
-			atomicMin(&first_key[slot], pack_rids(sp, ts, i));
+			atomicMin(hit ? &s_cache[E + e] : &first_key[slot], pack_rids(sp, ts, i));
+		int a = 0;
 		for (int o = 0; o < sp->n_out; o++) {
 			const DOut &out = sp->out[o];
 			if (out.kind == MDBCU_OUT_COLUMN)
 				continue;
+			unsigned long long *nn = hit ? &s_cache[(3 + 2 * a) * E + e] : &out.nn[slot];
+			long long *acc = hit ? (long long*)&s_cache[(2 + 2 * a) * E + e] : &out.acc[slot];
+			a++;
 			if (out.kind == MDBCU_OUT_COUNT_STAR) {
-				atomicAdd(&out.nn[slot], 1ull);
+				atomicAdd(nn, 1ull);
 				continue;
 			}
 			uint32_t r = ts.rid[out.tbl][i];
 			if (out.present && !mdb_bit(out.present, r))
 				continue;
 			long long v = out.data[r];
-			atomicAdd(&out.nn[slot], 1ull);
-			switch (out.kind) {
-			case MDBCU_OUT_SUM: case MDBCU_OUT_AVG:
-				if (out.is_dbl)
-					atomicAdd((double*)&out.acc[slot], __longlong_as_double(v));
-				else
-					atomicAdd((unsigned long long*)&out.acc[slot], (unsigned long long)v);
-				break;
-			case MDBCU_OUT_MIN:
-				atomicMin(&out.acc[slot], out.is_dbl ? mdb_dbl_to_ordered(v) : v);
-				break;
-			case MDBCU_OUT_MAX:
-				atomicMax(&out.acc[slot], out.is_dbl ? mdb_dbl_to_ordered(v) : v);
-				break;
-			}
+			atomicAdd(nn, 1ull);
+			if (out.kind == MDBCU_OUT_MIN || out.kind == MDBCU_OUT_MAX)
+				v = out.is_dbl ? mdb_dbl_to_ordered(v) : v;
+			group_acc_merge(out, acc, v);
+		}
+	}
+
+	if (!E)
+		return;
+	__syncthreads();
+	for (uint32_t e = threadIdx.x; e < E; e += blockDim.x) {
+		unsigned long long slot = s_cache[e];
+		if (slot == NO_TAG)
+			continue;
+		used[slot] = 1;
+		if (sp->pack_ok)
+			atomicMin(&first_key[slot], s_cache[E + e]);
+		int a = 0;
+		for (int o = 0; o < sp->n_out; o++) {
+			const DOut &out = sp->out[o];
+			if (out.kind == MDBCU_OUT_COLUMN)
+				continue;
+			long long acc = (long long)s_cache[(2 + 2 * a) * E + e];
+			unsigned long long nn = s_cache[(3 + 2 * a) * E + e];
+			a++;
+			if (nn == 0)
+				continue;
+			atomicAdd(&out.nn[slot], nn);
+			if (out.acc)
+				group_acc_merge(out, &out.acc[slot], acc);
 		}
 	}
 }
@@ -1126,6 +1215,7 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 			cap <<= 1;
 	uint64_t nslots = cap + 3;
 
+	HostLap lap;
 	DevTemp tmp(ctx);
 	long long *keys;
 	unsigned long long *first_key;
@@ -1157,16 +1247,30 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 		MDB_LAUNCH(ctx, k_fill_i64, grid_for(ctx, nslots, 256), 256, 0, d.acc, nslots, init);
 	}
 	CUDA_TRY(ctx, cudaMemcpyAsync(d_sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, ctx->stream));
+	lap("aggregate: allocate + init", nslots);
 
-	MDB_LAUNCH(ctx, k_group_update, grid_for(ctx, ts.n, 256), 256, 0, (const DGroupSpec*)d_sp, to_dev(ts), keys, cap - 1,
-			first_key, used);
+	// per-CTA cache of hot groups: the largest power of two of entries that fits 48 KiB (none if even 256 do not)
+	int n_agg = 0;
+	for (int o = 0; o < plan->n_out; o++)
+		n_agg += sp.out[o].kind != MDBCU_OUT_COLUMN;
+	const size_t entry_bytes = 8 * (2 + 2 * (size_t)n_agg);
+	uint32_t cache_entries = 2048;
+	while (cache_entries >= 256 && cache_entries * entry_bytes > 48 * 1024)
+		cache_entries >>= 1;
+	if (cache_entries < 256 || !getenv("MDBCU_GROUP_CACHE")) // opt-in until the GPU parity run has covered it
+		cache_entries = 0;
+	MDB_LAUNCH(ctx, k_group_update, grid_for(ctx, ts.n, 256), 256, cache_entries * entry_bytes, (const DGroupSpec*)d_sp,
+			to_dev(ts), keys, cap - 1, first_key, used, cache_entries);
 	CUDA_CHECK_LAUNCH(ctx);
 	MDB_LAUNCH(ctx, k_flags_to_bits, grid_for(ctx, nslots, 256), 256, 0, (const uint32_t*)used, nslots, bits);
 	CUDA_CHECK_LAUNCH(ctx);
 
 	Tuples slots;
+	lap("aggregate: launches", ts.n);
 	MDB_TRY(compact_tuples(ctx, bits, nslots, nullptr, 1, &slots));
+	lap("aggregate: compact (sync)", slots.n);
 	int rc = mdb_result_alloc(ctx, plan, res, slots.n, sp.pack_ok != 0);
+	lap("aggregate: result alloc", slots.n);
 	if (rc == MDBCU_OK && slots.n) {
 		DResultCols rcols;
 		memset(&rcols, 0, sizeof(rcols));
@@ -1216,27 +1320,35 @@ int mdb_select_general(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res
 	PhaseClock clock(ctx);
 	int rc;
 
+	HostLap lap; // MDBCU_TRACE=2: host wall time of each operator (includes the stream synchronisations inside it)
+
 	ctx->stats.path = MDBCU_PATH_GENERAL;
 	clock.begin(0);
 	rc = scan_live(ctx, plan->tables[0], &ts);
+	lap("general: scan", ts.n);
 	for (int j = 0; rc == MDBCU_OK && j < plan->n_joins; j++) {
 		clock.begin(j == 0 ? 2 : 3);
 		rc = join_step(ctx, plan, j, &ts);
+		lap("general: join", ts.n);
 	}
 	if (rc == MDBCU_OK) {
 		clock.begin(0);
 		rc = filter_tuples(ctx, plan, &ts);
+		lap("general: filter", ts.n);
 	}
 	if (rc == MDBCU_OK) {
 		if (plan->n_group > 0 || plan_has_aggregate(plan)) {
 			clock.begin(4);
 			rc = aggregate_tuples(ctx, plan, ts, res);
+			lap("general: aggregate", ts.n);
 		} else {
 			clock.begin(5);
 			rc = project_tuples(ctx, plan, ts, res);
+			lap("general: project", ts.n);
 		}
 	}
 	free_tuples(ctx, ts);
 	clock.finish();
+	lap("general: finish", ts.n);
 	return rc;
 }
