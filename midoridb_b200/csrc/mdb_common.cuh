@@ -42,6 +42,12 @@ struct mdbcu_ctx {
 	uint64_t *h_scalar = nullptr; // pinned, 64 entries
 	uint64_t *d_scalar = nullptr; // device, 64 entries
 	cudaEvent_t user_events[MDBCU_EVENT_SLOTS] = {};
+	// scratch arena of the general operators: their temporaries are bump-allocated here in stack order (DevTemp) because
+	// the stream-ordered pool takes 1-5 ms of host time for every block of hundreds of MB (MDBCU_TRACE=2 shows them).
+	// scratch_top may run past scratch_cap: the overflow comes from the pool and the arena is regrown to scratch_peak
+	// when the query has finished (mdb_scratch_settle).
+	char *scratch = nullptr;
+	size_t scratch_cap = 0, scratch_top = 0, scratch_peak = 0;
 };
 
 struct DevColumn {
@@ -174,32 +180,74 @@ static inline void mdb_free(mdbcu_ctx *ctx, void *p)
 		cudaFreeAsync(p, ctx->stream);
 }
 
-// RAII holder for query temporaries
+// RAII holder for query temporaries. use_scratch: take them from the context's scratch arena (operators of the
+// general path: one stream, scopes strictly nested, so releasing = moving the top back).
 struct DevTemp {
 	mdbcu_ctx *ctx;
 	std::vector<void*> ptrs;
-	explicit DevTemp(mdbcu_ctx *c) : ctx(c) {}
+	bool use_scratch;
+	size_t mark;
+	explicit DevTemp(mdbcu_ctx *c, bool scratch = false) : ctx(c), use_scratch(scratch), mark(c->scratch_top) {}
 	~DevTemp()
 	{
 		for (void *p : ptrs)
 			mdb_free(ctx, p);
+		if (use_scratch)
+			ctx->scratch_top = mark;
 	}
 	template <typename T>
 	int alloc(T **out, size_t count)
 	{
+		if (use_scratch) {
+			size_t bytes = ((count ? count : 1) * sizeof(T) + 511) & ~(size_t)511;
+			size_t off = ctx->scratch_top;
+			ctx->scratch_top += bytes;
+			if (ctx->scratch_top > ctx->scratch_peak)
+				ctx->scratch_peak = ctx->scratch_top;
+			if (off + bytes <= ctx->scratch_cap) {
+				*out = (T*)(ctx->scratch + off);
+				return MDBCU_OK;
+			}
+		}
 		int rc = mdb_alloc(ctx, out, count);
 		if (rc == MDBCU_OK)
 			ptrs.push_back(*out);
 		return rc;
 	}
-	// hand ownership of p to the caller
-	void release(void *p)
-	{
-		for (auto &q : ptrs)
-			if (q == p)
-				q = nullptr;
-	}
 };
+
+// after a query: grow the arena to the largest footprint seen (at most a quarter of the device memory)
+static inline void mdb_scratch_settle(mdbcu_ctx *ctx)
+{
+	ctx->scratch_top = 0;
+	if (ctx->scratch_peak <= ctx->scratch_cap)
+		return;
+	size_t free_b = 0, total_b = 0;
+	cudaStreamSynchronize(ctx->stream);
+	if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) {
+		cudaGetLastError();
+		return;
+	}
+	size_t want = (ctx->scratch_peak + (ctx->scratch_peak >> 3) + ((size_t)2 << 20)) & ~(((size_t)2 << 20) - 1);
+	if (want > total_b / 4 || want > (free_b + ctx->scratch_cap) / 2) {
+		ctx->scratch_peak = ctx->scratch_cap; // does not fit: stay with the pool for the overflow
+		return;
+	}
+	if (ctx->scratch)
+		cudaFree(ctx->scratch);
+	ctx->scratch = nullptr;
+	ctx->scratch_cap = 0;
+	void *p = nullptr;
+	if (cudaMalloc(&p, want) != cudaSuccess) {
+		cudaGetLastError();
+		ctx->scratch_peak = 0;
+		return;
+	}
+	ctx->scratch = (char*)p;
+	ctx->scratch_cap = want;
+	if (mdb_trace_level() >= 1)
+		fprintf(stderr, "[mdbcu] scratch arena grown to %zu MiB\n", want >> 20);
+}
 
 // ---------------------------------------------------------------- device helpers
 

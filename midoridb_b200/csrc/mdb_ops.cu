@@ -115,7 +115,7 @@ static int scan_impl(mdbcu_ctx *ctx, const TIn *in, uint64_t *out, size_t n, uin
 		CUDA_CHECK_LAUNCH(ctx);
 		return MDBCU_OK;
 	}
-	DevTemp tmp(ctx);
+	DevTemp tmp(ctx, true);
 	uint64_t *sums, *offs;
 	MDB_TRY(tmp.alloc(&sums, nblocks));
 	MDB_TRY(tmp.alloc(&offs, nblocks));
@@ -227,7 +227,7 @@ static int compact_tuples(mdbcu_ctx *ctx, const uint32_t *bits, uint64_t n, cons
 	out->n = 0;
 	if (n == 0)
 		return MDBCU_OK;
-	DevTemp tmp(ctx);
+	DevTemp tmp(ctx, true);
 	uint64_t words = (n + 31) / 32;
 	size_t nblocks = mdb_div_up(words, CMP_THREADS);
 	uint32_t *counts;
@@ -507,7 +507,7 @@ static int filter_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, Tuples *ts)
 		return MDBCU_OK;
 	DPredProgram h;
 	MDB_TRY(build_pred(ctx, plan, &h));
-	DevTemp tmp(ctx);
+	DevTemp tmp(ctx, true);
 	DPredProgram *d_prog;
 	uint32_t *bits;
 	MDB_TRY(tmp.alloc(&d_prog, 1));
@@ -730,7 +730,7 @@ static int join_step(mdbcu_ctx *ctx, const mdbcu_plan *plan, int j, Tuples *ts)
 	}
 
 	HostLap lap;
-	DevTemp tmp(ctx);
+	DevTemp tmp(ctx, true);
 	uint64_t cap = 1024;
 	while (cap < rt->n_slots * 2)
 		cap <<= 1;
@@ -1216,7 +1216,7 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 	uint64_t nslots = cap + 3;
 
 	HostLap lap;
-	DevTemp tmp(ctx);
+	DevTemp tmp(ctx, true);
 	long long *keys;
 	unsigned long long *first_key;
 	uint32_t *used, *bits;
@@ -1257,7 +1257,7 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 	uint32_t cache_entries = 2048;
 	while (cache_entries >= 256 && cache_entries * entry_bytes > 48 * 1024)
 		cache_entries >>= 1;
-	if (cache_entries < 256 || !getenv("MDBCU_GROUP_CACHE")) // opt-in until the GPU parity run has covered it
+	if (cache_entries < 256 || getenv("MDBCU_NO_GROUP_CACHE")) // the switch is for A/B measurements
 		cache_entries = 0;
 	MDB_LAUNCH(ctx, k_group_update, grid_for(ctx, ts.n, 256), 256, cache_entries * entry_bytes, (const DGroupSpec*)d_sp,
 			to_dev(ts), keys, cap - 1, first_key, used, cache_entries);
@@ -1296,7 +1296,7 @@ static int project_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples &
 	MDB_TRY(mdb_result_alloc(ctx, plan, res, ts.n, sp.pack_ok != 0));
 	if (ts.n == 0)
 		return MDBCU_OK;
-	DevTemp tmp(ctx);
+	DevTemp tmp(ctx, true);
 	DGroupSpec *d_sp;
 	MDB_TRY(tmp.alloc(&d_sp, 1));
 	CUDA_TRY(ctx, cudaMemcpyAsync(d_sp, &sp, sizeof(sp), cudaMemcpyHostToDevice, ctx->stream));

@@ -89,6 +89,7 @@ extern "C" int mdbcu_select(mdbcu_ctx *ctx, const struct mdbcu_plan *plan, mdbcu
 	}
 	ctx->stats.total_kernel_launches = ctx->total_launches;
 	ctx->stats.kernel_launches = ctx->total_launches - total_before;
+	mdb_scratch_settle(ctx);
 	if (rc != MDBCU_OK) {
 		cudaStreamSynchronize(ctx->stream);
 		cudaGetLastError();

@@ -105,6 +105,7 @@ extern "C" void mdbcu_shutdown(mdbcu_ctx *ctx)
 	mdb_comm_destroy(ctx);
 	cudaFreeHost(ctx->h_scalar);
 	cudaFree(ctx->d_scalar);
+	cudaFree(ctx->scratch);
 	if (ctx->side_stream) {
 		cudaStreamDestroy(ctx->side_stream);
 		cudaEventDestroy(ctx->side_ev[0]);
