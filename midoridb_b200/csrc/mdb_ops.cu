@@ -501,20 +501,32 @@ static int build_pred(mdbcu_ctx *ctx, const mdbcu_plan *plan, DPredProgram *h)
 	return MDBCU_OK;
 }
 
-static int filter_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, Tuples *ts)
+// WHERE verdicts of the tuples as a bitmap in `tmp` (nullptr: no predicate, every tuple qualifies)
+static int eval_pred_bits(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples &ts, DevTemp &tmp, uint32_t **bits_out)
 {
-	if (plan->n_pred == 0 || ts->n == 0)
+	*bits_out = nullptr;
+	if (plan->n_pred == 0 || ts.n == 0)
 		return MDBCU_OK;
 	DPredProgram h;
 	MDB_TRY(build_pred(ctx, plan, &h));
-	DevTemp tmp(ctx, true);
 	DPredProgram *d_prog;
 	uint32_t *bits;
 	MDB_TRY(tmp.alloc(&d_prog, 1));
-	MDB_TRY(tmp.alloc(&bits, (ts->n + 31) / 32));
+	MDB_TRY(tmp.alloc(&bits, (ts.n + 31) / 32));
 	CUDA_TRY(ctx, cudaMemcpyAsync(d_prog, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
-	MDB_LAUNCH(ctx, k_eval_pred, grid_for(ctx, ts->n, 256), 256, 0, (const DPredProgram*)d_prog, to_dev(*ts), bits);
+	MDB_LAUNCH(ctx, k_eval_pred, grid_for(ctx, ts.n, 256), 256, 0, (const DPredProgram*)d_prog, to_dev(ts), bits);
 	CUDA_CHECK_LAUNCH(ctx);
+	*bits_out = bits;
+	return MDBCU_OK;
+}
+
+static int filter_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, Tuples *ts)
+{
+	DevTemp tmp(ctx, true);
+	uint32_t *bits;
+	MDB_TRY(eval_pred_bits(ctx, plan, *ts, tmp, &bits));
+	if (!bits)
+		return MDBCU_OK;
 	Tuples out;
 	MDB_TRY(compact_tuples(ctx, bits, ts->n, ts, ts->ntab, &out));
 	free_tuples(ctx, *ts);
@@ -805,6 +817,8 @@ struct DGroupSpec {
 	int32_t n_out;
 	int32_t ntab;
 	int32_t pack_ok;         // order keys are available
+	int32_t dense;           // single INT group key with a narrow zone map: slot = key - dense_min, no hash table
+	long long dense_min;
 	int32_t pack_shift[MDBCU_MAX_TABLES];
 	struct {
 		int32_t tbl, is_dbl, mode; // mode 0: whole 64-bit key (single group column), 1: low 32 bits packed
@@ -854,7 +868,8 @@ __device__ static inline void group_acc_merge(const DOut &out, long long *acc, l
 }
 
 __global__ void k_group_update(const DGroupSpec *__restrict__ sp, TuplesDev ts, long long *__restrict__ keys, uint64_t cap_mask,
-		unsigned long long *__restrict__ first_key, uint32_t *__restrict__ used, uint32_t cache_entries)
+		unsigned long long *__restrict__ first_key, uint32_t *__restrict__ used, uint32_t cache_entries,
+		const uint32_t *__restrict__ keep)
 {
 	extern __shared__ unsigned long long s_cache[];
 	const uint32_t E = cache_entries;
@@ -879,6 +894,8 @@ __global__ void k_group_update(const DGroupSpec *__restrict__ sp, TuplesDev ts, 
 
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < ts.n; i += (uint64_t)gridDim.x * blockDim.x) {
 		uint64_t slot;
+		if (keep && !mdb_bit(keep, i))
+			continue; // WHERE verdicts of the tuples (the filter was not materialised)
 		if (sp->n_group == 0) {
 			slot = 0;
 		} else {
@@ -901,6 +918,8 @@ __global__ void k_group_update(const DGroupSpec *__restrict__ sp, TuplesDev ts, 
 			if (any_null) {
 				// the NULL group; composite keys containing NULLs are rejected on the host (build_group_spec)
 				slot = cap_mask + 2;
+			} else if (sp->dense) {
+				slot = (uint64_t)key - (uint64_t)sp->dense_min;
 			} else {
 				slot = ht_insert(keys, cap_mask, key);
 			}
@@ -1016,7 +1035,7 @@ __global__ void k_group_emit(const DGroupSpec *__restrict__ sp, const uint32_t *
 		bool key_null = sp->n_group > 0 && slot == cap_mask + 2;
 		long long key = 0;
 		if (sp->n_group > 0 && !key_null)
-			key = slot == cap_mask + 1 ? HT_EMPTY : keys[slot];
+			key = slot == cap_mask + 1 ? HT_EMPTY : sp->dense ? (long long)(slot + (uint64_t)sp->dense_min) : keys[slot];
 		for (int o = 0; o < sp->n_out; o++) {
 			const DOut &out = sp->out[o];
 			long long cell = 0;
@@ -1194,7 +1213,8 @@ static bool plan_has_aggregate(const mdbcu_plan *plan)
 	return false;
 }
 
-static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples &ts, mdbcu_result *res)
+// keep: optional WHERE verdict bitmap over the tuples (bit i = tuple i qualifies)
+static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples &ts, const uint32_t *keep, mdbcu_result *res)
 {
 	DGroupSpec sp;
 	MDB_TRY(build_group_spec(ctx, plan, ts.ntab, &sp));
@@ -1209,10 +1229,27 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 	if (ts.n == 0)
 		return mdb_result_alloc(ctx, plan, res, 0, false); // no qualifying row: no result row (executor keeps zero rows)
 
+	// a single INT key whose zone map is narrow is its own slot number (tables small enough to stay in L2, nothing to probe)
+	if (plan->n_group == 1 && sp.g[0].mode == 0 && !sp.g[0].is_dbl) {
+		const DevColumn &gc = plan->tables[plan->group[0].tbl]->cols[plan->group[0].col];
+		if (gc.stats_ok && gc.imin <= gc.imax && gc.imin > INT64_MIN) {
+			unsigned long long range = (unsigned long long)gc.imax - (unsigned long long)gc.imin + 1ull;
+			if (range != 0 && range <= std::max<unsigned long long>(1ull << 16, 4ull * ts.n)) {
+				sp.dense = 1;
+				sp.dense_min = gc.imin;
+			}
+		}
+	}
+
 	uint64_t cap = 1024;
-	if (plan->n_group > 0)
+	if (sp.dense) {
+		const DevColumn &gc = plan->tables[plan->group[0].tbl]->cols[plan->group[0].col];
+		while (cap < (unsigned long long)gc.imax - (unsigned long long)gc.imin + 1ull)
+			cap <<= 1;
+	} else if (plan->n_group > 0) {
 		while (cap < ts.n * 2)
 			cap <<= 1;
+	}
 	uint64_t nslots = cap + 3;
 
 	HostLap lap;
@@ -1221,12 +1258,13 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 	unsigned long long *first_key;
 	uint32_t *used, *bits;
 	DGroupSpec *d_sp;
-	MDB_TRY(tmp.alloc(&keys, cap));
+	MDB_TRY(tmp.alloc(&keys, sp.dense ? 1 : cap));
 	MDB_TRY(tmp.alloc(&first_key, nslots));
 	MDB_TRY(tmp.alloc(&used, nslots));
 	MDB_TRY(tmp.alloc(&bits, (nslots + 31) / 32));
 	MDB_TRY(tmp.alloc(&d_sp, 1));
-	MDB_LAUNCH(ctx, k_fill_i64, grid_for(ctx, cap, 256), 256, 0, keys, cap, HT_EMPTY);
+	if (!sp.dense)
+		MDB_LAUNCH(ctx, k_fill_i64, grid_for(ctx, cap, 256), 256, 0, keys, cap, HT_EMPTY);
 	MDB_LAUNCH(ctx, k_fill_u64, grid_for(ctx, nslots, 256), 256, 0, first_key, nslots, ~0ull);
 	CUDA_TRY(ctx, cudaMemsetAsync(used, 0, nslots * sizeof(uint32_t), ctx->stream));
 
@@ -1260,7 +1298,7 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 	if (cache_entries < 256 || getenv("MDBCU_NO_GROUP_CACHE")) // the switch is for A/B measurements
 		cache_entries = 0;
 	MDB_LAUNCH(ctx, k_group_update, grid_for(ctx, ts.n, 256), 256, cache_entries * entry_bytes, (const DGroupSpec*)d_sp,
-			to_dev(ts), keys, cap - 1, first_key, used, cache_entries);
+			to_dev(ts), keys, cap - 1, first_key, used, cache_entries, keep);
 	CUDA_CHECK_LAUNCH(ctx);
 	MDB_LAUNCH(ctx, k_flags_to_bits, grid_for(ctx, nslots, 256), 256, 0, (const uint32_t*)used, nslots, bits);
 	CUDA_CHECK_LAUNCH(ctx);
@@ -1331,15 +1369,19 @@ int mdb_select_general(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res
 		rc = join_step(ctx, plan, j, &ts);
 		lap("general: join", ts.n);
 	}
+	const bool aggregates = plan->n_group > 0 || plan_has_aggregate(plan);
+	DevTemp verdicts(ctx, true);
+	uint32_t *keep = nullptr;
 	if (rc == MDBCU_OK) {
 		clock.begin(0);
-		rc = filter_tuples(ctx, plan, &ts);
+		// an aggregate consumes the verdict bitmap directly; a projection needs the surviving tuples materialised
+		rc = aggregates ? eval_pred_bits(ctx, plan, ts, verdicts, &keep) : filter_tuples(ctx, plan, &ts);
 		lap("general: filter", ts.n);
 	}
 	if (rc == MDBCU_OK) {
-		if (plan->n_group > 0 || plan_has_aggregate(plan)) {
+		if (aggregates) {
 			clock.begin(4);
-			rc = aggregate_tuples(ctx, plan, ts, res);
+			rc = aggregate_tuples(ctx, plan, ts, keep, res);
 			lap("general: aggregate", ts.n);
 		} else {
 			clock.begin(5);

@@ -382,3 +382,47 @@ def test_star_join_fastpath(be, fact_first):
     assert helpers.canon_close(grows, orows, rel=1e-9)
     for t in (gd, gf):
         t.drop()
+
+
+@pytest.mark.parametrize("mode", ["dense", "dense_negative_nulls", "hash_wide", "hash_double", "hash_composite"])
+def test_group_by_slot_modes(be, mode):
+    """the hash aggregate's slot schemes (direct slots for a narrow INT key, hash table otherwise), each with a WHERE whose
+    verdict bitmap is consumed by the aggregate, > 2048 groups so that the per-CTA group cache has conflicts, NULL group,
+    INT64_MIN key"""
+    rng = np.random.default_rng(77)
+    n = 30000
+    v = (rng.random(n) * 1000).round(2)
+    vn = (rng.random(n) < 0.1).astype(np.uint8)
+    w = rng.integers(-50, 50, n)
+    kn = None
+    types = [I, D, I]
+    group = [(0, 0)]
+    if mode == "dense":
+        k = rng.integers(0, 5000, n)
+    elif mode == "dense_negative_nulls":
+        k = rng.integers(-3000, 3000, n)
+        kn = (rng.random(n) < 0.05).astype(np.uint8)
+    elif mode == "hash_wide":
+        k = rng.integers(-2500, 2500, n) * (10**12)
+        k[:7] = np.iinfo(np.int64).min
+        kn = (rng.random(n) < 0.05).astype(np.uint8)
+    elif mode == "hash_double":
+        types = [D, D, I]
+        k = rng.integers(0, 4000, n) / 8.0
+        k[:5] = -0.0
+        k[5:9] = 0.0
+    else:
+        k = rng.integers(0, 70, n)
+        group = [(0, 0), (0, 2)]
+    gt, ot = both_tables(be, types, [k, v, w], [kn, vn, None])
+    out = [(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,), (OUT_COUNT_COL, 0, 1), (OUT_SUM, 0, 1), (OUT_MIN, 0, 2), (OUT_MAX, 0, 1), (OUT_AVG, 0, 2)]
+    if mode == "hash_composite":
+        out.insert(1, (OUT_COLUMN, 0, 2))
+    for pred in (None, [("col", 0, 2), ("int", 10), ("cmp", 1), ("col", 0, 1), ("dbl", 900.0), ("cmp", 1), ("and",)]):
+        kw = dict(group=group, out=out)
+        if pred:
+            kw["pred"] = pred
+        grows, orows, _, st = run_both(be, [gt], [ot], flags=PLAN_NO_FASTPATH, **kw)
+        assert len(orows) > 2048
+        assert helpers.canon_close(grows, orows, rel=1e-9)
+    gt.drop()
