@@ -595,7 +595,7 @@ __global__ void k_fill_i64(long long *p, uint64_t n, long long v)
 }
 
 __global__ void k_join_build_count(const int64_t *__restrict__ data, const uint32_t *__restrict__ present, uint64_t n, int is_dbl,
-		long long *__restrict__ keys, uint64_t cap_mask, uint32_t *__restrict__ cnt)
+		long long *__restrict__ keys, uint64_t cap_mask, uint32_t *__restrict__ cnt, unsigned long long *__restrict__ dup)
 {
 	for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
 		if (present && !mdb_bit(present, r))
@@ -604,7 +604,8 @@ __global__ void k_join_build_count(const int64_t *__restrict__ data, const uint3
 		if (is_dbl && key_is_nan(v))
 			continue;
 		uint64_t s = ht_insert(keys, cap_mask, norm_key(v, is_dbl));
-		atomicAdd(&cnt[s], 1u);
+		if (atomicAdd(&cnt[s], 1u))
+			*dup = 1; // some key occurs twice
 	}
 }
 
@@ -642,6 +643,37 @@ __global__ void k_join_probe_count(TuplesDev ts, int ltbl, const int64_t *__rest
 		matches[i] = m;
 		first_row[i] = m ? row_off[s] : 0;
 	}
+}
+
+// build side without duplicate keys: a tuple matches at most one row, so the join appends one row-id column (0xffffffff =
+// no match) and a keep bitmap instead of expanding the tuples; n_match tells the host whether anything has to be dropped
+__global__ void k_join_probe_unique(TuplesDev ts, int ltbl, const int64_t *__restrict__ data, const uint32_t *__restrict__ present,
+		int is_dbl, const long long *__restrict__ keys, uint64_t cap_mask, const uint32_t *__restrict__ cnt,
+		const uint64_t *__restrict__ row_off, const uint32_t *__restrict__ rows, uint32_t *__restrict__ newcol,
+		uint32_t *__restrict__ keep, unsigned long long *__restrict__ n_match)
+{
+	uint32_t mine = 0;
+	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x; // a multiple of 32: the lanes of a warp stay on one bitmap word
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; (i & ~31ull) < ts.n; i += stride) {
+		uint32_t row = 0xffffffffu;
+		if (i < ts.n) {
+			uint32_t r = ts.rid[ltbl][i];
+			uint64_t s = 0;
+			if (!present || mdb_bit(present, r)) {
+				int64_t v = data[r];
+				if (!(is_dbl && key_is_nan(v)) && ht_find(keys, cap_mask, norm_key(v, is_dbl), &s) && cnt[s])
+					row = rows[row_off[s]];
+			}
+			newcol[i] = row;
+		}
+		uint32_t b = __ballot_sync(0xffffffffu, row != 0xffffffffu);
+		if ((threadIdx.x & 31) == 0) {
+			keep[i >> 5] = b;
+			mine += __popc(b);
+		}
+	}
+	if ((threadIdx.x & 31) == 0 && mine)
+		atomicAdd(n_match, (unsigned long long)mine);
 }
 
 __global__ void k_join_probe_emit(TuplesDev ts, const uint32_t *__restrict__ matches, const uint64_t *__restrict__ first_row,
@@ -766,7 +798,11 @@ static int join_step(mdbcu_ctx *ctx, const mdbcu_plan *plan, int j, Tuples *ts)
 	const uint32_t *r_present = col_all_present(rt, jn.right.col) ? nullptr : rc_.present;
 	const uint32_t *l_present = col_all_present(lt, jn.left.col) ? nullptr : lc.present;
 	int gr = grid_for(ctx, rt->n_slots, 256);
-	MDB_LAUNCH(ctx, k_join_build_count, gr, 256, 0, (const int64_t*)rc_.data, r_present, rt->n_slots, r_dbl, keys, cap - 1, cnt);
+	unsigned long long *d_dup;
+	MDB_TRY(tmp.alloc(&d_dup, 1));
+	CUDA_TRY(ctx, cudaMemsetAsync(d_dup, 0, sizeof(*d_dup), ctx->stream));
+	MDB_LAUNCH(ctx, k_join_build_count, gr, 256, 0, (const int64_t*)rc_.data, r_present, rt->n_slots, r_dbl, keys, cap - 1, cnt,
+			d_dup);
 	CUDA_CHECK_LAUNCH(ctx);
 	MDB_TRY(mdb_scan_u32_u64(ctx, cnt, off, cap + 2, nullptr));
 	MDB_LAUNCH(ctx, k_join_build_fill, gr, 256, 0, (const int64_t*)rc_.data, r_present, rt->n_slots, r_dbl,
@@ -774,6 +810,34 @@ static int join_step(mdbcu_ctx *ctx, const mdbcu_plan *plan, int j, Tuples *ts)
 	CUDA_CHECK_LAUNCH(ctx);
 
 	int gp = grid_for(ctx, ts->n, 256);
+	uint64_t dup = 1;
+	MDB_TRY(mdb_read_u64(ctx, (const uint64_t*)d_dup, &dup));
+	if (!dup && ts->ntab < MDBCU_MAX_TABLES) {
+		// foreign-key shape: the tuples keep their arrays and gain one column; they are compacted only if some tuple has no partner
+		uint32_t *newcol = nullptr, *keep;
+		MDB_TRY(tmp.alloc(&keep, (ts->n + 31) / 32));
+		CUDA_TRY(ctx, cudaMemsetAsync(d_total, 0, sizeof(*d_total), ctx->stream));
+		MDB_TRY(mdb_alloc(ctx, &newcol, ts->n));
+		MDB_LAUNCH(ctx, k_join_probe_unique, gp, 256, 0, to_dev(*ts), jn.left.tbl, (const int64_t*)lc.data, l_present, l_dbl,
+				(const long long*)keys, cap - 1, (const uint32_t*)cnt, (const uint64_t*)off, (const uint32_t*)rows, newcol, keep,
+				(unsigned long long*)d_total);
+		uint64_t matched = 0;
+		int rc = cudaGetLastError() == cudaSuccess ? mdb_read_u64(ctx, d_total, &matched)
+				: mdb_fail(ctx, MDBCU_ECUDA, "k_join_probe_unique failed to launch");
+		lap("join: unique probe (sync)", matched);
+		ts->rid[ts->ntab] = newcol; // from here on the column belongs to the tuples
+		ts->ntab++;
+		if (rc != MDBCU_OK || matched == ts->n)
+			return rc;
+		Tuples kept;
+		rc = compact_tuples(ctx, keep, ts->n, ts, ts->ntab, &kept);
+		free_tuples(ctx, *ts);
+		if (rc == MDBCU_OK)
+			*ts = kept;
+		else
+			ts->ntab = j + 2;
+		return rc;
+	}
 	MDB_LAUNCH(ctx, k_join_probe_count, gp, 256, 0, to_dev(*ts), jn.left.tbl, (const int64_t*)lc.data, l_present, l_dbl,
 			(const long long*)keys, cap - 1, (const uint32_t*)cnt, (const uint64_t*)off, matches, first_row);
 	CUDA_CHECK_LAUNCH(ctx);
