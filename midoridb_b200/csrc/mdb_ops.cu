@@ -645,28 +645,61 @@ __global__ void k_join_probe_count(TuplesDev ts, int ltbl, const int64_t *__rest
 	}
 }
 
-// build side without duplicate keys: a tuple matches at most one row, so the join appends one row-id column (0xffffffff =
+// how a probe finds the partner of a key when the build side has no duplicate keys
+struct JoinLookup {
+	// direct != nullptr: narrow INT key range, row = direct[key - dmin] (0xffffffff = no such key)
+	const uint32_t *direct;
+	long long dmin;
+	uint64_t drange;
+	// otherwise the hash table of the general route
+	const long long *keys;
+	uint64_t cap_mask;
+	const uint32_t *cnt;
+	const uint64_t *row_off;
+	const uint32_t *rows;
+};
+
+#define JOIN_NO_ROW 0xffffffffu
+
+__global__ void k_join_build_direct(const int64_t *__restrict__ data, const uint32_t *__restrict__ present, uint64_t n, long long kmin,
+		uint64_t range, uint32_t *__restrict__ direct, unsigned long long *__restrict__ dup)
+{
+	for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r < n; r += (uint64_t)gridDim.x * blockDim.x) {
+		if (present && !mdb_bit(present, r))
+			continue; // NULL (or tombstoned) rows never match, executor_select.c:716-738
+		uint64_t d = (uint64_t)data[r] - (uint64_t)kmin;
+		if (d >= range)
+			continue; // outside the zone map: cannot happen, the bounds are supersets
+		if (atomicCAS(&direct[d], JOIN_NO_ROW, (uint32_t)r) != JOIN_NO_ROW)
+			*dup = 1; // some key occurs twice
+	}
+}
+
+// build side without duplicate keys: a tuple matches at most one row, so the join appends one row-id column (JOIN_NO_ROW =
 // no match) and a keep bitmap instead of expanding the tuples; n_match tells the host whether anything has to be dropped
 __global__ void k_join_probe_unique(TuplesDev ts, int ltbl, const int64_t *__restrict__ data, const uint32_t *__restrict__ present,
-		int is_dbl, const long long *__restrict__ keys, uint64_t cap_mask, const uint32_t *__restrict__ cnt,
-		const uint64_t *__restrict__ row_off, const uint32_t *__restrict__ rows, uint32_t *__restrict__ newcol,
-		uint32_t *__restrict__ keep, unsigned long long *__restrict__ n_match)
+		int is_dbl, JoinLookup lk, uint32_t *__restrict__ newcol, uint32_t *__restrict__ keep, unsigned long long *__restrict__ n_match)
 {
 	uint32_t mine = 0;
 	const uint64_t stride = (uint64_t)gridDim.x * blockDim.x; // a multiple of 32: the lanes of a warp stay on one bitmap word
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; (i & ~31ull) < ts.n; i += stride) {
-		uint32_t row = 0xffffffffu;
+		uint32_t row = JOIN_NO_ROW;
 		if (i < ts.n) {
 			uint32_t r = ts.rid[ltbl][i];
-			uint64_t s = 0;
 			if (!present || mdb_bit(present, r)) {
 				int64_t v = data[r];
-				if (!(is_dbl && key_is_nan(v)) && ht_find(keys, cap_mask, norm_key(v, is_dbl), &s) && cnt[s])
-					row = rows[row_off[s]];
+				uint64_t s = 0;
+				if (lk.direct) {
+					uint64_t d = (uint64_t)v - (uint64_t)lk.dmin;
+					if (d < lk.drange)
+						row = lk.direct[d];
+				} else if (!(is_dbl && key_is_nan(v)) && ht_find(lk.keys, lk.cap_mask, norm_key(v, is_dbl), &s) && lk.cnt[s]) {
+					row = lk.rows[lk.row_off[s]];
+				}
 			}
 			newcol[i] = row;
 		}
-		uint32_t b = __ballot_sync(0xffffffffu, row != 0xffffffffu);
+		uint32_t b = __ballot_sync(0xffffffffu, row != JOIN_NO_ROW);
 		if ((threadIdx.x & 31) == 0) {
 			keep[i >> 5] = b;
 			mine += __popc(b);
@@ -775,56 +808,29 @@ static int join_step(mdbcu_ctx *ctx, const mdbcu_plan *plan, int j, Tuples *ts)
 
 	HostLap lap;
 	DevTemp tmp(ctx, true);
-	uint64_t cap = 1024;
-	while (cap < rt->n_slots * 2)
-		cap <<= 1;
-	long long *keys;
-	uint32_t *cnt, *fill, *rows, *matches;
-	uint64_t *off, *out_off, *d_total, *first_row;
-	MDB_TRY(tmp.alloc(&keys, cap));
-	MDB_TRY(tmp.alloc(&cnt, cap + 2));
-	MDB_TRY(tmp.alloc(&fill, cap + 2));
-	MDB_TRY(tmp.alloc(&off, cap + 2));
-	MDB_TRY(tmp.alloc(&rows, rt->n_slots));
-	MDB_TRY(tmp.alloc(&matches, ts->n));
-	MDB_TRY(tmp.alloc(&first_row, ts->n));
-	MDB_TRY(tmp.alloc(&out_off, ts->n));
-	MDB_TRY(tmp.alloc(&d_total, 1));
-	lap("join: allocate", cap);
-	MDB_LAUNCH(ctx, k_fill_i64, grid_for(ctx, cap, 256), 256, 0, keys, cap, HT_EMPTY);
-	CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, (cap + 2) * sizeof(uint32_t), ctx->stream));
-	CUDA_TRY(ctx, cudaMemsetAsync(fill, 0, (cap + 2) * sizeof(uint32_t), ctx->stream));
-
 	const uint32_t *r_present = col_all_present(rt, jn.right.col) ? nullptr : rc_.present;
 	const uint32_t *l_present = col_all_present(lt, jn.left.col) ? nullptr : lc.present;
-	int gr = grid_for(ctx, rt->n_slots, 256);
+	const int gr = grid_for(ctx, rt->n_slots, 256), gp = grid_for(ctx, ts->n, 256);
+	uint64_t *d_total;
 	unsigned long long *d_dup;
+	MDB_TRY(tmp.alloc(&d_total, 1));
 	MDB_TRY(tmp.alloc(&d_dup, 1));
-	CUDA_TRY(ctx, cudaMemsetAsync(d_dup, 0, sizeof(*d_dup), ctx->stream));
-	MDB_LAUNCH(ctx, k_join_build_count, gr, 256, 0, (const int64_t*)rc_.data, r_present, rt->n_slots, r_dbl, keys, cap - 1, cnt,
-			d_dup);
-	CUDA_CHECK_LAUNCH(ctx);
-	MDB_TRY(mdb_scan_u32_u64(ctx, cnt, off, cap + 2, nullptr));
-	MDB_LAUNCH(ctx, k_join_build_fill, gr, 256, 0, (const int64_t*)rc_.data, r_present, rt->n_slots, r_dbl,
-			(const long long*)keys, cap - 1, (const uint64_t*)off, fill, rows);
-	CUDA_CHECK_LAUNCH(ctx);
 
-	int gp = grid_for(ctx, ts->n, 256);
-	uint64_t dup = 1;
-	MDB_TRY(mdb_read_u64(ctx, (const uint64_t*)d_dup, &dup));
-	if (!dup && ts->ntab < MDBCU_MAX_TABLES) {
-		// foreign-key shape: the tuples keep their arrays and gain one column; they are compacted only if some tuple has no partner
+	// Build sides without duplicate keys (the foreign-key shape): the tuples keep their arrays and gain one column; they
+	// are compacted only if some tuple has no partner.
+	JoinLookup lk;
+	memset(&lk, 0, sizeof(lk));
+	auto probe_unique = [&]() -> int {
 		uint32_t *newcol = nullptr, *keep;
 		MDB_TRY(tmp.alloc(&keep, (ts->n + 31) / 32));
 		CUDA_TRY(ctx, cudaMemsetAsync(d_total, 0, sizeof(*d_total), ctx->stream));
 		MDB_TRY(mdb_alloc(ctx, &newcol, ts->n));
-		MDB_LAUNCH(ctx, k_join_probe_unique, gp, 256, 0, to_dev(*ts), jn.left.tbl, (const int64_t*)lc.data, l_present, l_dbl,
-				(const long long*)keys, cap - 1, (const uint32_t*)cnt, (const uint64_t*)off, (const uint32_t*)rows, newcol, keep,
-				(unsigned long long*)d_total);
+		MDB_LAUNCH(ctx, k_join_probe_unique, gp, 256, 0, to_dev(*ts), jn.left.tbl, (const int64_t*)lc.data, l_present, l_dbl, lk,
+				newcol, keep, (unsigned long long*)d_total);
 		uint64_t matched = 0;
 		int rc = cudaGetLastError() == cudaSuccess ? mdb_read_u64(ctx, d_total, &matched)
 				: mdb_fail(ctx, MDBCU_ECUDA, "k_join_probe_unique failed to launch");
-		lap("join: unique probe (sync)", matched);
+		lap(lk.direct ? "join: direct probe (sync)" : "join: unique probe (sync)", matched);
 		ts->rid[ts->ntab] = newcol; // from here on the column belongs to the tuples
 		ts->ntab++;
 		if (rc != MDBCU_OK || matched == ts->n)
@@ -837,18 +843,84 @@ static int join_step(mdbcu_ctx *ctx, const mdbcu_plan *plan, int j, Tuples *ts)
 		else
 			ts->ntab = j + 2;
 		return rc;
+	};
+
+	// 1. INT keys whose zone map is narrow: a direct row table instead of a hash table (one 4-byte lookup per tuple)
+	uint64_t dup = 0;
+	bool dup_known = false;
+	if (!r_dbl && rc_.stats_ok && rc_.imin <= rc_.imax) {
+		const unsigned long long range = (unsigned long long)rc_.imax - (unsigned long long)rc_.imin + 1ull;
+		if (range != 0 && range <= std::max<unsigned long long>(1ull << 16, 4ull * rt->n_slots)) {
+			uint32_t *direct;
+			MDB_TRY(tmp.alloc(&direct, range));
+			CUDA_TRY(ctx, cudaMemsetAsync(direct, 0xff, range * sizeof(uint32_t), ctx->stream));
+			CUDA_TRY(ctx, cudaMemsetAsync(d_dup, 0, sizeof(*d_dup), ctx->stream));
+			MDB_LAUNCH(ctx, k_join_build_direct, gr, 256, 0, (const int64_t*)rc_.data, r_present, rt->n_slots, (long long)rc_.imin,
+					(uint64_t)range, direct, d_dup);
+			CUDA_CHECK_LAUNCH(ctx);
+			MDB_TRY(mdb_read_u64(ctx, (const uint64_t*)d_dup, &dup));
+			dup_known = true;
+			lap("join: direct build (sync)", range);
+			if (!dup) {
+				lk.direct = direct;
+				lk.dmin = rc_.imin;
+				lk.drange = range;
+				return probe_unique();
+			}
+		}
 	}
+
+	// 2. hash table of the build side as a CSR multimap (count -> scan -> fill)
+	uint64_t cap = 1024;
+	while (cap < rt->n_slots * 2)
+		cap <<= 1;
+	long long *keys;
+	uint32_t *cnt, *fill, *rows;
+	uint64_t *off;
+	MDB_TRY(tmp.alloc(&keys, cap));
+	MDB_TRY(tmp.alloc(&cnt, cap + 2));
+	MDB_TRY(tmp.alloc(&fill, cap + 2));
+	MDB_TRY(tmp.alloc(&off, cap + 2));
+	MDB_TRY(tmp.alloc(&rows, rt->n_slots));
+	MDB_LAUNCH(ctx, k_fill_i64, grid_for(ctx, cap, 256), 256, 0, keys, cap, HT_EMPTY);
+	CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, (cap + 2) * sizeof(uint32_t), ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(fill, 0, (cap + 2) * sizeof(uint32_t), ctx->stream));
+	CUDA_TRY(ctx, cudaMemsetAsync(d_dup, 0, sizeof(*d_dup), ctx->stream));
+	MDB_LAUNCH(ctx, k_join_build_count, gr, 256, 0, (const int64_t*)rc_.data, r_present, rt->n_slots, r_dbl, keys, cap - 1, cnt,
+			d_dup);
+	CUDA_CHECK_LAUNCH(ctx);
+	MDB_TRY(mdb_scan_u32_u64(ctx, cnt, off, cap + 2, nullptr));
+	MDB_LAUNCH(ctx, k_join_build_fill, gr, 256, 0, (const int64_t*)rc_.data, r_present, rt->n_slots, r_dbl,
+			(const long long*)keys, cap - 1, (const uint64_t*)off, fill, rows);
+	CUDA_CHECK_LAUNCH(ctx);
+	if (!dup_known) {
+		MDB_TRY(mdb_read_u64(ctx, (const uint64_t*)d_dup, &dup));
+		lap("join: hash build (sync)", cap);
+	}
+	if (!dup) {
+		lk.keys = keys;
+		lk.cap_mask = cap - 1;
+		lk.cnt = cnt;
+		lk.row_off = off;
+		lk.rows = rows;
+		return probe_unique();
+	}
+
+	// 3. duplicates on the build side: count the matches of every tuple, scan, emit into new arrays
+	uint32_t *matches;
+	uint64_t *out_off, *first_row;
+	MDB_TRY(tmp.alloc(&matches, ts->n));
+	MDB_TRY(tmp.alloc(&first_row, ts->n));
+	MDB_TRY(tmp.alloc(&out_off, ts->n));
 	MDB_LAUNCH(ctx, k_join_probe_count, gp, 256, 0, to_dev(*ts), jn.left.tbl, (const int64_t*)lc.data, l_present, l_dbl,
 			(const long long*)keys, cap - 1, (const uint32_t*)cnt, (const uint64_t*)off, matches, first_row);
 	CUDA_CHECK_LAUNCH(ctx);
 	MDB_TRY(mdb_scan_u32_u64(ctx, matches, out_off, ts->n, d_total));
 	uint64_t total = 0;
-	lap("join: launches", ts->n);
 	MDB_TRY(mdb_read_u64(ctx, d_total, &total));
-	lap("join: build+count (sync)", total);
+	lap("join: count matches (sync)", total);
 
 	MDB_TRY(alloc_out_tuples(ctx, &out, ts->ntab + 1, total, &arr));
-	lap("join: allocate output", total);
 	if (total) {
 		MDB_LAUNCH(ctx, k_join_probe_emit, gp, 256, 0, to_dev(*ts), (const uint32_t*)matches, (const uint64_t*)first_row,
 				(const uint64_t*)out_off, (const uint32_t*)rows, arr);

@@ -428,10 +428,11 @@ def test_group_by_slot_modes(be, mode):
     gt.drop()
 
 
-@pytest.mark.parametrize("shape", ["all_match", "some_miss", "none_match", "null_keys"])
+@pytest.mark.parametrize("shape", ["all_match", "some_miss", "none_match", "null_keys", "wide_keys", "wide_dups", "double_keys"])
 def test_join_with_unique_build_side(be, shape):
     """foreign-key joins (build side without duplicate keys) append a row-id column instead of expanding the tuples;
-    the tuples are compacted only when some tuple has no partner. Row order must stay the reference's."""
+    the tuples are compacted only when some tuple has no partner. Row order must stay the reference's.
+    Narrow INT keys take the direct row table, wide INT keys and DOUBLE keys the hash table, duplicates the CSR route."""
     rng = np.random.default_rng(91)
     n, nd = 6000, 300
     fk = rng.integers(0, nd, n)
@@ -442,20 +443,28 @@ def test_join_with_unique_build_side(be, shape):
         dk = dk[: nd // 2]
     elif shape == "none_match":
         dk = dk + 10 * nd
+    kt = I
+    if shape in ("wide_keys", "wide_dups"):
+        fk, dk = fk * 10**10 - 7, dk * 10**10 - 7
+        if shape == "wide_dups":
+            dk = np.concatenate([dk, dk[:40]])
+    elif shape == "double_keys":
+        kt = D
+        fk, dk = fk / 4.0, dk / 4.0
     dv = rng.integers(0, 9, len(dk))
     dkn = (rng.random(len(dk)) < 0.1).astype(np.uint8) if shape == "null_keys" else None
     ek = rng.permutation(nd).astype(np.int64)  # second dimension: always complete
     ev = (rng.random(nd) * 10).round(1)
-    gf, of = both_tables(be, [I, I], [fk, val], [fkn, None])
-    gd, od = both_tables(be, [I, I], [dk, dv], [dkn, None], paged=True)
+    gf, of = both_tables(be, [kt, I, I], [fk, val, rng.integers(0, nd, n)], [fkn, None, None])
+    gd, od = both_tables(be, [kt, I], [dk, dv], [dkn, None], paged=True)
     ge, oe = both_tables(be, [I, D], [ek, ev])
     # projection of a 3-way join, in the reference's row order
-    grows, orows, _, _ = run_both(be, [gf, gd, ge], [of, od, oe], flags=PLAN_NO_FASTPATH, joins=[((0, 0), (1, 0)), ((0, 0), (2, 0))],
+    grows, orows, _, _ = run_both(be, [gf, gd, ge], [of, od, oe], flags=PLAN_NO_FASTPATH, joins=[((0, 0), (1, 0)), ((0, 2), (2, 0))],
                                   out=[(OUT_COLUMN, 0, 1), (OUT_COLUMN, 1, 1), (OUT_COLUMN, 2, 1)])
     assert (len(orows) == 0) == (shape == "none_match")
     assert [helpers.norm_row(r) for r in grows] == [helpers.norm_row(r) for r in orows]
     # and under WHERE + GROUP BY
-    grows, orows, _, _ = run_both(be, [gf, gd, ge], [of, od, oe], flags=PLAN_NO_FASTPATH, joins=[((0, 0), (1, 0)), ((1, 0), (2, 0))],
+    grows, orows, _, _ = run_both(be, [gf, gd, ge], [of, od, oe], flags=PLAN_NO_FASTPATH, joins=[((0, 0), (1, 0)), ((0, 2), (2, 0))],
                                   pred=[("col", 0, 1), ("int", 50), ("cmp", 1)], group=[(1, 1)],
                                   out=[(OUT_COLUMN, 1, 1), (OUT_COUNT_STAR,), (OUT_SUM, 0, 1), (OUT_AVG, 2, 1)])
     assert helpers.canon_close(grows, orows, rel=1e-9)
