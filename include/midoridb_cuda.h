@@ -231,6 +231,8 @@ struct mdbcu_stats {
 #define MDBCU_PATH_SCAN_AGG       1 /* fused filter + aggregate scan (no join, no GROUP BY) */
 #define MDBCU_PATH_RADIX_JOINCOUNT 2 /* radix-partitioned join + GROUP BY join key, COUNT(*) */
 #define MDBCU_PATH_DIRECT_STAR    3 /* small build side, direct-addressed probe + grouped MIN/MAX/SUM/COUNT */
+#define MDBCU_PATH_FUSED_MULTIWAY 4 /* scan of tables[0] with direct row tables for every joined table, WHERE and grouped
+                                      aggregates in one kernel (no tuple arrays); opt-in: MDBCU_FUSED_MULTIWAY=1 */
 int mdbcu_get_stats(mdbcu_ctx *ctx, struct mdbcu_stats *out);
 
 /* CUDA events on the context's own stream (the stream every kernel of this library is launched on), so a

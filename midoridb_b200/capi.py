@@ -23,7 +23,7 @@ CMP_LT, CMP_GT, CMP_NE, CMP_EQ, CMP_LE, CMP_GE = 1, 2, 3, 4, 5, 6
 OUT_COLUMN, OUT_COUNT_STAR, OUT_COUNT_COL, OUT_SUM, OUT_MIN, OUT_MAX, OUT_AVG = range(7)
 PLAN_DISTRIBUTED, PLAN_NO_FASTPATH = 1, 2
 GEN_UNIFORM_INT, GEN_UNIFORM_DBL, GEN_PERMUTATION, GEN_ZIPF, GEN_SEQUENCE = range(5)
-PATH_GENERAL, PATH_SCAN_AGG, PATH_RADIX_JOINCOUNT, PATH_DIRECT_STAR = range(4)
+PATH_GENERAL, PATH_SCAN_AGG, PATH_RADIX_JOINCOUNT, PATH_DIRECT_STAR, PATH_FUSED_MULTIWAY = range(5)
 
 EXPORTED_SYMBOLS = [
     "mdbcu_init", "mdbcu_shutdown", "mdbcu_last_error", "mdbcu_device_sync", "mdbcu_host_alloc", "mdbcu_host_free",

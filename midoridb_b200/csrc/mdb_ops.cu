@@ -344,7 +344,20 @@ __device__ static inline bool pv_cmp(int cmp, PVal a, PVal b)
 
 #define PRED_STACK 24
 
-__device__ static bool eval_program(const DPredProgram *__restrict__ prog, const TuplesDev &ts, uint64_t i)
+// Row ids of one joined tuple, by table. The general operators read them from the materialised tuple arrays ...
+struct TupleRows {
+	const TuplesDev *ts;
+	uint64_t i;
+	__device__ uint32_t operator()(int t) const { return ts->rid[t][i]; }
+};
+// ... the fused multiway aggregate holds them in registers.
+struct StarRows {
+	uint32_t r[MDBCU_MAX_TABLES];
+	__device__ uint32_t operator()(int t) const { return r[t]; }
+};
+
+template <typename Rows>
+__device__ static bool eval_program(const DPredProgram *__restrict__ prog, const Rows &rows)
 {
 	PVal st[PRED_STACK];
 	int sp = 0;
@@ -355,7 +368,7 @@ __device__ static bool eval_program(const DPredProgram *__restrict__ prog, const
 		v.i = 0;
 		switch (op.op) {
 		case MDBCU_P_COL: {
-			uint32_t r = ts.rid[op.tbl][i];
+			uint32_t r = rows(op.tbl);
 			if (op.present && !mdb_bit(op.present, r)) {
 				v.kind = 2;
 			} else {
@@ -420,7 +433,8 @@ __global__ void k_eval_pred(const DPredProgram *__restrict__ prog, TuplesDev ts,
 	int lane = threadIdx.x & 31;
 	for (uint64_t g = warp; g < groups; g += nwarps) {
 		uint64_t i = g * 32 + lane;
-		bool keep = i < ts.n && eval_program(prog, ts, i);
+		TupleRows rows = {&ts, i};
+		bool keep = i < ts.n && eval_program(prog, rows);
 		uint32_t b = __ballot_sync(0xffffffffu, keep);
 		if (lane == 0)
 			bits[g] = b;
@@ -965,12 +979,19 @@ struct DGroupSpec {
 	DOut out[MDBCU_MAX_OUT];
 };
 
-__device__ static inline unsigned long long pack_rids(const DGroupSpec *sp, const TuplesDev &ts, uint64_t i)
+template <typename Rows>
+__device__ static inline unsigned long long pack_rids(const DGroupSpec *sp, const Rows &rows)
 {
 	unsigned long long k = 0;
 	for (int t = 0; t < sp->ntab; t++)
-		k |= (unsigned long long)ts.rid[t][i] << sp->pack_shift[t];
+		k |= (unsigned long long)rows(t) << sp->pack_shift[t];
 	return k;
+}
+
+__device__ static inline unsigned long long pack_rids(const DGroupSpec *sp, const TuplesDev &ts, uint64_t i)
+{
+	TupleRows rows = {&ts, i};
+	return pack_rids(sp, rows);
 }
 
 // slot layout: [0, cap) hashed keys, cap = key INT64_MIN, cap+1 = NULL group (NULLs collate equal, :1476-1482)
@@ -1003,9 +1024,70 @@ __device__ static inline void group_acc_merge(const DOut &out, long long *acc, l
 	}
 }
 
-__global__ void k_group_update(const DGroupSpec *__restrict__ sp, TuplesDev ts, long long *__restrict__ keys, uint64_t cap_mask,
-		unsigned long long *__restrict__ first_key, uint32_t *__restrict__ used, uint32_t cache_entries,
-		const uint32_t *__restrict__ keep)
+// Where the aggregate gets its joined tuples from.
+// (1) The general operators: materialised tuple arrays, optionally with the WHERE verdicts as a bitmap.
+struct TupleSource {
+	typedef TupleRows Rows;
+	TuplesDev ts;
+	const uint32_t *keep; // bit i = tuple i qualifies (nullptr: all do; the filter was not materialised)
+	__device__ uint64_t count() const { return ts.n; }
+	__device__ bool fetch(uint64_t i, Rows &rows) const
+	{
+		if (keep && !mdb_bit(keep, i))
+			return false;
+		rows.ts = &ts;
+		rows.i = i;
+		return true;
+	}
+};
+
+// (2) The fused multiway aggregate: the rows of tables[0] are scanned once; the partner in every further table is looked up
+// in a direct row table (build keys duplicate-free with a narrow zone map, see k_join_build_direct), WHERE is evaluated on
+// the row ids in registers. No tuple array is ever written.
+struct StarDim {
+	int32_t ltbl; // the join's left operand is a column of this (earlier) table
+	int32_t _pad;
+	const int64_t *ldata;
+	const uint32_t *lpresent;
+	const uint32_t *direct;
+	long long dmin;
+	uint64_t drange;
+};
+
+struct StarSource {
+	typedef StarRows Rows;
+	uint64_t n_fact;
+	const uint32_t *live0; // nullptr: every slot of tables[0] is a live row
+	int32_t n_dims;
+	int32_t _pad;
+	StarDim dim[MDBCU_MAX_TABLES - 1];
+	const DPredProgram *prog; // nullptr: no WHERE
+	__device__ uint64_t count() const { return n_fact; }
+	__device__ bool fetch(uint64_t i, Rows &rows) const
+	{
+		if (live0 && !mdb_bit(live0, i))
+			return false;
+		rows.r[0] = (uint32_t)i;
+		for (int d = 0; d < n_dims; d++) {
+			const StarDim &m = dim[d];
+			uint32_t r = rows.r[m.ltbl];
+			if (m.lpresent && !mdb_bit(m.lpresent, r))
+				return false; // NULL keys never match
+			uint64_t k = (uint64_t)m.ldata[r] - (uint64_t)m.dmin;
+			if (k >= m.drange)
+				return false;
+			uint32_t partner = m.direct[k];
+			if (partner == JOIN_NO_ROW)
+				return false;
+			rows.r[d + 1] = partner;
+		}
+		return !prog || eval_program(prog, rows);
+	}
+};
+
+template <typename Source>
+__global__ void k_group_update(const DGroupSpec *__restrict__ sp, Source src, long long *__restrict__ keys, uint64_t cap_mask,
+		unsigned long long *__restrict__ first_key, uint32_t *__restrict__ used, uint32_t cache_entries)
 {
 	extern __shared__ unsigned long long s_cache[];
 	const uint32_t E = cache_entries;
@@ -1028,17 +1110,19 @@ __global__ void k_group_update(const DGroupSpec *__restrict__ sp, TuplesDev ts, 
 		__syncthreads();
 	}
 
-	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < ts.n; i += (uint64_t)gridDim.x * blockDim.x) {
+	const uint64_t n_in = src.count();
+	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_in; i += (uint64_t)gridDim.x * blockDim.x) {
 		uint64_t slot;
-		if (keep && !mdb_bit(keep, i))
-			continue; // WHERE verdicts of the tuples (the filter was not materialised)
+		typename Source::Rows rows;
+		if (!src.fetch(i, rows))
+			continue;
 		if (sp->n_group == 0) {
 			slot = 0;
 		} else {
 			bool any_null = false;
 			long long key = 0;
 			for (int g = 0; g < sp->n_group; g++) {
-				uint32_t r = ts.rid[sp->g[g].tbl][i];
+				uint32_t r = rows(sp->g[g].tbl);
 				bool isnull = sp->g[g].present && !mdb_bit(sp->g[g].present, r);
 				long long v = isnull ? 0 : norm_key(sp->g[g].data[r], sp->g[g].is_dbl);
 				if (sp->g[g].mode == 0) {
@@ -1077,7 +1161,7 @@ __global__ void k_group_update(const DGroupSpec *__restrict__ sp, TuplesDev ts, 
 		if (!hit)
 			used[slot] = 1;
 		if (sp->pack_ok)
-			atomicMin(hit ? &s_cache[E + e] : &first_key[slot], pack_rids(sp, ts, i));
+			atomicMin(hit ? &s_cache[E + e] : &first_key[slot], pack_rids(sp, rows));
 		int a = 0;
 		for (int o = 0; o < sp->n_out; o++) {
 			const DOut &out = sp->out[o];
@@ -1090,7 +1174,7 @@ __global__ void k_group_update(const DGroupSpec *__restrict__ sp, TuplesDev ts, 
 				atomicAdd(nn, 1ull);
 				continue;
 			}
-			uint32_t r = ts.rid[out.tbl][i];
+			uint32_t r = rows(out.tbl);
 			if (out.present && !mdb_bit(out.present, r))
 				continue;
 			long long v = out.data[r];
@@ -1350,10 +1434,13 @@ static bool plan_has_aggregate(const mdbcu_plan *plan)
 }
 
 // keep: optional WHERE verdict bitmap over the tuples (bit i = tuple i qualifies)
-static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples &ts, const uint32_t *keep, mdbcu_result *res)
+// star: the joined tuples are not materialised at all but produced on the fly (StarSource); ts is ignored then
+static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples &ts, const uint32_t *keep, const StarSource *star,
+		mdbcu_result *res)
 {
+	const uint64_t n_in = star ? star->n_fact : ts.n;
 	DGroupSpec sp;
-	MDB_TRY(build_group_spec(ctx, plan, ts.ntab, &sp));
+	MDB_TRY(build_group_spec(ctx, plan, star ? star->n_dims + 1 : ts.ntab, &sp));
 
 	bool need_first = false;
 	for (int o = 0; o < plan->n_out; o++)
@@ -1362,7 +1449,7 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 	if (need_first && !sp.pack_ok)
 		return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "plain columns under GROUP BY need row ids that pack into 64 bits");
 
-	if (ts.n == 0)
+	if (n_in == 0)
 		return mdb_result_alloc(ctx, plan, res, 0, false); // no qualifying row: no result row (executor keeps zero rows)
 
 	// a single INT key whose zone map is narrow is its own slot number (tables small enough to stay in L2, nothing to probe)
@@ -1370,7 +1457,7 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 		const DevColumn &gc = plan->tables[plan->group[0].tbl]->cols[plan->group[0].col];
 		if (gc.stats_ok && gc.imin <= gc.imax && gc.imin > INT64_MIN) {
 			unsigned long long range = (unsigned long long)gc.imax - (unsigned long long)gc.imin + 1ull;
-			if (range != 0 && range <= std::max<unsigned long long>(1ull << 16, 4ull * ts.n)) {
+			if (range != 0 && range <= std::max<unsigned long long>(1ull << 16, 4ull * n_in)) {
 				sp.dense = 1;
 				sp.dense_min = gc.imin;
 			}
@@ -1383,7 +1470,7 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 		while (cap < (unsigned long long)gc.imax - (unsigned long long)gc.imin + 1ull)
 			cap <<= 1;
 	} else if (plan->n_group > 0) {
-		while (cap < ts.n * 2)
+		while (cap < n_in * 2)
 			cap <<= 1;
 	}
 	uint64_t nslots = cap + 3;
@@ -1433,14 +1520,20 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 		cache_entries >>= 1;
 	if (cache_entries < 256 || getenv("MDBCU_NO_GROUP_CACHE")) // the switch is for A/B measurements
 		cache_entries = 0;
-	MDB_LAUNCH(ctx, k_group_update, grid_for(ctx, ts.n, 256), 256, cache_entries * entry_bytes, (const DGroupSpec*)d_sp,
-			to_dev(ts), keys, cap - 1, first_key, used, cache_entries, keep);
+	if (star) {
+		MDB_LAUNCH(ctx, k_group_update<StarSource>, grid_for(ctx, n_in, 256), 256, cache_entries * entry_bytes,
+				(const DGroupSpec*)d_sp, *star, keys, cap - 1, first_key, used, cache_entries);
+	} else {
+		TupleSource src = {to_dev(ts), keep};
+		MDB_LAUNCH(ctx, k_group_update<TupleSource>, grid_for(ctx, n_in, 256), 256, cache_entries * entry_bytes,
+				(const DGroupSpec*)d_sp, src, keys, cap - 1, first_key, used, cache_entries);
+	}
 	CUDA_CHECK_LAUNCH(ctx);
 	MDB_LAUNCH(ctx, k_flags_to_bits, grid_for(ctx, nslots, 256), 256, 0, (const uint32_t*)used, nslots, bits);
 	CUDA_CHECK_LAUNCH(ctx);
 
 	Tuples slots;
-	lap("aggregate: launches", ts.n);
+	lap("aggregate: launches", n_in);
 	MDB_TRY(compact_tuples(ctx, bits, nslots, nullptr, 1, &slots));
 	lap("aggregate: compact (sync)", slots.n);
 	int rc = mdb_result_alloc(ctx, plan, res, slots.n, sp.pack_ok != 0);
@@ -1486,6 +1579,76 @@ static int project_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples &
 	return MDBCU_OK;
 }
 
+// =========================================================================================== fused multiway aggregate
+
+// Joins whose build sides are duplicate-free INT keys with a narrow zone map need no tuple arrays: one direct row table per
+// joined table, then ONE kernel scans tables[0], looks the partners up, evaluates WHERE and aggregates (StarSource).
+// *ok = false (and MDBCU_OK): the plan does not have that shape; the general operators take it.
+static int star_source(mdbcu_ctx *ctx, const mdbcu_plan *plan, DevTemp &tmp, StarSource *src, bool *ok)
+{
+	*ok = false;
+	memset(src, 0, sizeof(*src));
+	const mdbcu_table *fact = plan->tables[0];
+	if (plan->n_joins < 1 || plan->n_tables != plan->n_joins + 1 || fact->n_slots == 0)
+		return MDBCU_OK;
+	for (int j = 0; j < plan->n_joins; j++) {
+		const mdbcu_join &jn = plan->joins[j];
+		if (jn.cross || jn.right.tbl != j + 1 || jn.left.tbl > j || jn.left.tbl < 0)
+			return MDBCU_OK;
+		MDB_TRY(check_colref(ctx, plan, jn.left.tbl, jn.left.col, "JOIN"));
+		MDB_TRY(check_colref(ctx, plan, jn.right.tbl, jn.right.col, "JOIN"));
+		const mdbcu_table *rt = plan->tables[j + 1];
+		const DevColumn &lc = plan->tables[jn.left.tbl]->cols[jn.left.col], &rc = rt->cols[jn.right.col];
+		if (lc.type == MDBCU_CT_DOUBLE || rc.type == MDBCU_CT_DOUBLE || !rc.stats_ok || rc.imin > rc.imax || rt->n_slots == 0)
+			return MDBCU_OK;
+		const unsigned long long range = (unsigned long long)rc.imax - (unsigned long long)rc.imin + 1ull;
+		if (range == 0 || range > std::max<unsigned long long>(1ull << 16, 4ull * rt->n_slots))
+			return MDBCU_OK;
+	}
+
+	unsigned long long *d_dup;
+	MDB_TRY(tmp.alloc(&d_dup, 1));
+	CUDA_TRY(ctx, cudaMemsetAsync(d_dup, 0, sizeof(*d_dup), ctx->stream));
+	src->n_fact = fact->n_slots;
+	src->live0 = fact->all_live ? nullptr : fact->live;
+	src->n_dims = plan->n_joins;
+	for (int j = 0; j < plan->n_joins; j++) {
+		const mdbcu_join &jn = plan->joins[j];
+		const mdbcu_table *lt = plan->tables[jn.left.tbl], *rt = plan->tables[j + 1];
+		const DevColumn &lc = lt->cols[jn.left.col], &rc = rt->cols[jn.right.col];
+		const uint64_t range = (uint64_t)rc.imax - (uint64_t)rc.imin + 1ull;
+		uint32_t *direct;
+		MDB_TRY(tmp.alloc(&direct, range));
+		CUDA_TRY(ctx, cudaMemsetAsync(direct, 0xff, range * sizeof(uint32_t), ctx->stream));
+		MDB_LAUNCH(ctx, k_join_build_direct, grid_for(ctx, rt->n_slots, 256), 256, 0, (const int64_t*)rc.data,
+				col_all_present(rt, jn.right.col) ? (const uint32_t*)nullptr : (const uint32_t*)rc.present, rt->n_slots,
+				(long long)rc.imin, range, direct, d_dup);
+		CUDA_CHECK_LAUNCH(ctx);
+		StarDim &m = src->dim[j];
+		m.ltbl = jn.left.tbl;
+		m.ldata = lc.data;
+		m.lpresent = col_all_present(lt, jn.left.col) ? nullptr : lc.present;
+		m.direct = direct;
+		m.dmin = rc.imin;
+		m.drange = range;
+	}
+	uint64_t dup = 1;
+	MDB_TRY(mdb_read_u64(ctx, (const uint64_t*)d_dup, &dup));
+	if (dup)
+		return MDBCU_OK; // some build key occurs twice: tuples multiply, the general join handles that
+
+	if (plan->n_pred > 0) {
+		DPredProgram h, *d_prog;
+		MDB_TRY(build_pred(ctx, plan, &h));
+		MDB_TRY(tmp.alloc(&d_prog, 1));
+		CUDA_TRY(ctx, cudaMemcpyAsync(d_prog, &h, sizeof(h), cudaMemcpyHostToDevice, ctx->stream));
+		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream)); // h lives on this stack frame
+		src->prog = d_prog;
+	}
+	*ok = true;
+	return MDBCU_OK;
+}
+
 // =========================================================================================== driver
 
 int mdb_select_general(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res)
@@ -1496,6 +1659,27 @@ int mdb_select_general(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res
 
 	HostLap lap; // MDBCU_TRACE=2: host wall time of each operator (includes the stream synchronisations inside it)
 
+	const bool aggregates = plan->n_group > 0 || plan_has_aggregate(plan);
+	if (aggregates && plan->n_joins > 0 && getenv("MDBCU_FUSED_MULTIWAY")) {
+		// opt-in until the whole GPU suite has run with it
+		DevTemp star_tmp(ctx, true);
+		StarSource star;
+		bool ok = false;
+		clock.begin(2);
+		rc = star_source(ctx, plan, star_tmp, &star, &ok);
+		lap("fused: direct tables (sync)", plan->n_joins);
+		if (rc != MDBCU_OK || ok) {
+			if (rc == MDBCU_OK) {
+				ctx->stats.path = MDBCU_PATH_FUSED_MULTIWAY;
+				clock.begin(4);
+				rc = aggregate_tuples(ctx, plan, ts, nullptr, &star, res);
+				lap("fused: aggregate", star.n_fact);
+			}
+			clock.finish();
+			return rc;
+		}
+	}
+
 	ctx->stats.path = MDBCU_PATH_GENERAL;
 	clock.begin(0);
 	rc = scan_live(ctx, plan->tables[0], &ts);
@@ -1505,7 +1689,6 @@ int mdb_select_general(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res
 		rc = join_step(ctx, plan, j, &ts);
 		lap("general: join", ts.n);
 	}
-	const bool aggregates = plan->n_group > 0 || plan_has_aggregate(plan);
 	DevTemp verdicts(ctx, true);
 	uint32_t *keep = nullptr;
 	if (rc == MDBCU_OK) {
@@ -1517,7 +1700,7 @@ int mdb_select_general(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res
 	if (rc == MDBCU_OK) {
 		if (aggregates) {
 			clock.begin(4);
-			rc = aggregate_tuples(ctx, plan, ts, keep, res);
+			rc = aggregate_tuples(ctx, plan, ts, keep, nullptr, res);
 			lap("general: aggregate", ts.n);
 		} else {
 			clock.begin(5);
