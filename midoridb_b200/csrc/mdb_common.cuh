@@ -160,6 +160,15 @@ static inline int mdb_alloc(mdbcu_ctx *ctx, T **out, size_t count)
 	size_t bytes = (count ? count : 1) * sizeof(T);
 	auto t0 = std::chrono::steady_clock::now();
 	cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+	if (e == cudaErrorMemoryAllocation && ctx->scratch && ctx->scratch_top == 0) {
+		// out of memory while the scratch arena of the general operators sits idle: give it back and try once more
+		cudaGetLastError();
+		cudaStreamSynchronize(ctx->stream);
+		cudaFree(ctx->scratch);
+		ctx->scratch = nullptr;
+		ctx->scratch_cap = ctx->scratch_peak = 0;
+		e = cudaMallocAsync(&p, bytes, ctx->stream);
+	}
 	if (mdb_trace_level() >= 2) {
 		double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 		if (ms > 0.2)
