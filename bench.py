@@ -129,6 +129,15 @@ class Dist:
         self.td.all_reduce(t, op=self.td.ReduceOp.SUM)
         return float(t[0])
 
+    def sum_cuda(self, t):
+        """all-reduce of a CUDA tensor (verification only; NCCL group created on first use)"""
+        if not self.td:
+            return t
+        if not hasattr(self, "nccl"):
+            self.nccl = self.td.new_group(backend="nccl")
+        self.td.all_reduce(t, op=self.td.ReduceOp.SUM, group=self.nccl)
+        return t
+
     def bcast_bytes(self, b, n):
         if not self.td:
             return b
@@ -141,6 +150,44 @@ class Dist:
     def close(self):
         if self.td:
             self.td.destroy_process_group()
+
+
+def verify_join_count(be, ta, tb, res, key_domain, dist, local_gpu):
+    """Full content check of one README-query result at benchmark size, independent of the library's kernels:
+    torch.bincount over the key columns (zero-copy views of the mirror), summed over the ranks, gives cntA and cntB;
+    every (key, count) row of this rank's result must equal cntA[key] * cntB[key] > 0, keys must be distinct, and the
+    number of result rows over all ranks must equal the number of keys present on both sides.
+    Matches the cardinality-asserting style of the reference's own test_select_11 (tests/engine/executor_select.c:348-374)."""
+    import torch
+    from midoridb_b200 import capi
+    dev = torch.device("cuda", local_gpu)
+
+    def hist(t):
+        ptr, n = t.device_ptr(0)
+        if n == 0:
+            return torch.zeros(key_domain, dtype=torch.int64, device=dev)
+        keys = torch.as_tensor(capi.DeviceArray(ptr, n), device=dev)
+        if int(keys.min()) < 0 or int(keys.max()) >= key_domain:
+            raise AssertionError("generated keys outside [0, %d)" % key_domain)
+        return torch.bincount(keys, minlength=key_domain)
+
+    ca, cb = hist(ta), hist(tb)
+    if dist.world > 1:
+        ca, cb = dist.sum_cuda(ca), dist.sum_cuda(cb)
+    expect = ca * cb
+    del ca, cb
+    want_groups = int(torch.count_nonzero(expect))
+    ok = True
+    n = res.nrows
+    if n:
+        k = torch.as_tensor(capi.DeviceArray(res.device_ptr(0), n), device=dev)
+        c = torch.as_tensor(capi.DeviceArray(res.device_ptr(1), n), device=dev)
+        ok = ok and int(k.min()) >= 0 and int(k.max()) < key_domain
+        ok = ok and bool(torch.equal(expect[k], c)) and int(c.min()) >= 1
+        ok = ok and int(torch.unique(k).numel()) == n
+    total = int(dist.sum(n))
+    ok = ok and total == want_groups
+    return bool(dist.sum(0 if ok else 1) == 0)
 
 
 def reference_step(n_rows, seed):

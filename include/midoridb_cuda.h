@@ -117,6 +117,11 @@ uint64_t mdbcu_table_live_rows(mdbcu_table *t);   /* counts on device */
 /* copy one mirrored column back (test hook): cells = 8-byte values, valid = byte flags (1 = live and not NULL) */
 int mdbcu_table_read_column(mdbcu_table *t, int col, uint64_t first, uint64_t n, void *cells, uint8_t *valid);
 
+/* zero-copy view of one mirrored column for a harness that has its own CUDA code (bench.py verifies results with an
+ * independent torch histogram): *cells = n_slots 8-byte cells in device memory, valid until the table changes or is
+ * dropped.  Rows are in slot order; NULL / tombstoned slots hold unspecified values (see mdbcu_table_read_column). */
+int mdbcu_table_column_device_ptr(mdbcu_table *t, int col, const void **cells, uint64_t *n_slots);
+
 /* ------------------------------------------------------------------ query plan */
 
 /* predicate program, postfix, mirroring the reference's RPN token stream (midorisql.y:250-282) as
@@ -202,6 +207,9 @@ int mdbcu_result_cols(const mdbcu_result *r);
 int mdbcu_result_col_type(const mdbcu_result *r, int col); /* MDBCU_CT_INTEGER or MDBCU_CT_DOUBLE */
 /* columnar fetch into caller buffers: cells[c] = rows x 8 bytes, nulls[c] = rows bytes (may be NULL) */
 int mdbcu_result_fetch_columns(mdbcu_result *r, void *const *cells, uint8_t *const *nulls);
+/* zero-copy view of one result column (device memory, rows in device order, valid until mdbcu_result_free):
+ * *cells = rows x 8 bytes, *nulls = rows byte flags or NULL when the column has no NULL cell */
+int mdbcu_result_column_device_ptr(mdbcu_result *r, int col, const void **cells, const uint8_t **nulls);
 /* replaces: table_insert_row on the result + table_vacuum (src/primitive/row.c:26, vacuum.c:12):
  * result rows laid out as page images in the reference row format (24-byte header, null bitmap,
  * packed 8-byte cells, floor(4095/row_size) rows per page, tail slots flags.empty=1; an empty

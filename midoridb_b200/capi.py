@@ -29,7 +29,8 @@ EXPORTED_SYMBOLS = [
     "mdbcu_init", "mdbcu_shutdown", "mdbcu_last_error", "mdbcu_device_sync", "mdbcu_host_alloc", "mdbcu_host_free",
     "mdbcu_table_create", "mdbcu_table_drop", "mdbcu_table_append_pages", "mdbcu_table_append_page_ptrs",
     "mdbcu_table_reload_pages", "mdbcu_table_tombstone", "mdbcu_table_append_columns", "mdbcu_table_generate",
-    "mdbcu_table_slots", "mdbcu_table_live_rows", "mdbcu_table_read_column",
+    "mdbcu_table_slots", "mdbcu_table_live_rows", "mdbcu_table_read_column", "mdbcu_table_column_device_ptr",
+    "mdbcu_result_column_device_ptr",
     "mdbcu_select",
     "mdbcu_result_rows", "mdbcu_result_cols", "mdbcu_result_col_type", "mdbcu_result_fetch_columns",
     "mdbcu_result_page_count", "mdbcu_result_row_size", "mdbcu_result_fetch_pages", "mdbcu_result_free",
@@ -118,6 +119,8 @@ def load_library():
     L.mdbcu_table_live_rows.argtypes = [vp]
     L.mdbcu_table_live_rows.restype = u64
     L.mdbcu_table_read_column.argtypes = [vp, C.c_int, u64, u64, vp, vp]
+    L.mdbcu_table_column_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(u64)]
+    L.mdbcu_result_column_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp)]
     L.mdbcu_select.argtypes = [vp, C.POINTER(Plan), C.POINTER(vp)]
     L.mdbcu_result_rows.argtypes = [vp]
     L.mdbcu_result_rows.restype = u64
@@ -269,10 +272,24 @@ class Table:
         self._check(self.backend.L.mdbcu_table_read_column(self.handle, col, first, n, cells.ctypes.data, valid.ctypes.data))
         return cells, valid
 
+    def device_ptr(self, col):
+        """(device address, slots) of one mirrored column: zero-copy hand-over to a harness with its own CUDA code"""
+        ptr, n = C.c_void_p(), C.c_uint64()
+        self._check(self.backend.L.mdbcu_table_column_device_ptr(self.handle, col, C.byref(ptr), C.byref(n)))
+        return ptr.value or 0, n.value
+
     def drop(self):
         if self.handle:
             self.backend.L.mdbcu_table_drop(self.handle)
             self.handle = None
+
+
+class DeviceArray:
+    """__cuda_array_interface__ view of library-owned device memory (torch.as_tensor(DeviceArray(...), device="cuda"))"""
+
+    def __init__(self, ptr, n, typestr="<i8", owner=None):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
 class Result:
@@ -297,6 +314,12 @@ class Result:
         cp = (C.c_void_p * max(self.ncols, 1))(*cell_ptrs)
         npn = None if null_ptrs is None else (C.c_void_p * max(self.ncols, 1))(*null_ptrs)
         self.backend._check(self.backend.L.mdbcu_result_fetch_columns(self.handle, cp, npn))
+
+    def device_ptr(self, col):
+        """device address of one result column (rows in device order)"""
+        ptr, nul = C.c_void_p(), C.c_void_p()
+        self.backend._check(self.backend.L.mdbcu_result_column_device_ptr(self.handle, col, C.byref(ptr), C.byref(nul)))
+        return ptr.value or 0
 
     def page_count(self):
         return self.backend.L.mdbcu_result_page_count(self.handle)

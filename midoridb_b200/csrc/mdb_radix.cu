@@ -54,9 +54,9 @@ static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_ta
 	static const uint32_t hints = getenv("MDBCU_P1_HINTS") ? (uint32_t)atoi(getenv("MDBCU_P1_HINTS")) : RJ_HINT_DEFAULT;
 	s->hints = hints;
 	s->cap = cap;
-	// every CTA leaves at most 15 remainders per partition; keys that overflow a staging row (about 1 in 1000 on
-	// uniform keys) land here as well: 1/32 of the main capacity on top
-	s->tail_cap = ((uint32_t)grid * RJ_FLUSH + cap / 32 + 15u) & ~15u;
+	// tail sectors (16 entries each): one per CTA and partition for the partial staging rows at the end of pass 1, one
+	// per key that found its staging row full (about 1 in 1000 on uniform keys): 1/16 of the main capacity on top
+	s->tail_cap = ((uint32_t)grid * RJ_FLUSH + cap / 16 + 15u) & ~15u;
 	if ((uint64_t)nparts * cap >= (1ull << 40))
 		return MDBCU_EUNSUPPORTED;
 	MDB_TRY(tmp.alloc(&s->stream, (size_t)nparts * cap));

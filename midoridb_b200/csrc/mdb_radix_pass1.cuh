@@ -4,12 +4,12 @@
 // One persistent 1024-thread CTA per SM.  Per round every thread takes 8 keys:
 //   insert   partition = (key - kmin) >> shift; ONE shared-memory atomic hands out a slot of the partition's
 //            40-byte staging row, ONE 2-byte shared store writes the remainder - nothing else per key.  A key that
-//            finds its row full (about 7 of 8192 per round) is put on a small CTA-wide spill list;
+//            finds its row full (about 7 of 8192 per round) stays in its thread's register until the flush;
 //   barrier  (all remainders handed out this round are in shared memory)
 //   flush    every warp owns 128 partitions: one 128-bit read of four slot counters per lane finds the rows that hold
 //            a whole sector, ballots compact them so that every lane gets one row; one global atomic on the
 //            partition's cursor gives the position, the first 16 remainders leave as ONE 256-bit store = one aligned
-//            32-byte sector; spilled keys are appended one by one to their partition's tail stream;
+//            32-byte sector; spilled keys become tail sectors of their own in the lanes the flush leaves idle;
 //   barrier
 // Measurements behind this shape (profiles/microbench/p1_lab*.cu and profiles/p1_lab_*.txt, B200, 2^28 keys):
 //   * 256-bit key loads stream at 6.4 TB/s where 128-bit loads reach 4.7;
@@ -40,7 +40,6 @@ __device__ unsigned long long rj_timeline[4][8];
 
 #define RJ_P1_WARPS (RJ_P1_THREADS / 32)
 #define RJ_P1_KEYS 8               // keys per thread per round
-#define RJ_SPILL_CAP 512           // keys per round that may find their staging row full (about 7 expected)
 #define RJ_WARP_PARTS (RJ_ROWS / RJ_P1_WARPS) // staging rows one warp flushes
 
 #define RJ_HINT_PREFETCH 1u        // prefetch.global.L2 two tiles ahead
@@ -52,8 +51,6 @@ struct RJP1Smem {
 	uint16_t stage[RJ_ROWS * RJ_CAP];         // 20 two-byte slots per staged partition (row r = partition r * RJ_SPLIT + this CTA's residue)
 	uint32_t fill[RJ_ROWS];                   // slots handed out since the last flush (may overshoot RJ_CAP)
 	uint16_t worklist[RJ_P1_WARPS][RJ_WARP_PARTS]; // per warp: those of its partitions that hold a whole sector this round
-	uint32_t spill[RJ_SPILL_CAP];             // (partition << 16 | remainder) of keys whose row was full this round
-	uint32_t spill_n[2];                      // by round parity
 };
 
 static_assert((sizeof(RJP1Smem) + 1024) * RJ_SPLIT <= 196 * 1024, "pass-1 shared memory of all CTAs of an SM must stay inside the 196 KiB carve-out");
@@ -113,20 +110,21 @@ __device__ __forceinline__ void rj_load_keys256(const void *p, uint32_t *lo, boo
 	lo[3] = t[6];
 }
 
-// the staging row of partition p is full until this round's flush: the key waits on the CTA's spill list
-__device__ static inline void rj_spill(RJP1Smem *sm, const RJParams &pr, uint32_t p, uint32_t rem, int par)
+// a single remainder as a tail sector of its own: [remainder, 14 unused, count = 1] (mdb_radix_types.cuh)
+// (out of line: cold, and the unrolled insert loop that calls it exists twice per kernel)
+__device__ __forceinline__ void rj_tail_single(uint32_t *tail_cursor, uint16_t *tail, uint32_t tail_cap, uint32_t *error_flag, uint32_t p, uint32_t rem)
 {
-	if (RJ_LAB & 1)
-		return;
-	const uint32_t o = rj_smem_add(&sm->spill_n[par], 1u);
-	if (o < RJ_SPILL_CAP)
-		sm->spill[o] = (p << 16) | rem;
+	const uint32_t at = atomicAdd(&tail_cursor[p * RJ_CUR_STRIDE], (uint32_t)RJ_FLUSH);
+	if (at + RJ_FLUSH <= tail_cap)
+		rj_store_sector(tail + (size_t)p * tail_cap + at, make_uint2(rem, 0u), make_uint2(0u, 0u), make_uint2(0u, 0u),
+				make_uint2(0u, 1u << 16), false);
 	else
-		atomicOr(pr.error_flag, RJ_ERR_SKEW);
+		atomicOr(error_flag, RJ_ERR_STREAM);
 }
 
-// insert of one item = (partition << 16 | remainder) if its partition is staged by this CTA: slot, store
-__device__ __forceinline__ void rj_insert_one(RJP1Smem *sm, const RJParams &pr, uint32_t item, int par, uint32_t half)
+// insert of one item = (partition << 16 | remainder) if its partition is staged by this CTA: slot, store.
+// (Ragged end of the column, CTA 0 only, lanes may be missing: a key that finds its row full goes to the tail directly.)
+__device__ __forceinline__ void rj_insert_one(const RJSide &s, RJP1Smem *sm, const RJParams &pr, uint32_t item, uint32_t half)
 {
 	const uint32_t p = item >> 16;
 	if (RJ_SPLIT > 1 && p % RJ_SPLIT != half)
@@ -135,15 +133,23 @@ __device__ __forceinline__ void rj_insert_one(RJP1Smem *sm, const RJParams &pr, 
 	const uint32_t pos = rj_fill_claim(sm, r);
 	if (pos < RJ_CAP)
 		sm->stage[r * RJ_CAP + pos] = (uint16_t)item;
-	else
-		rj_spill(sm, pr, p, item & 0xffffu, par);
+	else if (!(RJ_LAB & 1))
+		rj_tail_single(s.tail_cursor, s.tail, s.tail_cap, pr.error_flag, p, item & 0xffffu);
 }
 
 // 8 keys per thread.  PACKED: item = (partition << 16 | remainder), RJ_NONE = no key (generic kernel);
 // otherwise item = key - kmin and every item is a key (lean kernel).
 // All slot requests of a thread are issued back to back (independent shared-memory atomics), then consumed.
+// Returns RJ_NONE, or (partition << 16 | remainder) of a key of THIS THREAD that found its row full (7 keys in 8192 do):
+// it stays in a register until the flush, which turns it into a tail sector.  Nothing warp-wide and no shared memory
+// here: a CTA-wide list behind a shared counter, per-warp lists filled by ballots - every cooperative scheme made the
+// warp that took it several hundred cycles late at the barrier, round after round (0.07-0.1 ms per launch,
+// profiles/r02_lab3_*.txt).  A thread's second overflow in one round (about once per launch) goes to the tail directly.
+// kept_at: the key's position in its partition's tail stream - the global atomic is ISSUED here and its result is first
+// looked at after the flush, a thousand cycles later, so nobody ever waits for it.
 template <bool PACKED>
-__device__ __forceinline__ void rj_insert_items(RJP1Smem *sm, const RJParams &pr, const uint32_t *item, int par, uint32_t half)
+__device__ __forceinline__ uint32_t rj_insert_items(const RJSide &s, RJP1Smem *sm, const RJParams &pr, const uint32_t *item, uint32_t half,
+		uint32_t &kept_at)
 {
 	constexpr bool ALL_MINE = !PACKED && RJ_SPLIT == 1; // every item is a key of a partition this CTA stages
 	const int pshift = PACKED ? 16 : pr.shift;
@@ -163,34 +169,47 @@ __device__ __forceinline__ void rj_insert_items(RJP1Smem *sm, const RJParams &pr
 			sm->stage[r * RJ_CAP + pos[k]] = (uint16_t)(item[k] & rmask);
 		worst = max(worst, ALL_MINE ? pos[k] : pos[k] + 1u);
 	}
-	if (worst >= (ALL_MINE ? RJ_CAP : RJ_CAP + 1u)) { // rare: some row was full
+	// rare (7 keys in 8192): some row was full
+	uint32_t kept = RJ_NONE;
+	if (__any_sync(0xffffffffu, worst >= (ALL_MINE ? RJ_CAP : RJ_CAP + 1u)) && !(RJ_LAB & 1)) {
+		// the whole warp, branch-free: the thread's LAST key that found its row full is kept
+		uint32_t n_over = 0;
 #pragma unroll
-		for (int k = 0; k < RJ_P1_KEYS; k++)
-			if (pos[k] >= RJ_CAP && pos[k] != RJ_NONE)
-				rj_spill(sm, pr, item[k] >> pshift, item[k] & rmask, par);
+		for (int k = 0; k < RJ_P1_KEYS; k++) {
+			const bool over = pos[k] >= RJ_CAP && pos[k] != RJ_NONE;
+			kept = over ? (((item[k] >> pshift) << 16) | (item[k] & rmask)) : kept;
+			n_over += over ? 1u : 0u;
+		}
+		if (kept != RJ_NONE)
+			kept_at = atomicAdd(&s.tail_cursor[(kept >> 16) * RJ_CUR_STRIDE], (uint32_t)RJ_FLUSH);
+		if (n_over > 1) { // the others (about 700 keys per launch of 2^28) go to the tail right away
+			bool last = true;
+#pragma unroll
+			for (int k = RJ_P1_KEYS - 1; k >= 0; k--) {
+				if (pos[k] < RJ_CAP || pos[k] == RJ_NONE)
+					continue;
+				if (!last)
+					rj_tail_single(s.tail_cursor, s.tail, s.tail_cap, pr.error_flag, item[k] >> pshift, item[k] & rmask);
+				last = false;
+			}
+		}
 	}
+	return kept;
 }
 
-// barrier, every warp flushes the full rows among ITS 128 partitions, spilled keys go to the tail streams, barrier
-__device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, RJP1Smem *sm, int par, uint32_t half, long long &rj_t_)
+// barrier, every warp flushes the full rows among ITS 128 partitions, kept keys go to the tail streams, barrier.
+// (The 7 keys in 8192 that find their row full once cost 0.15 ms of a 0.85 ms launch: handled ahead of the flush by the
+// first threads of the CTA they put one more global-atomic latency on warp 0's path to the second barrier, and every
+// cooperative way of listing them made one warp late at the first: profiles/r02_lab3_*.txt.)
+// kept: this thread's key that found its row full, or RJ_NONE; kept_at: its tail position (rj_insert_items)
+__device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, RJP1Smem *sm, uint32_t kept, uint32_t kept_at, uint32_t half,
+		long long &rj_t_)
 {
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	uint16_t *wl = sm->worklist[warp];
 	RJ_STAMP(0);
 	__syncthreads();
 	RJ_STAMP(1);
-	// spilled keys: one global atomic + one 2-byte store each, issued together with the flush's atomics
-	const uint32_t nspill = min(sm->spill_n[par], (uint32_t)RJ_SPILL_CAP);
-	if (tid == 0)
-		sm->spill_n[par ^ 1] = 0; // (read by every thread before the previous round's second barrier)
-	for (uint32_t i = tid; i < nspill; i += RJ_P1_THREADS) {
-		const uint32_t item = sm->spill[i], p = item >> 16;
-		const uint32_t at = atomicAdd(&s.tail_cursor[p * RJ_CUR_STRIDE], 1u);
-		if (at < s.tail_cap)
-			s.tail[(size_t)p * s.tail_cap + at] = (uint16_t)item;
-		else
-			atomicOr(pr.error_flag, RJ_ERR_STREAM);
-	}
 	// which of this warp's rows hold a whole sector?  (the insert loop itself never looks at "row complete")
 	uint32_t wl_n = 0;
 	{
@@ -221,7 +240,16 @@ __device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, 
 		if (RJ_LAB & 4)
 			continue;
 		if (at + RJ_FLUSH <= s.cap)
-			rj_store_sector(s.stream + (size_t)p * s.cap + at, a, b, c, d, evict_last);
+			rj_store_sector(s.stream + (size_t)p * s.cap + ((RJ_LAB & 32) ? (at & 0x3f0u) : at), a, b, c, d, evict_last);
+		else
+			atomicOr(pr.error_flag, RJ_ERR_STREAM);
+	}
+	// a kept key becomes a tail sector of its own, [remainder, 14 unused, count = 1]; its position was requested during
+	// the insert phase
+	if (kept != RJ_NONE && !(RJ_LAB & 256)) {
+		if (kept_at + RJ_FLUSH <= s.tail_cap)
+			rj_store_sector(s.tail + (size_t)(kept >> 16) * s.tail_cap + kept_at, make_uint2(kept & 0xffffu, 0u), make_uint2(0u, 0u),
+					make_uint2(0u, 0u), make_uint2(0u, 1u << 16), false);
 		else
 			atomicOr(pr.error_flag, RJ_ERR_STREAM);
 	}
@@ -230,19 +258,27 @@ __device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, 
 	RJ_STAMP(3);
 }
 
-// every staged partition's partial sector goes to the partition's tail stream
+// every staged partition's partial sector (at most 15 remainders after the last flush) becomes ONE tail sector:
+// [remainders..., count in entry 15] - one global atomic and one 32-byte store per row
 __device__ static inline void rj_drain(const RJSide &s, const RJParams &pr, RJP1Smem *sm, uint32_t half)
 {
+	if (RJ_LAB & 16)
+		return;
 	for (uint32_t r = threadIdx.x; r < RJ_ROWS; r += RJ_P1_THREADS) {
 		const uint32_t p = r * RJ_SPLIT + half;
 		const uint32_t f = min(sm->fill[r], (uint32_t)RJ_CAP);
 		if (f == 0 || p >= (uint32_t)pr.nparts)
 			continue;
-		const uint32_t at = atomicAdd(&s.tail_cursor[p * RJ_CUR_STRIDE], f);
-		if (at + f <= s.tail_cap) {
-			uint16_t *dst = s.tail + (size_t)p * s.tail_cap + at;
-			for (uint32_t i = 0; i < f; i++)
-				dst[i] = sm->stage[r * RJ_CAP + i];
+		if (f >= RJ_FLUSH) { // cannot happen: the last round's flush leaves fewer than 16 behind
+			atomicOr(pr.error_flag, RJ_ERR_STREAM);
+			continue;
+		}
+		const uint32_t at = atomicAdd(&s.tail_cursor[p * RJ_CUR_STRIDE], (uint32_t)RJ_FLUSH);
+		if (at + RJ_FLUSH <= s.tail_cap) {
+			const uint2 *row = reinterpret_cast<const uint2*>(&sm->stage[r * RJ_CAP]);
+			uint2 d = row[3];
+			d.y = (d.y & 0xffffu) | (f << 16);
+			rj_store_sector(s.tail + (size_t)p * s.tail_cap + at, row[0], row[1], row[2], d, false);
 		} else {
 			atomicOr(pr.error_flag, RJ_ERR_STREAM);
 		}
@@ -253,8 +289,6 @@ __device__ static inline void rj_smem_init(RJP1Smem *sm)
 {
 	for (int r = threadIdx.x; r < RJ_ROWS; r += RJ_P1_THREADS)
 		sm->fill[r] = 0;
-	if (threadIdx.x < 2)
-		sm->spill_n[threadIdx.x] = 0;
 	__syncthreads();
 }
 
@@ -274,7 +308,6 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition_fas
 	const uint32_t kmin_lo = (uint32_t)(unsigned long long)pr.kmin;
 	const bool pf = (s.hints & RJ_HINT_PREFETCH) != 0, evict_first = (s.hints & RJ_HINT_LOAD_EVICT_FIRST) != 0;
 	uint32_t buf_a[RJ_P1_KEYS], buf_b[RJ_P1_KEYS];
-	int par = 0;
 	long long rj_t_ = (RJ_LAB & 8) ? clock64() : 0; // (timeline experiments only)
 	auto load = [&](uint64_t tile, uint32_t *dst) {
 		if (pf) {
@@ -292,9 +325,9 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition_fas
 #pragma unroll
 		for (int k = 0; k < RJ_P1_KEYS; k++)
 			item[k] = buf[k] - kmin_lo;
-		rj_insert_items<false>(sm, pr, item, par, half);
-		rj_round_end(s, pr, sm, par, half, rj_t_);
-		par ^= 1;
+		uint32_t kept_at = 0;
+		const uint32_t kept = rj_insert_items<false>(s, sm, pr, item, half, kept_at);
+		rj_round_end(s, pr, sm, kept, kept_at, half, rj_t_);
 	};
 	uint64_t tile = slot;
 	if (tile < nfull)
@@ -316,9 +349,9 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition_fas
 	if (slot == 0 && nfull * TILE != s.n) {
 		for (uint64_t r = nfull * TILE + tid; r < s.n; r += RJ_P1_THREADS) {
 			const uint32_t d = (uint32_t)(unsigned long long)s.keys[r] - kmin_lo;
-			rj_insert_one(sm, pr, ((d >> pr.shift) << 16) | (d & pr.mask), par, half);
+			rj_insert_one(s, sm, pr, ((d >> pr.shift) << 16) | (d & pr.mask), half);
 		}
-		rj_round_end(s, pr, sm, par, half, rj_t_);
+		rj_round_end(s, pr, sm, RJ_NONE, 0u, half, rj_t_);
 	}
 	rj_drain(s, pr, sm, half);
 }
@@ -352,8 +385,8 @@ __device__ static inline void rj_load_tile(const RJSide &s, uint64_t tile, int4 
 
 // generic insert phase: range test, NULL/tombstone bitmap, ragged last tile.  FULL: every row of the tile exists
 template <bool HAS_PRESENT, bool FULL>
-__device__ static inline void rj_insert_tile(const RJSide &s, const RJParams &pr, RJP1Smem *sm, const int4 *buf, uint64_t tile, int par,
-		uint32_t half)
+__device__ static inline uint32_t rj_insert_tile(const RJSide &s, const RJParams &pr, RJP1Smem *sm, const int4 *buf, uint64_t tile,
+		uint32_t half, uint32_t &kept_at)
 {
 	constexpr uint32_t TILE = RJ_P1_THREADS * RJ_P1_KEYS;
 	const uint64_t base_pair = tile * (TILE / 2);
@@ -377,7 +410,7 @@ __device__ static inline void rj_insert_tile(const RJSide &s, const RJParams &pr
 		item[2 * j] = ok0 ? ((((uint32_t)d0 >> pr.shift) << 16) | ((uint32_t)d0 & pr.mask)) : RJ_NONE;
 		item[2 * j + 1] = ok1 ? ((((uint32_t)d1 >> pr.shift) << 16) | ((uint32_t)d1 & pr.mask)) : RJ_NONE;
 	}
-	rj_insert_items<true>(sm, pr, item, par, half);
+	return rj_insert_items<true>(s, sm, pr, item, half, kept_at);
 }
 
 // Pass 1, generic variant (NULLs / tombstones / keys outside the partitioned range): same rounds as the lean
@@ -395,17 +428,14 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition(RJS
 	const uint64_t nfull = s.n / TILE; // tiles [0, nfull) are complete
 	int4 buf_a[RJ_P1_KEYS / 2], buf_b[RJ_P1_KEYS / 2];
 	uint64_t tile = slot;
-	int par = 0;
 	long long rj_t_ = (RJ_LAB & 8) ? clock64() : 0; // (timeline experiments only)
 	if (tile < ntiles)
 		rj_load_tile(s, tile, buf_a);
 	auto round = [&](const int4 *buf, uint64_t t) {
-		if (t < nfull)
-			rj_insert_tile<HAS_PRESENT, true>(s, pr, sm, buf, t, par, half);
-		else
-			rj_insert_tile<HAS_PRESENT, false>(s, pr, sm, buf, t, par, half);
-		rj_round_end(s, pr, sm, par, half, rj_t_);
-		par ^= 1;
+		uint32_t kept_at = 0;
+		const uint32_t kept = t < nfull ? rj_insert_tile<HAS_PRESENT, true>(s, pr, sm, buf, t, half, kept_at)
+				: rj_insert_tile<HAS_PRESENT, false>(s, pr, sm, buf, t, half, kept_at);
+		rj_round_end(s, pr, sm, kept, kept_at, half, rj_t_);
 	};
 	while (tile < ntiles) {
 		uint64_t next = tile + nslots;

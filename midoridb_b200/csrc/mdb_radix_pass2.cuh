@@ -6,7 +6,7 @@
 //
 // What bounds it: the remainders are read once (2 B/key) and the groups written once (16 B/group); everything
 // else is shared memory.
-//   * a partition's remainders are contiguous per source rank (main stream + tail stream, mdb_radix_types.cuh):
+//   * a partition's remainders are contiguous per source rank (main stream + tail sectors, mdb_radix_types.cuh):
 //     256-bit loads, a warp covers 1 KiB per instruction, two loads in flight per lane;
 //   * groups are written with warp-ballot compaction: for one counter position at a time the matching lanes
 //     write to consecutive output rows, so every store instruction covers a contiguous run;
@@ -52,10 +52,13 @@ __device__ __forceinline__ void rj_load256(const void *p, uint32_t *w)
 			: "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
 }
 
-// count the `ne` remainders starting at `run` (32-byte aligned; reading up to the next 32-byte boundary is safe)
-template <int BITS, int THREADS>
-__device__ __forceinline__ void rj_histogram_run(const uint16_t *__restrict__ run, uint32_t ne, uint32_t *cnt)
+// count the `ne` remainders starting at `run` (32-byte aligned; reading up to the next 32-byte boundary is safe).
+// TAIL: `run` is a tail stream - every 32-byte sector holds up to 15 remainders and their number in entry 15
+// (mdb_radix_types.cuh); returns how many remainders this thread counted (0 for main streams, whose length is known)
+template <int BITS, int THREADS, bool TAIL>
+__device__ __forceinline__ uint32_t rj_histogram_run(const uint16_t *__restrict__ run, uint32_t ne, uint32_t *cnt)
 {
+	uint32_t counted = 0;
 	constexpr int MLP = 2; // 32-byte vectors in flight per thread
 	const uint32_t nvec = (ne + 15u) / 16u;
 	for (uint32_t v0 = threadIdx.x; v0 < nvec; v0 += THREADS * MLP) {
@@ -68,7 +71,9 @@ __device__ __forceinline__ void rj_histogram_run(const uint16_t *__restrict__ ru
 			const uint32_t v = v0 + u * THREADS;
 			if (v >= nvec)
 				continue;
-			const uint32_t valid = min(16u, ne - v * 16u);
+			const uint32_t valid = TAIL ? min(15u, w[u][7] >> 16) : min(16u, ne - v * 16u);
+			if (TAIL)
+				counted += valid;
 			if (valid == 16u) {
 #pragma unroll
 				for (int j = 0; j < 8; j++) {
@@ -84,6 +89,7 @@ __device__ __forceinline__ void rj_histogram_run(const uint16_t *__restrict__ ru
 			}
 		}
 	}
+	return counted;
 }
 
 // count the keys of rows [lo, hi) of a sorted column (all of them belong to the partition being counted)
@@ -114,18 +120,19 @@ __device__ __forceinline__ void rj_histogram_sorted(const int64_t *__restrict__ 
 	}
 }
 
-// all streams of partition p on one side; returns the number of remainders (identical in every thread).
+// all streams of partition p on one side; returns the number of remainders of the main streams (identical in every
+// thread) and adds the remainders found in tail sectors to *tail_total (shared memory).
 // counts[s] = {main, tail} entries of source s, fetched for all sources at once by rj_fetch_counts.
 template <int BITS, int THREADS, bool MULTI>
 __device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, const RJParams &pr, uint32_t p, uint32_t *cnt,
-		const uint32_t (*counts)[2])
+		const uint32_t (*counts)[2], uint32_t *tail_total)
 {
 	if (r.nsrc == 0) {
 		const uint64_t lo = r.sorted_bnd[p], hi = r.sorted_bnd[p + 1];
 		rj_histogram_sorted<BITS, THREADS>(r.sorted_keys, lo, hi, (uint32_t)(unsigned long long)pr.kmin, pr.mask, cnt);
 		return (uint32_t)(hi - lo);
 	}
-	uint32_t total = 0;
+	uint32_t total = 0, in_tails = 0;
 	for (int s = 0; s < r.nsrc; s++) {
 		const uint32_t q = p - r.first[s];
 		uint32_t n_main, n_tail;
@@ -136,10 +143,12 @@ __device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, const RJP
 			n_main = min(r.cursor[s][q * r.cur_stride[s]], r.cap);
 			n_tail = min(r.tail_cursor[s][q * r.cur_stride[s]], r.tail_cap);
 		}
-		rj_histogram_run<BITS, THREADS>(r.stream[s] + (size_t)q * r.cap, n_main, cnt);
-		rj_histogram_run<BITS, THREADS>(r.tail[s] + (size_t)q * r.tail_cap, n_tail, cnt);
-		total += n_main + n_tail;
+		rj_histogram_run<BITS, THREADS, false>(r.stream[s] + (size_t)q * r.cap, n_main, cnt);
+		in_tails += rj_histogram_run<BITS, THREADS, true>(r.tail[s] + (size_t)q * r.tail_cap, n_tail, cnt);
+		total += n_main;
 	}
+	if (in_tails)
+		atomicAdd(tail_total, in_tails);
 	return total;
 }
 
@@ -179,7 +188,7 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 	const int words = D >= KPW ? D / KPW : 1;
 	uint32_t *cntA = reinterpret_cast<uint32_t*>(smem_raw);
 	uint32_t *cntB = cntA + words;
-	__shared__ uint32_t s_part, s_sumA, s_sumB;
+	__shared__ uint32_t s_part, s_sumA, s_sumB, s_tailA, s_tailB;
 	__shared__ uint32_t s_counts[2][RJ_MAX_RANKS][2]; // [side][source][main | tail] entries of the current partition
 	__shared__ uint32_t s_warp[NWARPS + 1];
 	__shared__ unsigned long long s_base;
@@ -190,7 +199,7 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 	while (true) {
 		if (tid == 0) {
 			s_part = (uint32_t)pr.part_first + atomicAdd(part_counter, 1u);
-			s_sumA = s_sumB = 0;
+			s_sumA = s_sumB = s_tailA = s_tailB = 0;
 		}
 		for (int w = tid; w < words * 2; w += THREADS)
 			cntA[w] = 0; // cntB follows cntA
@@ -207,8 +216,8 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 		}
 
 		// ---- count both sides
-		const uint32_t totA = rj_histogram_side<BITS, THREADS, MULTI>(a, pr, p, cntA, s_counts[0]);
-		const uint32_t totB = rj_histogram_side<BITS, THREADS, MULTI>(b, pr, p, cntB, s_counts[1]);
+		const uint32_t totA = rj_histogram_side<BITS, THREADS, MULTI>(a, pr, p, cntA, s_counts[0], &s_tailA);
+		const uint32_t totB = rj_histogram_side<BITS, THREADS, MULTI>(b, pr, p, cntB, s_counts[1], &s_tailB);
 		__syncthreads();
 
 		// ---- checksum + number of groups of this partition
@@ -244,7 +253,7 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 			if (lane == 31) {
 				s_base = incl ? atomicAdd(out.cursor, (unsigned long long)incl) : 0ull;
 				s_warp[NWARPS] = incl;
-				if (s_sumA != totA || s_sumB != totB)
+				if (s_sumA != totA + s_tailA || s_sumB != totB + s_tailB)
 					atomicOr(pr.error_flag, RJ_ERR_COUNTER);
 			}
 		}

@@ -25,8 +25,9 @@
 //                                                         one global atomic per sector: consecutive sectors of a
 //                                                         128-byte line are written within about a microsecond by
 //                                                         different CTAs and merge in L2 on their way to DRAM)
-//   tail  tail + p * tail_cap,    tail_cursor[p] entries  single remainders: keys that found their staging row full, and
-//                                                         the partial sectors left in the staging rows at the end
+//   tail  tail + p * tail_cap,    tail_cursor[p] entries  32-byte TAIL SECTORS [up to 15 remainders, count in entry 15]: one per
+//                                                         key that found its staging row full (count 1), and one per staging
+//                                                         row that is left partially filled at the end of pass 1
 struct RJSide {
 	const int64_t *keys;
 	const uint32_t *present;

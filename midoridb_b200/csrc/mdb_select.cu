@@ -180,6 +180,18 @@ extern "C" int mdbcu_result_col_type(const mdbcu_result *r, int col)
 	return r->cols[col].type;
 }
 
+extern "C" int mdbcu_result_column_device_ptr(mdbcu_result *r, int col, const void **cells, const uint8_t **nulls)
+{
+	if (!r || !cells || col < 0 || col >= (int)r->cols.size())
+		return MDBCU_EERROR;
+	cudaSetDevice(r->ctx->device);
+	cudaStreamSynchronize(r->ctx->stream);
+	*cells = r->cols[col].cells;
+	if (nulls)
+		*nulls = r->cols[col].nulls;
+	return MDBCU_OK;
+}
+
 extern "C" void mdbcu_result_free(mdbcu_result *r)
 {
 	if (!r)

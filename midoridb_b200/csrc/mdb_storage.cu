@@ -1043,6 +1043,20 @@ extern "C" uint64_t mdbcu_table_live_rows(mdbcu_table *t)
 	return v;
 }
 
+extern "C" int mdbcu_table_column_device_ptr(mdbcu_table *t, int col, const void **cells, uint64_t *n_slots)
+{
+	if (!t || !cells)
+		return MDBCU_EERROR;
+	if (col < 0 || col >= t->ncols)
+		return mdb_fail(t->ctx, MDBCU_EERROR, "mdbcu_table_column_device_ptr: no column %d", col);
+	cudaSetDevice(t->ctx->device);
+	cudaStreamSynchronize(t->ctx->stream); // loads issued so far are complete: any stream may read the column
+	*cells = t->cols[col].data;
+	if (n_slots)
+		*n_slots = t->n_slots;
+	return MDBCU_OK;
+}
+
 __global__ void k_expand_bits(const uint32_t *__restrict__ bm, uint64_t first, uint64_t n, uint8_t *__restrict__ out)
 {
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)

@@ -34,7 +34,7 @@ int main(int argc, char **argv)
 	s.n = n;
 	s.all_in_range = 1;
 	s.cap = (uint32_t)(2 * (n / 4096) + 2048);
-	s.tail_cap = (sms * RJ_FLUSH + s.cap / 32 + 15u) & ~15u;
+	s.tail_cap = (sms * RJ_FLUSH + s.cap / 16 + 15u) & ~15u;
 	CK(cudaMalloc(&s.stream, (size_t)4096 * s.cap * 2));
 	CK(cudaMalloc(&s.tail, (size_t)4096 * s.tail_cap * 2));
 	CK(cudaMalloc(&s.cursor, (size_t)RJ_MAX_PART * RJ_CUR_STRIDE * 4));
@@ -82,6 +82,25 @@ int main(int argc, char **argv)
 		unsigned long long total_entries = 0;
 		for (int i = 0; i < RJ_MAX_PART * RJ_CUR_STRIDE; i++)
 			total_entries += cur[i];
+		// every key must be in exactly one place: main streams hold whole sectors, tail sectors carry their count in entry 15
+		unsigned long long keys_found = 0, tail_sectors = 0;
+		{
+			static uint16_t *h_tail = nullptr;
+			if (!h_tail)
+				h_tail = (uint16_t*)malloc((size_t)4096 * s.tail_cap * 2);
+			CK(cudaMemcpy(h_tail, s.tail, (size_t)4096 * s.tail_cap * 2, cudaMemcpyDeviceToHost));
+			for (int p = 0; p < 4096; p++) {
+				keys_found += cur[p * RJ_CUR_STRIDE];
+				const uint32_t nt = cur[p * RJ_CUR_STRIDE + 1] < s.tail_cap ? cur[p * RJ_CUR_STRIDE + 1] : s.tail_cap;
+				for (uint32_t e = 0; e + 16 <= nt; e += 16) {
+					const uint32_t c = h_tail[(size_t)p * s.tail_cap + e + 15];
+					keys_found += c < 15 ? c : 15;
+					tail_sectors++;
+				}
+			}
+		}
+		printf("   keys accounted for: %llu of %llu (%lld missing), %llu tail sectors\n", keys_found, (unsigned long long)n,
+				(long long)n - (long long)keys_found, tail_sectors);
 		printf("%s hints %d: %8.3f ms  %7.1f GB/s of keys   (error flags %u, entries in streams %llu of %llu)\n",
 				variant < 8 ? "fast   " : "generic", variant < 8 ? variant : 0, total / reps, 8.0 * n / (total / reps) / 1e6, h[0], total_entries,
 				(unsigned long long)n);
