@@ -222,33 +222,72 @@ def port_step(log2_rows):
 
 
 def run_reference_arm(args, rank, world):
+    """the reference's own CPU executor on a BOUNDED SAMPLE of the workload; `config` states what actually ran"""
     if rank != 0:
         return
     from oracle import refdb
-    n = args.ref_rows
-    if refdb.available():
-        kind, sample = "reference", "README query, %dx%d rows, unique INT keys, reference nested-loop executor, 1 thread" % (n, n)
-        for _ in range(args.warmup):
-            reference_step(n, 0)
-        t = [reference_step(n, 1 + i) for i in range(args.steps)]
+    if args.config == 2:
+        n = 1 << args.ref_scan_log2
+        kind = "reference" if refdb.available() else "port"
+        for _ in range(min(args.warmup, 1)):
+            cpu_scan_step(n, kind)
+        t = [cpu_scan_step(n, kind) for _ in range(args.steps)]
         ms = 1000.0 * float(np.mean(t))
-        value = 2 * n / (ms / 1000.0)
+        value, metric = n / (ms / 1000.0), "scan_filter_aggregate_rows_per_s"
+        sample = ("SELECT COUNT(*) FROM T WHERE k >= lo AND k <= hi on 2^%d rows (the reference has no SUM; filter + COUNT only), "
+                  "reference executor, 1 thread" % args.ref_scan_log2)
+        cfg = {"workload": "BOUNDED SAMPLE of config 2: " + sample, "rows_per_table": n,
+               "sample_of": "SELECT COUNT(*), SUM(v) FROM T WHERE k BETWEEN lo AND hi, 2^30 rows BIGINT/DOUBLE"}
     else:
-        kind = "port"
-        l2 = 22
-        sample = "README query, 2^%d x 2^%d rows, uniform keys, oracle hash join+count (C port), 1 thread" % (l2, l2)
-        for _ in range(args.warmup):
-            port_step(l2)
-        t = [port_step(l2)[0] for _ in range(args.steps)]
-        ms = 1000.0 * float(np.mean(t))
-        value = 2 * (1 << l2) / (ms / 1000.0)
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        n = args.ref_rows
+        if refdb.available():
+            kind, sample = "reference", "README query, %d x %d rows, unique INT keys, reference nested-loop executor, 1 thread" % (n, n)
+            for _ in range(min(args.warmup, 1)):
+                reference_step(n, 0)
+            t = [reference_step(n, 1 + i) for i in range(args.steps)]
+            ms = 1000.0 * float(np.mean(t))
+            value = 2 * n / (ms / 1000.0)
+        else:
+            kind, n = "port", 1 << 22
+            sample = "README query, 2^22 x 2^22 rows, uniform keys, oracle hash join+count (C port), 1 thread"
+            for _ in range(min(args.warmup, 1)):
+                port_step(22)
+            t = [port_step(22)[0] for _ in range(args.steps)]
+            ms = 1000.0 * float(np.mean(t))
+            value = 2 * n / (ms / 1000.0)
+        metric = METRIC
+        cfg = {"workload": "BOUNDED SAMPLE of the headline workload: " + sample + " (O(n^2): its rows/s do not carry over to 2^28 rows)",
+               "rows_per_table": n, "key_domain": n, "sample_of": workload_config(args, world)["workload"]}
+    line = {"impl": "reference", "metric": metric, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "int64", "data": "synthetic",
-            "config": workload_config(args, world),
+            "dtype": "int64", "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def cpu_scan_step(n, kind):
+    """filter + COUNT scan on the CPU: the unmodified reference (oracle/_ref) or, without it, the oracle port"""
+    rng = np.random.default_rng(3)
+    k = rng.integers(0, 1 << 31, n).astype(np.int64)
+    lo, hi = 1 << 29, 3 * (1 << 29) - 1
+    if kind == "reference":
+        from oracle import refdb
+        with refdb.RefDatabase() as db:
+            t = db.create_table("T", ["k"], [refdb.CT_INTEGER])
+            db.append(t, k)
+            t0 = time.perf_counter()
+            db.query("SELECT COUNT(*) FROM T WHERE k >= %d AND k <= %d;" % (lo, hi))
+            return time.perf_counter() - t0
+    from midoridb_b200 import capi
+    from oracle import oracle
+    ot = oracle.OracleTable([capi.CT_INTEGER])
+    ot.append_columns([k])
+    plan = capi.make_plan([ot], pred=[("col", 0, 0), ("int", lo), ("cmp", 6), ("col", 0, 0), ("int", hi), ("cmp", 5), ("and",)],
+                          out=[(capi.OUT_COUNT_STAR,)])
+    t0 = time.perf_counter()
+    oracle.select(plan)
+    return time.perf_counter() - t0
 
 
 def workload_config(args, world):
@@ -259,6 +298,258 @@ def workload_config(args, world):
             "l2_hygiene": "inputs (%.1f GB) far larger than the 126 MB L2" % (16.0 * (1 << args.log2_rows) / 1e9)}
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# The other configurations of BASELINE.json (2, 4, 5): device-resident inputs, CUDA events on the library's stream,
+# every result checked against an independent torch computation over zero-copy views of the mirrored columns.
+
+def _dev_tensor(t, col, dtype_str="<i8"):
+    import torch
+    from midoridb_b200 import capi
+    ptr, n = t.device_ptr(col)
+    return torch.as_tensor(capi.DeviceArray(ptr, n, dtype_str), device=torch.device("cuda", t.backend.device))
+
+
+def _timed(be, step, steps, warmup):
+    for _ in range(warmup):
+        step()
+    be.sync()
+    be.event_record(2)
+    for _ in range(steps):
+        st = step()
+    be.event_record(3)
+    be.sync()
+    return be.event_elapsed_ms(2, 3) / steps, st
+
+
+def run_config2(be, args, peak, log2_rows=30, steps=5, warmup=3):
+    """SELECT COUNT(*), SUM(v) FROM T WHERE k BETWEEN lo AND hi   T(k BIGINT, v DOUBLE), 16 B per row read once"""
+    import torch
+    from midoridb_b200 import capi
+    n = 1 << log2_rows
+    t = be.create_table("T", [capi.CT_INTEGER, capi.CT_DOUBLE])
+    t.generate(n, [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=(1 << 31) - 1, seed=3),
+                   capi.GenSpec(kind=capi.GEN_UNIFORM_DBL, lo=0, hi=1, seed=4)])
+    lo, hi = 1 << 29, 3 * (1 << 29) - 1  # 50 % selectivity (SURVEY.md 8d)
+    plan = capi.make_plan([t], pred=[("col", 0, 0), ("int", lo), ("cmp", 6), ("col", 0, 0), ("int", hi), ("cmp", 5), ("and",)],
+                          out=[(capi.OUT_COUNT_STAR,), (capi.OUT_SUM, 0, 1)])
+    got = {}
+
+    def step():
+        res = be.select(plan)
+        st = be.stats()
+        cols, _ = res.fetch_columns()
+        got["count"], got["sum"] = int(cols[0][0]), float(cols[1][0])
+        res.free()
+        return st
+
+    ms, st = _timed(be, step, steps, warmup)
+    if st.path != capi.PATH_SCAN_AGG:
+        raise SystemExit("bench: the fused scan+aggregate path did not run (path=%d)" % st.path)
+    verified = None
+    if not args.no_verify:
+        k, v = _dev_tensor(t, 0), _dev_tensor(t, 1, "<f8")
+        m = (k >= lo) & (k <= hi)
+        want_count = int(m.sum())
+        want_sum = float(torch.where(m, v, torch.zeros((), dtype=v.dtype, device=v.device)).sum())
+        verified = bool(want_count == got["count"] and abs(want_sum - got["sum"]) <= 1e-9 * abs(want_sum))
+        del k, v, m
+        torch.cuda.empty_cache()
+    t.drop()
+    gbs = 16.0 * n / (ms / 1000.0) / 1e9
+    return {"config": 2, "workload": "SELECT COUNT(*), SUM(v) FROM T WHERE k BETWEEN lo AND hi, 2^%d rows BIGINT/DOUBLE, 50%% selectivity" % log2_rows,
+            "path": "k_scan_filter_aggregate", "ms_per_query": ms, "rows_per_s": n / (ms / 1000.0), "algorithmic_bytes": 16 * n,
+            "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak, "count": got["count"], "verified": verified,
+            "tolerance": "COUNT exact, DOUBLE SUM 1e-9 relative (torch float64 reduction)",
+            "note": "query time includes the 16-byte result fetch and the host round trip"}
+
+
+def run_config5(be, args, peak, log2_rows=30, steps=5, warmup=3):
+    """D(id, g) 65 536 rows JOIN F(fk, m) 2^30 rows ON id = fk GROUP BY g MIN(m), MAX(m): 16 B per fact row read once"""
+    import torch
+    from midoridb_b200 import capi
+    n = 1 << log2_rows
+    I = capi.CT_INTEGER
+    td, tf = be.create_table("D", [I, I]), be.create_table("F", [I, I])
+    td.generate(65536, [capi.GenSpec(kind=capi.GEN_PERMUTATION, lo=0, hi=65535, seed=5), capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=1023, seed=6)])
+    tf.generate(n, [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=65535, seed=7), capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=(1 << 31) - 1, seed=8)])
+    plan = capi.make_plan([td, tf], joins=[((0, 0), (1, 0))], group=[(0, 1)],
+                          out=[(capi.OUT_COLUMN, 0, 1), (capi.OUT_MIN, 1, 1), (capi.OUT_MAX, 1, 1)])
+    got = {}
+
+    def step():
+        res = be.select(plan)
+        st = be.stats()
+        got["cols"], _ = res.fetch_columns()
+        res.free()
+        return st
+
+    ms, st = _timed(be, step, steps, warmup)
+    if st.path != capi.PATH_DIRECT_STAR:
+        raise SystemExit("bench: the star-join path did not run (path=%d)" % st.path)
+    verified = None
+    if not args.no_verify:
+        did, dg, fk, m = _dev_tensor(td, 0), _dev_tensor(td, 1), _dev_tensor(tf, 0), _dev_tensor(tf, 1)
+        gmap = torch.empty(65536, dtype=torch.int64, device=did.device)
+        gmap[did] = dg
+        grp = gmap[fk]
+        big = torch.iinfo(torch.int64)
+        mn = torch.full((1024,), big.max, dtype=torch.int64, device=did.device).scatter_reduce_(0, grp, m, "amin")
+        mx = torch.full((1024,), big.min, dtype=torch.int64, device=did.device).scatter_reduce_(0, grp, m, "amax")
+        g_got = torch.from_numpy(np.ascontiguousarray(got["cols"][0])).to(did.device)
+        verified = bool(len(got["cols"][0]) == int((mn != big.max).sum()) and
+                        torch.equal(mn[g_got].cpu(), torch.from_numpy(np.ascontiguousarray(got["cols"][1]))) and
+                        torch.equal(mx[g_got].cpu(), torch.from_numpy(np.ascontiguousarray(got["cols"][2]))))
+        del did, dg, fk, m, gmap, grp
+        torch.cuda.empty_cache()
+    groups = len(got["cols"][0])
+    td.drop()
+    tf.drop()
+    gbs = 16.0 * n / (ms / 1000.0) / 1e9
+    return {"config": 5, "workload": "D(65536 rows) JOIN F(2^%d rows) ON id = fk GROUP BY g MIN(m), MAX(m)" % log2_rows,
+            "path": "k_star_probe", "ms_per_query": ms, "probe_kernel_ms": st.dominant_ms, "rows_per_s": n / (ms / 1000.0),
+            "algorithmic_bytes": 16 * n, "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak,
+            "kernel_frac": 16.0 * n / (st.dominant_ms / 1000.0) / 1e9 / peak if st.dominant_ms else None,
+            "groups": groups, "verified": verified, "tolerance": "bit-exact (integer MIN/MAX)"}
+
+
+def run_config4(be, args, peak, log2_rows=26, log2_dim=20, steps=5, warmup=4):
+    """A(id Zipf 1.1, x) JOIN B(id, y) JOIN C(id, z) WHERE A.x >= 0.25 AND B.y < 500 GROUP BY A.id SUM(A.x), AVG(C.z)"""
+    import torch
+    from midoridb_b200 import capi
+    n, nd = 1 << log2_rows, 1 << log2_dim
+    I, D = capi.CT_INTEGER, capi.CT_DOUBLE
+    ta, tb, tc = be.create_table("A", [I, D]), be.create_table("B", [I, I]), be.create_table("C", [I, I])
+    ta.generate(n, [capi.GenSpec(kind=capi.GEN_ZIPF, lo=0, hi=nd - 1, param=1.1, seed=11), capi.GenSpec(kind=capi.GEN_UNIFORM_DBL, seed=12)])
+    tb.generate(nd, [capi.GenSpec(kind=capi.GEN_PERMUTATION, lo=0, hi=nd - 1, seed=13), capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=999, seed=14)])
+    tc.generate(nd, [capi.GenSpec(kind=capi.GEN_PERMUTATION, lo=0, hi=nd - 1, seed=15), capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=49, seed=16)])
+    plan = capi.make_plan([ta, tb, tc], joins=[((0, 0), (1, 0)), ((0, 0), (2, 0))],
+                          pred=[("col", 0, 1), ("dbl", 0.25), ("cmp", 6), ("col", 1, 1), ("int", 500), ("cmp", 1), ("and",)],
+                          group=[(0, 0)], out=[(capi.OUT_COLUMN, 0, 0), (capi.OUT_SUM, 0, 1), (capi.OUT_AVG, 2, 1)])
+    got = {}
+
+    def step():
+        res = be.select(plan)
+        st = be.stats()
+        got["n"] = res.nrows
+        return st, res
+
+    def timed_step():
+        st, res = step()
+        res.free()
+        return st
+
+    ms, st = _timed(be, timed_step, steps, warmup)
+    verified = None
+    if not args.no_verify:
+        st2, res = step()
+        cols, _ = res.fetch_columns()
+        res.free()
+        aid, ax = _dev_tensor(ta, 0), _dev_tensor(ta, 1, "<f8")
+        ymap = torch.empty(nd, dtype=torch.int64, device=aid.device)
+        zmap = torch.empty(nd, dtype=torch.int64, device=aid.device)
+        ymap[_dev_tensor(tb, 0)] = _dev_tensor(tb, 1)
+        zmap[_dev_tensor(tc, 0)] = _dev_tensor(tc, 1)
+        m = (ax >= 0.25) & (ymap[aid] < 500)
+        ids = aid[m]
+        sx = torch.zeros(nd, dtype=torch.float64, device=aid.device).index_add_(0, ids, ax[m])
+        sz = torch.zeros(nd, dtype=torch.float64, device=aid.device).index_add_(0, ids, zmap[ids].to(torch.float64))
+        cn = torch.bincount(ids, minlength=nd)
+        g = torch.from_numpy(np.ascontiguousarray(cols[0])).to(aid.device)
+        got_sum = torch.from_numpy(np.ascontiguousarray(cols[1])).to(aid.device)
+        got_avg = torch.from_numpy(np.ascontiguousarray(cols[2])).to(aid.device)
+        ok = int((cn > 0).sum()) == len(cols[0]) and int(torch.unique(g).numel()) == len(cols[0])
+        ok = ok and bool(((got_sum - sx[g]).abs() <= 1e-9 * sx[g].abs()).all())
+        want_avg = sz[g] / cn[g].to(torch.float64)
+        ok = ok and bool(((got_avg - want_avg).abs() <= 1e-9 * want_avg.abs().clamp_min(1e-300)).all())
+        verified = bool(ok)
+        del aid, ax, ymap, zmap, m, ids, sx, sz, cn
+        torch.cuda.empty_cache()
+    for t in (ta, tb, tc):
+        t.drop()
+    rows = n + 2 * nd
+    alg = 16 * n + 2 * 16 * nd + 24 * got["n"]  # SURVEY.md 8(d)
+    gbs = alg / (ms / 1000.0) / 1e9
+    names = {capi.PATH_GENERAL: "general operators", capi.PATH_FUSED_MULTIWAY: "k_group_update<StarSource> (fused multiway)"}
+    return {"config": 4, "workload": "A(2^%d, Zipf 1.1) JOIN B JOIN C (2^%d each) WHERE A.x >= 0.25 AND B.y < 500 GROUP BY A.id SUM(A.x), AVG(C.z)"
+                                    % (log2_rows, log2_dim),
+            "path": names.get(st.path, str(st.path)), "ms_per_query": ms, "rows_per_s": rows / (ms / 1000.0), "algorithmic_bytes": alg,
+            "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak, "groups": got["n"], "kernel_launches": int(st.kernel_launches),
+            "phase_ms": list(st.phase_ms), "verified": verified, "tolerance": "keys exact, DOUBLE SUM / AVG 1e-9 relative"}
+
+
+def cpu_port_baseline(config):
+    """labelled oracle 'port' baselines for the configurations the reference cannot run at all (no SUM/MIN/MAX/AVG, broken
+    second join: SURVEY.md D3): the plain-C restatement, one thread, reduced scale"""
+    from midoridb_b200 import capi
+    from oracle import oracle
+    rng = np.random.default_rng(config)
+    I, D = capi.CT_INTEGER, capi.CT_DOUBLE
+    if config == 4:
+        n, nd = 1 << 20, 1 << 14
+        w = 1.0 / np.arange(1, nd + 1) ** 1.1
+        a_id = rng.choice(nd, size=n, p=w / w.sum()).astype(np.int64)
+        oa, ob, oc = oracle.OracleTable([I, D]), oracle.OracleTable([I, I]), oracle.OracleTable([I, I])
+        oa.append_columns([a_id, rng.random(n)])
+        ob.append_columns([rng.permutation(nd).astype(np.int64), rng.integers(0, 1000, nd).astype(np.int64)])
+        oc.append_columns([rng.permutation(nd).astype(np.int64), rng.integers(0, 50, nd).astype(np.int64)])
+        plan = capi.make_plan([oa, ob, oc], joins=[((0, 0), (1, 0)), ((0, 0), (2, 0))],
+                              pred=[("col", 0, 1), ("dbl", 0.25), ("cmp", 6), ("col", 1, 1), ("int", 500), ("cmp", 1), ("and",)],
+                              group=[(0, 0)], out=[(capi.OUT_COLUMN, 0, 0), (capi.OUT_SUM, 0, 1), (capi.OUT_AVG, 2, 1)])
+        rows, sample = n + 2 * nd, "config 4 at A = 2^20 rows, B = C = 2^14 rows"
+    else:
+        n = 1 << 22
+        od, of = oracle.OracleTable([I, I]), oracle.OracleTable([I, I])
+        od.append_columns([rng.permutation(65536).astype(np.int64), rng.integers(0, 1024, 65536).astype(np.int64)])
+        of.append_columns([rng.integers(0, 65536, n).astype(np.int64), rng.integers(0, 1 << 31, n).astype(np.int64)])
+        plan = capi.make_plan([od, of], joins=[((0, 0), (1, 0))], group=[(0, 1)],
+                              out=[(capi.OUT_COLUMN, 0, 1), (capi.OUT_MIN, 1, 1), (capi.OUT_MAX, 1, 1)])
+        rows, sample = n, "config 5 at F = 2^22 rows, D = 65536 rows"
+    t0 = time.perf_counter()
+    oracle.select(plan)
+    dt = time.perf_counter() - t0
+    return {"value": rows / dt, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
+            "sample": sample + ", oracle/mdb_oracle.c (plain-C restatement with hash join / hash group-by, NOT the reference: "
+                               "the reference cannot execute this query), 1 thread"}
+
+
+def cpu_scan_baseline(args):
+    from oracle import refdb
+    kind = "reference" if refdb.available() else "port"
+    n = 1 << args.ref_scan_log2
+    dt = cpu_scan_step(n, kind)
+    return {"value": n / dt, "unit": UNIT, "cores": 1, "kind": kind, "seconds": dt,
+            "sample": "SELECT COUNT(*) FROM T WHERE k >= lo AND k <= hi on 2^%d rows (filter + COUNT only: the reference has no SUM), "
+                      "1 of the host's cores" % args.ref_scan_log2}
+
+
+EXTRA = {2: run_config2, 4: run_config4, 5: run_config5}
+
+
+def run_single_config(args, rank, world, local):
+    """python bench.py --config {2,4,5}: that configuration alone, same JSON contract (single GPU)"""
+    from midoridb_b200 import capi
+    if rank != 0:
+        return
+    be = capi.Backend(local)
+    peak, peak_src = measured_peaks()
+    sampler = ClockSampler(local)
+    r = EXTRA[args.config](be, args, peak, steps=args.steps, warmup=args.warmup)
+    clocks = sampler.stop()
+    cpu = None
+    if not args.no_cpu_baseline:
+        cpu = cpu_scan_baseline(args) if args.config == 2 else cpu_port_baseline(args.config)
+    be.close()
+    metric = {2: "scan_filter_aggregate_rows_per_s", 4: "threeway_join_groupby_rows_per_s", 5: "star_join_groupby_rows_per_s"}[args.config]
+    line = {"metric": metric, "value": r["rows_per_s"], "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": r["ms_per_query"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64" if args.config != 5 else "int64", "data": "synthetic", "config": {"workload": r["workload"]},
+            "verified": r["verified"], "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": r["path"], "achieved": r["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": r["frac"],
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": r["algorithmic_bytes"]},
+            "cpu_baseline": cpu, "detail": r}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -266,15 +557,26 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log2-rows", type=int, default=28)
+    ap.add_argument("--config", type=int, default=3, choices=[1, 2, 3, 4, 5], help="BASELINE.json configuration (3 = headline)")
     ap.add_argument("--ref-rows", type=int, default=3072, help="rows per table of the reference arm's bounded sample")
+    ap.add_argument("--cpu-rows", type=int, default=10000, help="rows per table of the cpu_baseline leg (BASELINE configs[0]: 10k x 10k)")
+    ap.add_argument("--ref-scan-log2", type=int, default=19, help="log2 rows of the reference's filter scan (config 2 baseline)")
+    ap.add_argument("--qe-log2-rows", type=int, default=20, help="rows per table of the query_execute leg (SQL INSERTs)")
+    ap.add_argument("--no-verify", action="store_true", help="skip the torch cross-check of the results")
+    ap.add_argument("--no-extra", action="store_true", help="skip the extra_configs block (configs 2, 4, 5)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
     rank, world, local = dist_env()
+    if args.config == 1:
+        args.log2_rows = 14  # BASELINE configs[0] (10k x 10k on the CPU reference) at the nearest power of two: a latency configuration
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
+        return
+    if args.config in EXTRA:
+        run_single_config(args, rank, world, local)
         return
 
     from midoridb_b200 import capi
@@ -311,7 +613,7 @@ def main():
 
     for _ in range(args.warmup):
         st, groups = step()
-    if st.path != capi.PATH_RADIX_JOINCOUNT:
+    if st.path != capi.PATH_RADIX_JOINCOUNT and args.log2_rows >= 20:
         raise SystemExit("bench: the radix join+count path did not run (path=%d)" % st.path)
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -341,6 +643,14 @@ def main():
     if clocks is not None:
         clocks["window"] = "timed region + %d further untimed steps of the same load" % n_extra
     total_groups = dist.sum(groups)
+    # ---- correctness where the numbers are: one more (untimed) execution, checked row by row against torch histograms
+    verified = None
+    if not args.no_verify:
+        res = be.select(plan)
+        verified = verify_join_count(be, ta, tb, res, n_total, dist, local) and res.nrows == groups
+        res.free()
+        import torch
+        torch.cuda.empty_cache()
     rows_per_step = 2 * n_total
     value = rows_per_step / (ms_per_step / 1000.0)
     phase /= args.steps
@@ -350,15 +660,9 @@ def main():
     part_ms_per_launch = dist.max(phase[1]) / 2.0
     part_bytes_per_launch = 8.0 * n_local
     achieved = part_bytes_per_launch / (part_ms_per_launch / 1000.0) / 1e9 if part_ms_per_launch > 0 else 0.0
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get("k_radix_partition_dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+    traffic, traffic_src = ncu_traffic(n_local)
     roofline = {"bound": "hbm", "kernel": "k_radix_partition", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": part_bytes_per_launch, "ms_per_launch": part_ms_per_launch}
     step_gbs = alg_bytes / (ms_per_step / 1000.0) / 1e9
     roofline_step = {"bound": "hbm", "what": "whole step: (8|A| + 8|B| + 16 G) bytes / step device time", "achieved": step_gbs,
@@ -381,19 +685,35 @@ def main():
     if not args.no_e2e:
         e2e = run_e2e(args, be, dist, ta, tb, n_local, rows_per_step, flags)
 
+    ta.drop()
+    tb.drop()
+    if e2e is not None and rank == 0 and world == 1:
+        e2e["query_execute"] = run_query_execute(args)
+
+    # ---- the other BASELINE configurations at full size (single GPU; they do not fit next to the headline tables at N > 1 shards)
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra and args.config == 3:
+        extra = {}
+        for c in (2, 4, 5):
+            extra["config_%d" % c] = EXTRA[c](be, args, peak)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = run_cpu_baseline(args)
-
-    ta.drop()
-    tb.drop()
+        if extra is not None:
+            extra["config_2"]["cpu_baseline"] = cpu_scan_baseline(args)
+            extra["config_4"]["cpu_baseline"] = cpu_port_baseline(4)
+            extra["config_5"]["cpu_baseline"] = cpu_port_baseline(5)
     be.close()
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int64",
                 "data": "synthetic", "config": workload_config(args, world), "wall_ms_per_step": wall_ms / args.steps,
-                "result_groups": int(total_groups), "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
-                "roofline_step": roofline_step, "nvlink": nvlink, "e2e": e2e, "cpu_baseline": cpu_baseline}
+                "result_groups": int(total_groups), "verified": verified,
+                "verified_how": "every (key, count) row of every rank == torch.bincount(A) * torch.bincount(B), keys distinct, "
+                                "total rows == keys present on both sides",
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline,
+                "roofline_step": roofline_step, "nvlink": nvlink, "e2e": e2e, "cpu_baseline": cpu_baseline, "extra_configs": extra}
         print(json.dumps(line))
     dist.close()
 
@@ -449,17 +769,106 @@ def run_e2e(args, be, dist, ta, tb, n_local, rows_per_step, flags):
     assert groups > 0 and k.min() >= 0 and c.min() >= 1
     out = {"value": rows_per_step / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms,
            "h2d_bytes_per_step": int((npa + npb) * capi.PAGE_SIZE), "d2h_bytes_per_step": int(16 * groups),
-           "what": "mdbcu_table_create + mdbcu_table_append_pages (host page images, reference row format, pinned) x2, "
-                   "mdbcu_select, mdbcu_result_fetch_columns to pinned host memory, per step"}
+           "what": "COLD mirror: mdbcu_table_create + mdbcu_table_append_pages (host page images, reference row format, pinned) x2, "
+                   "mdbcu_select, mdbcu_result_fetch_columns to pinned host memory, per step",
+           "h2d_gbs": (npa + npb) * capi.PAGE_SIZE / (ms / 1000.0) / 1e9,
+           "note": "PCIe-bound: the reference row format carries 32 bytes per 8-byte key"}
     for a in (pa, pb, out_keys, out_cnts):
         be.host_free(a)
+
+    # ---- warm mirror: what a SELECT costs once the tables are mirrored (the design's normal state: INSERT/UPDATE/DELETE keep the
+    # mirror in sync page by page): mdbcu_select + the result as page images in the reference's row format on the host
+    plan = capi.make_plan([ta, tb], joins=[((0, 0), (1, 0))], group=[(0, 0)],
+                          out=[(capi.OUT_COLUMN, 0, 0), (capi.OUT_COUNT_STAR,)], flags=flags)
+    res = be.select(plan)
+    n_res_pages = res.page_count()
+    res.free()
+    host_pages = be.host_array((n_res_pages + 1024) * capi.PAGE_SIZE)
+
+    def warm_step():
+        res = be.select(plan)
+        npg = res.page_count()
+        res.fetch_pages(out=host_pages)
+        res.free()
+        return npg
+
+    warm_step()
+    dist.barrier()
+    be.sync()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        npg = warm_step()
+    be.sync()
+    wms = dist.max(1000.0 * (time.perf_counter() - t0) / args.e2e_steps)
+    be.host_free(host_pages)
+    out["warm"] = {"value": rows_per_step / (wms / 1000.0), "unit": UNIT, "ms_per_step": wms, "h2d_bytes_per_step": 0,
+                   "d2h_bytes_per_step": int(npg * capi.PAGE_SIZE),
+                   "what": "WARM mirror (tables already mirrored in HBM): mdbcu_select + mdbcu_result_fetch_pages (result rows as "
+                           "page images in the reference row format, what query_cur_step walks) to pinned host memory, per step"}
     return out
+
+
+def run_query_execute(args):
+    """the reference's own public surface (database_open / query_execute / query_cur_step / query_column_int64 / query_free,
+    src/engine/query.c:35-146) served by libmidoridb_b200.so: rows INSERTed through SQL, the README query, the cursor walked"""
+    import ctypes as C
+    from midoridb_b200 import db as mdb
+    n = 1 << args.qe_log2_rows
+    rng = np.random.default_rng(5)
+    with mdb.Database() as d:
+        d.execute("CREATE TABLE A (id_a INT);")
+        d.execute("CREATE TABLE B (id_b INT);")
+        t0 = time.perf_counter()
+        for name, seed_keys in (("A", rng.integers(0, n, n)), ("B", rng.integers(0, n, n))):
+            for i in range(0, n, 8192):
+                d.execute("INSERT INTO %s VALUES %s;" % (name, ",".join("(%d)" % v for v in seed_keys[i:i + 8192])))
+        insert_s = time.perf_counter() - t0
+        L = d.L
+        times = []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            out = L.query_execute(C.byref(d.db), QUERY.encode())
+            t1 = time.perf_counter()
+            if out.contents.status != mdb.ST_OK_WITH_RESULTS:
+                raise SystemExit("query_execute failed: %s" % out.contents.error.decode(errors="replace"))
+            rs = C.byref(out.contents.results)
+            rows, total = 0, 0
+            while L.query_cur_step(rs) == mdb.MIDORIDB_ROW:
+                rows += 1
+                total += L.query_column_int64(rs, 1) if rep == 2 else 0
+            t2 = time.perf_counter()
+            L.query_free(out)
+            times.append((t1 - t0, t2 - t1))
+        path, _ = d.last_path()
+    qe_ms = 1000.0 * min(t[0] for t in times)
+    return {"value": 2 * n / (qe_ms / 1000.0), "unit": UNIT, "ms_per_query_execute": qe_ms, "rows_per_table": n, "result_rows": rows,
+            "cursor_walk_ms_python_ctypes": 1000.0 * times[-1][1], "sql_insert_s": insert_s, "path": int(path),
+            "what": "query_execute(db, README query) on tables filled by SQL INSERT through libmidoridb_b200.so (host pages -> device mirror "
+                    "kept in sync -> mdbcu_select -> result pages); the cursor walk is timed separately (one ctypes call per row and "
+                    "column from Python: FFI overhead, not library time)"}
+
+
+def ncu_traffic(n_local):
+    """DRAM bytes per k_radix_partition launch from the newest `ncu --set full` capture under profiles/ - only when that capture
+    was taken on THIS version of the kernel (sha of the pass-1 source) and on the same shard size; else None (stale)"""
+    import glob
+    import hashlib
+    src = os.path.join(ROOT, "midoridb_b200", "csrc", "mdb_radix_pass1.cuh")
+    sig = hashlib.sha1(open(src, "rb").read()).hexdigest()[:16]
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_traffic.json")), reverse=True):
+        try:
+            j = json.load(open(path))
+        except Exception:
+            continue
+        if j.get("pass1_source_sha1_16") == sig and int(j.get("keys_per_launch", 0)) == int(n_local):
+            return j.get("k_radix_partition_dram_bytes_per_launch"), os.path.relpath(path, ROOT)
+    return None, "no ncu capture of this kernel version at this shard size under profiles/ (sha %s)" % sig
 
 
 def run_cpu_baseline(args):
     from oracle import refdb
     if refdb.available():
-        n = args.ref_rows
+        n = args.cpu_rows
         reference_step(256, 0)
         dt = reference_step(n, 1)
         return {"value": 2 * n / dt, "unit": UNIT, "cores": 1, "kind": "reference", "seconds": dt,

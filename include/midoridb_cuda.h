@@ -240,7 +240,10 @@ struct mdbcu_stats {
 #define MDBCU_PATH_RADIX_JOINCOUNT 2 /* radix-partitioned join + GROUP BY join key, COUNT(*) */
 #define MDBCU_PATH_DIRECT_STAR    3 /* small build side, direct-addressed probe + grouped MIN/MAX/SUM/COUNT */
 #define MDBCU_PATH_FUSED_MULTIWAY 4 /* scan of tables[0] with direct row tables for every joined table, WHERE and grouped
-                                      aggregates in one kernel (no tuple arrays); opt-in: MDBCU_FUSED_MULTIWAY=1 */
+                                      aggregates in one kernel (no tuple arrays); MDBCU_FUSED_MULTIWAY=0 disables it */
+#define MDBCU_PATH_DIRECT_COUNT   5 /* join + GROUP BY join key + COUNT(*) with one 32-bit counter per key value: any key
+                                      multiplicity, skew or order (what the radix path hands back); distributed plans sum
+                                      the counters over the ranks */
 int mdbcu_get_stats(mdbcu_ctx *ctx, struct mdbcu_stats *out);
 
 /* CUDA events on the context's own stream (the stream every kernel of this library is launched on), so a
@@ -257,10 +260,30 @@ int mdbcu_event_elapsed_ms(mdbcu_ctx *ctx, int slot_start, int slot_stop, double
 int mdbcu_comm_unique_id(mdbcu_ctx *ctx, void *id128);
 int mdbcu_comm_init(mdbcu_ctx *ctx, int rank, int world, const void *id128);
 int mdbcu_comm_world(mdbcu_ctx *ctx, int *rank, int *world);
+/* Several contexts of ONE process as the ranks 0..world-1 of a communicator (instead of mdbcu_comm_init): one host thread
+ * per context drives its rank, collectives meet in a host rendezvous, exchange arenas are plain peer pointers.  The
+ * contexts may sit on different GPUs (peer access is enabled) or all on the same GPU - the loop-back mode that lets a
+ * single-GPU box run the exchange kernels of a distributed plan.  Call once, from one thread, before the
+ * contexts are used; every collective call (mdbcu_table_sync_stats, a MDBCU_PLAN_DISTRIBUTED select) must then be made
+ * by all ranks concurrently, each from its own thread. */
+int mdbcu_comm_init_local(mdbcu_ctx *const *ctxs, int world);
 /* COLLECTIVE (every rank calls it for its shard of the same table): exchanges the zone-map statistics
  * (min / max per integer column) so every rank partitions by the same global key range.  Call after loading
  * or changing a sharded table, before a MDBCU_PLAN_DISTRIBUTED select. */
 int mdbcu_table_sync_stats(mdbcu_table *t);
+
+/* How a distributed radix join (join + GROUP BY join key + COUNT(*)) lays out its exchange; pure host arithmetic, usable
+ * without a device (tests).  Rank r owns partitions [part_first[r], part_first[r + 1]); every rank's arena holds, per
+ * join side, one slot per source rank with the streams of the partitions the arena's owner owns. */
+struct mdbcu_dist_layout {
+	uint32_t part_first[9];       /* world + 1 entries */
+	uint32_t stream_cap, tail_cap; /* entries per partition in the main / tail stream (identical on every rank) */
+	uint32_t owned_max;           /* partitions a slot has room for */
+	uint64_t slot_main_off, slot_tail_off, slot_cursor_off, slot_tail_cursor_off, slot_bytes;
+	uint64_t arena_half_bytes;    /* one of the two halves alternate queries use */
+};
+int mdbcu_dist_describe(int nparts, int world, uint64_t global_rows, int sms, struct mdbcu_dist_layout *out);
+int mdbcu_dist_owner(uint32_t partition, int nparts, int world); /* rank that owns `partition`, -1 if out of range */
 
 const char *mdbcu_version(void);
 

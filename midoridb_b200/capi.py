@@ -23,7 +23,7 @@ CMP_LT, CMP_GT, CMP_NE, CMP_EQ, CMP_LE, CMP_GE = 1, 2, 3, 4, 5, 6
 OUT_COLUMN, OUT_COUNT_STAR, OUT_COUNT_COL, OUT_SUM, OUT_MIN, OUT_MAX, OUT_AVG = range(7)
 PLAN_DISTRIBUTED, PLAN_NO_FASTPATH = 1, 2
 GEN_UNIFORM_INT, GEN_UNIFORM_DBL, GEN_PERMUTATION, GEN_ZIPF, GEN_SEQUENCE = range(5)
-PATH_GENERAL, PATH_SCAN_AGG, PATH_RADIX_JOINCOUNT, PATH_DIRECT_STAR, PATH_FUSED_MULTIWAY = range(5)
+PATH_GENERAL, PATH_SCAN_AGG, PATH_RADIX_JOINCOUNT, PATH_DIRECT_STAR, PATH_FUSED_MULTIWAY, PATH_DIRECT_COUNT = range(6)
 
 EXPORTED_SYMBOLS = [
     "mdbcu_init", "mdbcu_shutdown", "mdbcu_last_error", "mdbcu_device_sync", "mdbcu_host_alloc", "mdbcu_host_free",
@@ -34,7 +34,7 @@ EXPORTED_SYMBOLS = [
     "mdbcu_select",
     "mdbcu_result_rows", "mdbcu_result_cols", "mdbcu_result_col_type", "mdbcu_result_fetch_columns",
     "mdbcu_result_page_count", "mdbcu_result_row_size", "mdbcu_result_fetch_pages", "mdbcu_result_free",
-    "mdbcu_get_stats", "mdbcu_event_record", "mdbcu_event_elapsed_ms", "mdbcu_comm_unique_id", "mdbcu_comm_init", "mdbcu_comm_world", "mdbcu_table_sync_stats", "mdbcu_version",
+    "mdbcu_get_stats", "mdbcu_event_record", "mdbcu_event_elapsed_ms", "mdbcu_comm_unique_id", "mdbcu_comm_init", "mdbcu_comm_init_local", "mdbcu_comm_world", "mdbcu_table_sync_stats", "mdbcu_dist_describe", "mdbcu_dist_owner", "mdbcu_version",
 ]
 
 
@@ -74,6 +74,26 @@ class Stats(C.Structure):
                 ("total_kernel_launches", C.c_uint64), ("input_rows", C.c_uint64), ("result_rows", C.c_uint64),
                 ("algorithmic_bytes", C.c_uint64), ("path", C.c_int32), ("_pad", C.c_int32),
                 ("dominant_ms", C.c_double), ("dominant_bytes", C.c_uint64), ("exchange_bytes", C.c_uint64)]
+
+
+class DistLayout(C.Structure):
+    _fields_ = [("part_first", C.c_uint32 * 9), ("stream_cap", C.c_uint32), ("tail_cap", C.c_uint32), ("owned_max", C.c_uint32),
+                ("slot_main_off", C.c_uint64), ("slot_tail_off", C.c_uint64), ("slot_cursor_off", C.c_uint64),
+                ("slot_tail_cursor_off", C.c_uint64), ("slot_bytes", C.c_uint64), ("arena_half_bytes", C.c_uint64)]
+
+
+def dist_describe(nparts, world, global_rows, sms=148):
+    """host-only: ownership and arena slot layout of a distributed radix join (mdbcu_dist_describe)"""
+    L = load_library()
+    out = DistLayout()
+    rc = L.mdbcu_dist_describe(nparts, world, global_rows, sms, C.byref(out))
+    if rc != OK:
+        raise MdbError(rc, "mdbcu_dist_describe: bad arguments")
+    return out
+
+
+def dist_owner(partition, nparts, world):
+    return load_library().mdbcu_dist_owner(partition, nparts, world)
 
 
 class MdbError(RuntimeError):
@@ -139,7 +159,10 @@ def load_library():
     L.mdbcu_event_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, C.POINTER(C.c_double)]
     L.mdbcu_comm_unique_id.argtypes = [vp, vp]
     L.mdbcu_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.mdbcu_comm_init_local.argtypes = [C.POINTER(vp), C.c_int]
     L.mdbcu_comm_world.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.mdbcu_dist_describe.argtypes = [C.c_int, C.c_int, u64, C.c_int, C.POINTER(DistLayout)]
+    L.mdbcu_dist_owner.argtypes = [C.c_uint32, C.c_int, C.c_int]
     L.mdbcu_table_sync_stats.argtypes = [vp]
     L.mdbcu_version.restype = C.c_char_p
     _lib = L
@@ -359,6 +382,7 @@ class Backend:
         if rc != OK:
             raise MdbError(rc, (self.L.mdbcu_last_error(None) or b"").decode())
         self.ctx = h
+        self.device = device
 
     def _check(self, rc):
         if rc != OK:
@@ -425,6 +449,13 @@ class Backend:
     def comm_init(self, rank, world, unique_id):
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         self._check(self.L.mdbcu_comm_init(self.ctx, rank, world, buf))
+
+
+def comm_init_local(backends):
+    """make the given Backends (same process) ranks 0..n-1 of one in-process communicator (loop-back mode when they share a GPU);
+    afterwards every collective must be called by all of them concurrently, one host thread each"""
+    arr = (C.c_void_p * len(backends))(*[b.ctx for b in backends])
+    backends[0]._check(backends[0].L.mdbcu_comm_init_local(arr, len(backends)))
 
 
 def make_plan(tables, joins=(), pred=(), group=(), out=(), flags=0):

@@ -19,6 +19,9 @@
 
 #define MDB_WARP 32
 #define MDB_MAX_RANKS 8 // one node: up to 8 GPUs behind NVSwitch
+// error bits that travel with the cross-rank barrier (4 bits per rank; 1, 2, 4 are the radix join's RJ_ERR_* flags)
+#define MDB_PEER_ABORT 8u   // the rank gave up on the query on the host (allocation failure ...)
+#define MDB_PEER_TIMEOUT 8u // the rank never reached the barrier
 
 struct mdbcu_ctx {
 	int device = 0;
@@ -30,6 +33,7 @@ struct mdbcu_ctx {
 	// multi-GPU
 	int rank = 0, world = 1;
 	void *nccl_comm = nullptr;
+	struct mdb_local_group *local_group = nullptr; // in-process communicator (mdbcu_comm_init_local), see mdb_comm.cu
 	// exchange arena of the multi-GPU radix join: own block + every peer's block mapped with CUDA IPC
 	void *arena_local = nullptr;
 	size_t arena_bytes = 0;
@@ -38,6 +42,7 @@ struct mdbcu_ctx {
 	cudaStream_t side_stream = nullptr; // multi-GPU: the push of one join side runs here while pass 1 of the other side runs
 	cudaEvent_t side_ev[2] = {};
 	uint32_t arena_queries = 0; // distributed queries so far: alternate queries use alternate halves of the arena
+	bool radix_gave_up = false; // the radix join handed the running query back because of its DATA (duplicates, skew)
 	// reusable scratch: pinned host word for small D2H reads
 	uint64_t *h_scalar = nullptr; // pinned, 64 entries
 	uint64_t *d_scalar = nullptr; // device, 64 entries
@@ -336,7 +341,11 @@ int mdb_comm_allgather_bytes(mdbcu_ctx *ctx, const void *send, void *recv, size_
 int mdb_comm_arena(mdbcu_ctx *ctx, size_t bytes, void **bases);
 int mdb_comm_arena_barrier(mdbcu_ctx *ctx, const uint32_t *d_err, uint32_t *d_all);
 void mdb_comm_arena_destroy(mdbcu_ctx *ctx);
+void mdb_comm_arena_abort(mdbcu_ctx *ctx);
 int mdb_comm_allgather_u64(mdbcu_ctx *ctx, const uint64_t *send, uint64_t *recv, size_t count);
+bool mdb_comm_ready(const mdbcu_ctx *ctx);
+int mdb_comm_reduce_owned_u32(mdbcu_ctx *ctx, uint32_t *buf, uint64_t n, int nsides, uint64_t *bytes_sent);
+int mdb_select_direct_count(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res, bool forced);
 
 // phase clock: events are only recorded while the query runs; one synchronise at the end
 struct PhaseClock {

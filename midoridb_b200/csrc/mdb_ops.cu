@@ -1651,6 +1651,14 @@ static int star_source(mdbcu_ctx *ctx, const mdbcu_plan *plan, DevTemp &tmp, Sta
 
 // =========================================================================================== driver
 
+// the fused multiway aggregate (scan of tables[0], direct row tables for the joined tables, WHERE and grouped aggregates
+// in one kernel) is the default for the plans it fits; MDBCU_FUSED_MULTIWAY=0 sends them to the tuple operators instead
+static bool mdb_fused_multiway_enabled()
+{
+	const char *e = getenv("MDBCU_FUSED_MULTIWAY");
+	return !e || atoi(e) != 0;
+}
+
 int mdb_select_general(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res)
 {
 	Tuples ts;
@@ -1660,7 +1668,7 @@ int mdb_select_general(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res
 	HostLap lap; // MDBCU_TRACE=2: host wall time of each operator (includes the stream synchronisations inside it)
 
 	const bool aggregates = plan->n_group > 0 || plan_has_aggregate(plan);
-	if (aggregates && plan->n_joins > 0 && getenv("MDBCU_FUSED_MULTIWAY")) {
+	if (aggregates && plan->n_joins > 0 && mdb_fused_multiway_enabled()) {
 		// opt-in until the whole GPU suite has run with it
 		DevTemp star_tmp(ctx, true);
 		StarSource star;

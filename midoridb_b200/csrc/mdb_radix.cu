@@ -127,7 +127,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 			plan->n_out < 1 || plan->n_out > 4)
 		return MDBCU_EUNSUPPORTED;
 	const bool dist = (plan->flags & MDBCU_PLAN_DISTRIBUTED) != 0;
-	if (dist && !ctx->nccl_comm)
+	if (dist && !mdb_comm_ready(ctx))
 		return mdb_fail(ctx, MDBCU_EERROR, "MDBCU_PLAN_DISTRIBUTED needs mdbcu_comm_init first");
 	const mdbcu_join &jn = plan->joins[0];
 	if (jn.left.tbl != 0 || jn.right.tbl != 1)
@@ -195,6 +195,20 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	DevTemp tmp(ctx);
 	const int grid1 = ctx->num_sms;
 	const int W = dist ? ctx->world : 1, me = dist ? ctx->rank : 0;
+	// Every decision up to here depends on the plan and on GLOBAL statistics only: all ranks of a distributed plan are here
+	// together.  From now on a rank that fails on its own (out of memory ...) must not leave its peers spinning in the
+	// cross-rank barrier: the guard publishes MDB_PEER_ABORT in place of the barrier this rank will not reach.
+	struct AbortGuard {
+		mdbcu_ctx *ctx;
+		bool armed;
+		~AbortGuard()
+		{
+			if (armed)
+				mdb_comm_arena_abort(ctx);
+		}
+	} guard = {ctx, false};
+	const uint32_t arena_query = (dist && W > 1) ? ctx->arena_queries++ : 0u; // (counted before anything can fail: the ranks stay in step)
+	guard.armed = dist && W > 1 && ctx->arena_local != nullptr;
 	RJSide sa, sb;
 	RJParams pr;
 	// stream capacities must be identical on every rank (the arena slots mirror the local layout)
@@ -208,17 +222,19 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	}
 	// control block of the query: ONE allocation, ONE memset, ONE read-back
 	//   bytes  0..15  groups emitted, bytes pushed to peers (u64 each)      16..23  error flags, partition counter (u32 each)
-	//   bytes 32..63  every rank's error flags after the exchange (u32 x 8)  64..     cursors of side A, then of side B
+	//   bytes 32..63  every rank's error flags after the exchange (u32 x 8)  64..95   every rank's error flags after pass 2
+	//   bytes 128..   cursors of side A, then of side B
 	const size_t cursor_words = (size_t)RJ_MAX_PART * RJ_CUR_STRIDE;
+	const size_t ctl_head = 32;
 	uint32_t *ctl;
-	MDB_TRY(tmp.alloc(&ctl, 16 + 2 * cursor_words));
-	CUDA_TRY(ctx, cudaMemsetAsync(ctl, 0, (16 + 2 * cursor_words) * sizeof(uint32_t), ctx->stream));
+	MDB_TRY(tmp.alloc(&ctl, ctl_head + 2 * cursor_words));
+	CUDA_TRY(ctx, cudaMemsetAsync(ctl, 0, (ctl_head + 2 * cursor_words) * sizeof(uint32_t), ctx->stream));
 	memset(&sa, 0, sizeof(sa));
 	memset(&sb, 0, sizeof(sb));
 	if (!sorted_a)
-		MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, nparts, cap_a, ctl + 16));
+		MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, nparts, cap_a, ctl + ctl_head));
 	if (!sorted_b)
-		MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, nparts, cap_b, ctl + 16 + cursor_words));
+		MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, nparts, cap_b, ctl + ctl_head + cursor_words));
 	sa.all_in_range = ca.imin >= kmin && ca.imax <= kmax;
 	sb.all_in_range = cb.imin >= kmin && cb.imax <= kmax;
 	pr.kmin = kmin;
@@ -226,16 +242,17 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	pr.shift = shift;
 	pr.mask = (1u << shift) - 1u;
 	pr.nparts = nparts;
-	pr.part_first = (int)((uint64_t)me * nparts / W);
-	pr.part_end = (int)((uint64_t)(me + 1) * nparts / W);
+	pr.part_first = (int)rj_part_first((uint32_t)me, (uint32_t)nparts, (uint32_t)W);
+	pr.part_end = (int)rj_part_first((uint32_t)me + 1u, (uint32_t)nparts, (uint32_t)W);
 	unsigned long long *d_cursor = reinterpret_cast<unsigned long long*>(ctl); // [0] groups emitted, [1] bytes pushed to peers
 	uint32_t *d_flags = ctl + 4;                                                // [0] error flags, [1] partition counter
 	pr.error_flag = d_flags;
 	pr.peer_flags = nullptr;
 	pr.n_peer_flags = 0;
-	uint32_t *d_peer_flags = nullptr;
+	uint32_t *d_peer_flags = nullptr, *d_peer_flags2 = nullptr;
 	if (dist && W > 1) {
 		d_peer_flags = ctl + 8;
+		d_peer_flags2 = ctl + 16;
 		pr.peer_flags = d_peer_flags;
 		pr.n_peer_flags = W;
 	}
@@ -266,7 +283,8 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		void *bases[MDB_MAX_RANKS];
 		const size_t half_bytes = (la.bytes + lb.bytes) * (size_t)W;
 		MDB_TRY(mdb_comm_arena(ctx, 2 * half_bytes, bases));
-		const size_t half_off = (ctx->arena_queries++ & 1u) ? half_bytes : 0;
+		guard.armed = true; // (the arena exists from here on, if it did not before)
+		const size_t half_off = (arena_query & 1u) ? half_bytes : 0;
 		auto fill = [&](RJShip *sh, RJRuns *r, const RJSlotLayout &l, size_t side_off) {
 			memset(sh, 0, sizeof(*sh));
 			sh->world = W;
@@ -353,6 +371,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		// barrier and stay on the device: pass 2 checks them itself, the host reads them with the result count
 		clock.begin(7);
 		MDB_TRY(mdb_comm_arena_barrier(ctx, d_flags, d_peer_flags));
+		guard.armed = false; // the barrier is in the stream: the peers get this rank's word
 	} else if (!sorted_b) {
 		launch_partition(ctx, grid1, sb, pr);
 	}
@@ -386,13 +405,20 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	const uint64_t rows_a = dist ? ta->global_slots : ta->n_slots, rows_b = dist ? tb->global_slots : tb->n_slots;
 	bool try4 = std::max(rows_a, rows_b) <= 2 * range;
 	uint64_t ngroups = 0;
-	uint32_t flags = 0;
-	for (int attempt = try4 ? 0 : 1; attempt < 2; attempt++) {
-		const int bitsw = attempt == 0 ? 4 : 8;
-		const size_t smem2 = 2 * (size_t)std::max<uint64_t>(1, D * bitsw / 32) * sizeof(uint32_t);
-		const int grid2 = std::max(1, std::min(pr.part_end - pr.part_first, ctx->num_sms * (bitsw == 4 ? 2 : 1)));
-		// result layout known at compile time for the two common shapes: [key, count] and [count, key]
-		const int layout = out.nout != 2 ? 0 : (!out.is_count[0] && out.is_count[1]) ? 1 : (out.is_count[0] && !out.is_count[1]) ? 2 : 0;
+	uint32_t flags = 0, any1 = 0, any2 = 0; // this rank's flags; all ranks' flags after pass 1 / after pass 2
+	const bool multi = d_peer_flags != nullptr;
+	int attempt = try4 ? 0 : 1;
+	bool run = true;
+	// Single GPU: a wrapped 4-bit counter repeats pass 2 once with 8-bit counters.  Several GPUs: every round ends with a
+	// barrier that carries the ranks' pass-2 flags, so that ALL ranks take the same decision (done / one more round for
+	// the ranks whose 4-bit counters wrapped / give the query to the direct-count path, which is a collective).
+	for (int round = 0; round < 2; round++) {
+		if (run) {
+			const int bitsw = attempt == 0 ? 4 : 8;
+			const size_t smem2 = 2 * (size_t)std::max<uint64_t>(1, D * bitsw / 32) * sizeof(uint32_t);
+			const int grid2 = std::max(1, std::min(pr.part_end - pr.part_first, ctx->num_sms * (bitsw == 4 ? 2 : 1)));
+			// result layout known at compile time for the two common shapes: [key, count] and [count, key]
+			const int layout = out.nout != 2 ? 0 : (!out.is_count[0] && out.is_count[1]) ? 1 : (out.is_count[0] && !out.is_count[1]) ? 2 : 0;
 #define RJ_LAUNCH2(B, T, L)                                                                                   \
 	do {                                                                                                  \
 		if (ra.nsrc > 1 || rb.nsrc > 1)                                                               \
@@ -400,53 +426,70 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		else                                                                                          \
 			MDB_LAUNCH(ctx, (k_radix_joincount<B, T, L, false>), grid2, T, smem2, ra, rb, pr, out, d_flags + 1); \
 	} while (0)
-		if (bitsw == 4) {
-			if (layout == 1)
-				RJ_LAUNCH2(4, 512, 1);
-			else if (layout == 2)
-				RJ_LAUNCH2(4, 512, 2);
-			else
-				RJ_LAUNCH2(4, 512, 0);
-		} else {
-			if (layout == 1)
-				RJ_LAUNCH2(8, 1024, 1);
-			else if (layout == 2)
-				RJ_LAUNCH2(8, 1024, 2);
-			else
-				RJ_LAUNCH2(8, 1024, 0);
-		}
+			if (bitsw == 4) {
+				if (layout == 1)
+					RJ_LAUNCH2(4, 512, 1);
+				else if (layout == 2)
+					RJ_LAUNCH2(4, 512, 2);
+				else
+					RJ_LAUNCH2(4, 512, 0);
+			} else {
+				if (layout == 1)
+					RJ_LAUNCH2(8, 1024, 1);
+				else if (layout == 2)
+					RJ_LAUNCH2(8, 1024, 2);
+				else
+					RJ_LAUNCH2(8, 1024, 0);
+			}
 #undef RJ_LAUNCH2
-		cudaError_t e = cudaGetLastError();
-		if (e != cudaSuccess)
-			return mdb_fail(ctx, MDBCU_ECUDA, "radix join launch failed: %s", cudaGetErrorString(e));
-		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar, ctl, 64, cudaMemcpyDeviceToHost, ctx->stream)); // the control block's head
+			cudaError_t e = cudaGetLastError();
+			if (e != cudaSuccess) {
+				guard.armed = multi;
+				return mdb_fail(ctx, MDBCU_ECUDA, "radix join launch failed: %s", cudaGetErrorString(e));
+			}
+		}
+		if (multi) {
+			guard.armed = true;
+			MDB_TRY(mdb_comm_arena_barrier(ctx, d_flags, d_peer_flags2));
+			guard.armed = false;
+		}
+		CUDA_TRY(ctx, cudaMemcpyAsync(ctx->h_scalar, ctl, 128, cudaMemcpyDeviceToHost, ctx->stream)); // the control block's head
 		CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
 		ngroups = ctx->h_scalar[0];
 		flags = (uint32_t)(ctx->h_scalar[2] & 0xffffffffu);
-		if (d_peer_flags) {
-			uint32_t any = 0;
-			for (int r = 0; r < W; r++)
-				any |= reinterpret_cast<const uint32_t*>(ctx->h_scalar + 4)[r];
-			if (any)
-				return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "distributed radix join: pass 1 failed on some rank (flags %u: "
-						"1 = a partition received more than twice its share of the keys, 4 = extreme skew)", any);
+		any1 = any2 = 0;
+		for (int r = 0; multi && r < W; r++) {
+			any1 |= reinterpret_cast<const uint32_t*>(ctx->h_scalar + 4)[r];
+			any2 |= reinterpret_cast<const uint32_t*>(ctx->h_scalar + 8)[r];
 		}
-		if (flags != RJ_ERR_COUNTER || attempt == 1)
+		const uint32_t seen = multi ? any2 : flags;
+		if (any1 || seen != RJ_ERR_COUNTER || !try4 || round == 1)
 			break;
-		// a 4-bit counter wrapped: repeat pass 2 with 8-bit counters (the partitioned remainders are still valid)
-		CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint32_t), ctx->stream));
-		CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
+		// somebody's 4-bit counters wrapped: those ranks repeat pass 2 with 8-bit counters (the partitioned remainders are
+		// still valid), the others only take part in the next barrier
+		run = flags == RJ_ERR_COUNTER;
+		if (run) {
+			attempt = 1;
+			CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, 2 * sizeof(uint32_t), ctx->stream));
+			CUDA_TRY(ctx, cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), ctx->stream));
+		}
 	}
 	clock.finish();
-	if (flags || ngroups > cap_groups) {
+	if (flags || any1 || any2) {
 		if (getenv("MDBCU_TRACE"))
-			fprintf(stderr, "[mdbcu] radix join gives up: flags %u (1 stream full, 2 counter wrapped, 4 skew), groups %llu of %llu\n",
-					flags, (unsigned long long)ngroups, (unsigned long long)cap_groups);
-		if (dist)
-			return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "distributed radix join: key multiplicity or skew beyond the counter width "
-					"(flags %u); the general operators are single-GPU only", flags);
-		return MDBCU_EUNSUPPORTED; // heavy duplicates / skew / stream overflow: the general operators redo the query
+			fprintf(stderr, "[mdbcu] radix join gives up: flags %u, any rank after pass 1 %u, after pass 2 %u (1 stream full, 2 counter "
+					"wrapped, 4 clustered keys, 8 a rank aborted), groups %llu of %llu\n", flags, any1, any2, (unsigned long long)ngroups,
+					(unsigned long long)cap_groups);
+		if ((any1 | any2) & MDB_PEER_ABORT)
+			return mdb_fail(ctx, MDBCU_EERROR, "distributed radix join: a peer rank aborted the query or never reached the barrier");
+		// heavy duplicates / skew / stream overflow: the direct-count path (mdb_direct.cu) answers such inputs exactly; in a
+		// distributed plan every rank is here (the flags travelled with the barriers)
+		ctx->radix_gave_up = true;
+		return MDBCU_EUNSUPPORTED;
 	}
+	if (ngroups > cap_groups)
+		return mdb_fail(ctx, MDBCU_EINTERNAL, "radix join emitted %llu groups into %llu rows", (unsigned long long)ngroups,
+				(unsigned long long)cap_groups);
 	res->nrows = ngroups;
 	ctx->stats.exchange_bytes = ctx->h_scalar[1];
 
@@ -454,4 +497,35 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	ctx->stats.dominant_ms = ctx->stats.phase_ms[1] + ctx->stats.phase_ms[2];
 	ctx->stats.dominant_bytes = ctx->stats.algorithmic_bytes;
 	return MDBCU_OK;
+}
+
+// Host-side description of how a distributed radix join lays its exchange out (no device needed): which partitions every
+// rank owns and where a side's streams sit inside an arena slot.  The numbers come from the functions the kernels and
+// mdb_select_radix_joincount use (rj_part_first / rj_owner_of / rj_stream_cap / rj_slot_layout), so the CPU test of the
+// multi-rank arithmetic (tests/test_dist_cpu.py, world_size 2 over gloo) checks the shipped code, not a copy of it.
+extern "C" int mdbcu_dist_describe(int nparts, int world, uint64_t global_rows, int sms, struct mdbcu_dist_layout *out)
+{
+	if (!out || nparts < 1 || nparts > RJ_MAX_PART || world < 1 || world > RJ_MAX_RANKS || sms < 1)
+		return MDBCU_EERROR;
+	memset(out, 0, sizeof(*out));
+	for (int r = 0; r <= world; r++)
+		out->part_first[r] = rj_part_first((uint32_t)r, (uint32_t)nparts, (uint32_t)world);
+	out->stream_cap = rj_stream_cap((global_rows + world - 1) / world, nparts);
+	out->tail_cap = ((uint32_t)sms * RJ_FLUSH + out->stream_cap / 16 + 15u) & ~15u;
+	out->owned_max = (uint32_t)((nparts + world - 1) / world) + 1;
+	const RJSlotLayout l = rj_slot_layout(out->owned_max, out->stream_cap, out->tail_cap);
+	out->slot_main_off = l.main;
+	out->slot_tail_off = l.tail;
+	out->slot_cursor_off = l.cursor;
+	out->slot_tail_cursor_off = l.tail_cursor;
+	out->slot_bytes = l.bytes;
+	out->arena_half_bytes = 2 * l.bytes * (size_t)world; // both sides, one slot per source rank (equal row counts per side)
+	return MDBCU_OK;
+}
+
+extern "C" int mdbcu_dist_owner(uint32_t partition, int nparts, int world)
+{
+	if (nparts < 1 || world < 1 || partition >= (uint32_t)nparts)
+		return -1;
+	return (int)rj_owner_of(partition, (uint32_t)nparts, (uint32_t)world);
 }

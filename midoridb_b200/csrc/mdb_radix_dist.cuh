@@ -9,13 +9,25 @@
 // with CUDA IPC, mdb_comm.cu) has one slot per source rank; k_radix_ship copies the streams of the partitions a
 // peer owns straight into that peer's slot with 256-bit stores (a warp writes 1 KiB of contiguous remote memory per
 // instruction) together with their entry counts.  What crosses the link is the 2-byte remainders, never the 8-byte keys.
-// Two tiny NCCL all-gathers act as the cross-rank barriers (arena free / pushes landed + error flags).
+// The cross-rank barrier (pushes landed + every rank's error flags) is a flag word per source rank in the arena header
+// (k_arena_barrier, mdb_comm.cu); alternate queries use alternate halves of the arena, so one barrier per exchange suffices.
 //
 // Measured on 2 B200s (profiles/): writing every flushed 32-byte sector directly into the owner's memory from inside
 // pass 1 (the first version of this exchange) ran pass 1 at half speed - remote 32-byte stores are bound by the
 // number of stores in flight, not by the link - and a staged NCCL send/recv of gathered chunks took 2-3 ms;
 // the bulk push below moves the same bytes at link speed after a pass 1 that runs at its single-GPU speed.
 #pragma once
+
+// Partition ownership, the one piece of arithmetic every rank (host and device) must agree on: rank r owns the contiguous
+// block [r * nparts / W, (r + 1) * nparts / W).  Exported for the CPU tests as mdbcu_dist_describe (mdb_radix.cu).
+__host__ __device__ static inline uint32_t rj_part_first(uint32_t rank, uint32_t nparts, uint32_t world)
+{
+	return (uint32_t)((uint64_t)rank * nparts / world);
+}
+__host__ __device__ static inline uint32_t rj_owner_of(uint32_t p, uint32_t nparts, uint32_t world)
+{
+	return (uint32_t)((((uint64_t)p + 1) * world - 1) / nparts);
+}
 
 // byte layout of one side inside an arena slot (identical on every rank)
 struct RJSlotLayout {
@@ -75,10 +87,10 @@ __global__ void __launch_bounds__(1024) k_radix_ship(RJSide s, RJShip sh)
 {
 	const uint32_t warps = blockDim.x >> 5, gw = blockIdx.x * warps + (threadIdx.x >> 5), nw = gridDim.x * warps;
 	for (uint32_t p = gw; p < (uint32_t)sh.nparts; p += nw) {
-		const int o = (int)(((p + 1) * (uint32_t)sh.world - 1u) / (uint32_t)sh.nparts); // owner of p
+		const int o = (int)rj_owner_of(p, (uint32_t)sh.nparts, (uint32_t)sh.world);
 		if (o == sh.self)
 			continue;
-		const uint32_t q = p - (uint32_t)((uint64_t)o * sh.nparts / sh.world);
+		const uint32_t q = p - rj_part_first((uint32_t)o, (uint32_t)sh.nparts, (uint32_t)sh.world);
 		const uint32_t n_main = min(s.cursor[p * RJ_CUR_STRIDE], s.cap), n_tail = min(s.tail_cursor[p * RJ_CUR_STRIDE], s.tail_cap);
 		rj_copy_vectors(reinterpret_cast<char*>(sh.main[o] + (size_t)q * s.cap), reinterpret_cast<const char*>(s.stream + (size_t)p * s.cap),
 				n_main / 16u);

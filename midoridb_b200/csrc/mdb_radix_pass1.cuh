@@ -182,7 +182,11 @@ __device__ __forceinline__ uint32_t rj_insert_items(const RJSide &s, RJP1Smem *s
 		}
 		if (kept != RJ_NONE)
 			kept_at = atomicAdd(&s.tail_cursor[(kept >> 16) * RJ_CUR_STRIDE], (uint32_t)RJ_FLUSH);
-		if (n_over > 1) { // the others (about 700 keys per launch of 2^28) go to the tail right away
+		if (n_over > 4) {
+			// clustered keys (a sorted column: all keys of a tile fall into one or two rows): this launch's result is
+			// abandoned, do not write millions of single-key tail sectors on the way out
+			atomicOr(pr.error_flag, RJ_ERR_SKEW);
+		} else if (n_over > 1) { // the others (about 700 keys per launch of 2^28) go to the tail right away
 			bool last = true;
 #pragma unroll
 			for (int k = RJ_P1_KEYS - 1; k >= 0; k--) {

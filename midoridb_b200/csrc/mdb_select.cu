@@ -69,7 +69,17 @@ extern "C" int mdbcu_select(mdbcu_ctx *ctx, const struct mdbcu_plan *plan, mdbcu
 		rc = mdb_select_scan_agg(ctx, plan, res);
 		if (rc == MDBCU_EUNSUPPORTED) {
 			release_result_buffers(res);
+			ctx->radix_gave_up = false;
 			rc = mdb_select_radix_joincount(ctx, plan, res);
+			if (rc == MDBCU_EUNSUPPORTED) {
+				// same plan shape, any key multiplicity / skew / order: one counter per key value (also the distributed answer)
+				release_result_buffers(res);
+				const bool forced = ctx->radix_gave_up;
+				uint64_t keep_rows = ctx->stats.input_rows;
+				memset(&ctx->stats, 0, sizeof(ctx->stats));
+				ctx->stats.input_rows = keep_rows;
+				rc = mdb_select_direct_count(ctx, plan, res, forced);
+			}
 		}
 		if (rc == MDBCU_EUNSUPPORTED) {
 			release_result_buffers(res);
@@ -78,7 +88,8 @@ extern "C" int mdbcu_select(mdbcu_ctx *ctx, const struct mdbcu_plan *plan, mdbcu
 	}
 	if (rc == MDBCU_EUNSUPPORTED) {
 		if (plan->flags & MDBCU_PLAN_DISTRIBUTED) {
-			rc = mdb_fail(ctx, MDBCU_EUNSUPPORTED, "distributed plans are only implemented for the radix join+count path");
+			rc = mdb_fail(ctx, MDBCU_EUNSUPPORTED, "this plan shape has no distributed implementation (join + GROUP BY join key + "
+					"COUNT(*), filter + aggregate scans and small-dimension star joins have)");
 		} else {
 			release_result_buffers(res);
 			uint64_t keep_rows = ctx->stats.input_rows;

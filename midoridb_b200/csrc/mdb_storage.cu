@@ -961,7 +961,7 @@ extern "C" int mdbcu_table_sync_stats(mdbcu_table *tt)
 	mdbcu_ctx *ctx = t->ctx;
 	cudaSetDevice(ctx->device);
 	const int W = ctx->world;
-	if (W == 1 && !ctx->nccl_comm) {
+	if (W == 1 && !mdb_comm_ready(ctx)) {
 		for (auto &c : t->cols) {
 			c.gstats_ok = c.stats_ok;
 			c.gmin = c.imin;

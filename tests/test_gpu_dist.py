@@ -1,17 +1,118 @@
-"""GPU tests (-m gpu) of the multi-GPU code path on ONE device: a world of size 1 takes the distributed plan's
-decisions (global statistics mandatory, ownership of all partitions, no peer to push to), so its result must equal
-the single-GPU path and the oracle.
-Real 2/4/8-GPU runs use tests/dist_check.py under torchrun (gpurun --gpus N)."""
+"""GPU tests (-m gpu) of the multi-GPU code path.
+
+* world of one: a distributed plan's decisions with nobody to exchange with;
+* LOOP-BACK: W ranks = W contexts of this process on ONE device (mdbcu_comm_init_local), one host thread
+  per rank - k_radix_ship, k_arena_barrier, the multi-source pass 2 and the owner reduction of the direct-count path are
+  the kernels a real multi-GPU run uses, so the single-GPU box exercises them;
+* the same with one context per device when the box has W GPUs (peer stores over NVLink), and the one-process-per-GPU
+  NCCL / CUDA-IPC variant under torchrun (tests/dist_check.py); both skip themselves on smaller boxes.
+Every case is checked against the CPU oracle on the whole (unsharded) tables."""
+import os
+import socket
+import subprocess
+import sys
+import threading
+
 import numpy as np
 import pytest
 
 from midoridb_b200 import capi
-from midoridb_b200.capi import CT_INTEGER, OUT_COLUMN, OUT_COUNT_STAR, PLAN_DISTRIBUTED
+from midoridb_b200.capi import CT_DOUBLE, CT_INTEGER, OUT_COLUMN, OUT_COUNT_STAR, OUT_MAX, OUT_MIN, OUT_SUM, PLAN_DISTRIBUTED
 from oracle import oracle
 from tests import helpers
 
 pytestmark = pytest.mark.gpu
-I = CT_INTEGER
+I, D = CT_INTEGER, CT_DOUBLE
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+JOIN = dict(joins=[((0, 0), (1, 0))], group=[(0, 0)], out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)])
+
+
+def gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def run_ranks(devices, body):
+    """body(rank, backend) on one thread per rank; the backends form one in-process communicator.  Returns the list of results."""
+    bes = [capi.Backend(d) for d in devices]
+    capi.comm_init_local(bes)
+    out, err = [None] * len(bes), [None] * len(bes)
+
+    def work(r):
+        try:
+            out[r] = body(r, bes[r])
+        except BaseException as e:  # noqa: BLE001 - reported below, per rank
+            err[r] = e
+
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(len(bes))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(timeout=300)
+    alive = [t.is_alive() for t in ts]
+    for b in bes:
+        if not any(alive):
+            b.close()
+    assert not any(alive), "a rank hung"
+    for r, e in enumerate(err):
+        if e is not None:
+            raise AssertionError("rank %d: %r" % (r, e))
+    return out
+
+
+def sharded_join(devices, specs_a, specs_b, n_total, check_path=None):
+    """README query on tables generated shard by shard (rank r: rows [r n / W, (r + 1) n / W)); returns per-rank
+    (keys, counts, stats path, exchange bytes, column A, valid A, column B, valid B)"""
+    W = len(devices)
+    n_local = n_total // W
+
+    def body(rank, be):
+        ta, tb = be.create_table("A", [I]), be.create_table("B", [I])
+        ta.generate(n_local, specs_a, row_offset=rank * n_local)
+        tb.generate(n_local, specs_b, row_offset=rank * n_local)
+        ta.sync_stats()
+        tb.sync_stats()
+        res = be.select(capi.make_plan([ta, tb], flags=PLAN_DISTRIBUTED, **JOIN))
+        st = be.stats()
+        (keys, cnts), _ = res.fetch_columns()
+        res.free()
+        a, av = ta.read_column(0)
+        b, bv = tb.read_column(0)
+        ta.drop()
+        tb.drop()
+        return keys, cnts, st.path, st.exchange_bytes, a, av, b, bv
+
+    return run_ranks(devices, body)
+
+
+def check_against_oracle(parts, histogram=False):
+    """histogram: the expected result from numpy histograms instead of the oracle, whose hash join visits every joined pair
+    (3 * 10^10 of them when both sides are Zipf-distributed)"""
+    ga = np.concatenate([p[4] for p in parts])
+    gav = np.concatenate([p[5] for p in parts])
+    gb = np.concatenate([p[6] for p in parts])
+    gbv = np.concatenate([p[7] for p in parts])
+    if histogram:
+        lo = int(min(ga.min(), gb.min()))
+        size = int(max(ga.max(), gb.max())) - lo + 1
+        prod = np.bincount(ga[gav != 0] - lo, minlength=size) * np.bincount(gb[gbv != 0] - lo, minlength=size)
+        nz = np.nonzero(prod)[0]
+        want = sorted(zip((nz + lo).tolist(), prod[nz].tolist()))
+    else:
+        oa, ob = oracle.OracleTable([I]), oracle.OracleTable([I])
+        oa.append_columns([ga], [(gav == 0).astype(np.uint8)])
+        ob.append_columns([gb], [(gbv == 0).astype(np.uint8)])
+        _, cells, _ = oracle.select(capi.make_plan([oa, ob], **JOIN))
+        want = sorted(zip(cells[0].tolist(), cells[1].tolist()))
+    got = sorted(zip(np.concatenate([p[0] for p in parts]).tolist(), np.concatenate([p[1] for p in parts]).tolist()))
+    assert got == want, "distributed result differs from the oracle (%d vs %d groups)" % (len(got), len(want))
+    # the ranks own disjoint, ascending key ranges: the per-rank results concatenate without a merge
+    last = None
+    for p in parts:
+        if p[0].size:
+            assert last is None or last < p[0].min()
+            last = p[0].max()
+    return len(want)
 
 
 def test_distributed_world_of_one_matches_oracle():
@@ -25,24 +126,89 @@ def test_distributed_world_of_one_matches_oracle():
         ta, tb = be.create_table("A", [I]), be.create_table("B", [I])
         ta.append_columns([a], [an])
         tb.append_columns([b])
-        kw = dict(joins=[((0, 0), (1, 0))], group=[(0, 0)], out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)])
         with pytest.raises(capi.MdbError):  # global statistics are mandatory for distributed plans
-            be.select(capi.make_plan([ta, tb], flags=PLAN_DISTRIBUTED, **kw))
+            be.select(capi.make_plan([ta, tb], flags=PLAN_DISTRIBUTED, **JOIN))
         ta.sync_stats()
         tb.sync_stats()
-        res = be.select(capi.make_plan([ta, tb], flags=PLAN_DISTRIBUTED, **kw))
+        res = be.select(capi.make_plan([ta, tb], flags=PLAN_DISTRIBUTED, **JOIN))
         st = be.stats()
         got = res.rows()
         res.free()
         assert st.path == capi.PATH_RADIX_JOINCOUNT
         assert st.exchange_bytes == 0  # everything "sent" to itself
-        res = be.select(capi.make_plan([ta, tb], **kw))
+        res = be.select(capi.make_plan([ta, tb], **JOIN))
         single = res.rows()
         res.free()
     oa, ob = oracle.OracleTable([I]), oracle.OracleTable([I])
     oa.append_columns([a], [an])
     ob.append_columns([b])
-    _, cells, nulls = oracle.select(capi.make_plan([oa, ob], **kw))
+    _, cells, nulls = oracle.select(capi.make_plan([oa, ob], **JOIN))
     want = oracle.rows_of(cells, nulls)
     assert helpers.canon(got) == helpers.canon(want)
     assert helpers.canon(single) == helpers.canon(want)
+
+
+def uniform_specs(n):
+    return ([capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=n - 1, seed=11, null_permille=20)],
+            [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=100, hi=n + 4000, seed=12)])
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_loopback_radix_exchange(world):
+    """W virtual ranks on device 0: pass 1 per shard, k_radix_ship into the peers' arena slots, k_arena_barrier, pass 2 over
+    W sources per partition.  Run twice so that both halves of the arena are used."""
+    n = 1 << 22
+    sa, sb = uniform_specs(n)
+    for _ in range(2):
+        parts = sharded_join([0] * world, sa, sb, n)
+        assert all(p[2] == capi.PATH_RADIX_JOINCOUNT for p in parts)
+        assert all(p[3] > 0 for p in parts)  # every rank pushed something to its peers
+        assert check_against_oracle(parts) > 1000
+
+
+@pytest.mark.parametrize("keys", ["zipf", "sorted", "heavy"])
+def test_loopback_skewed_and_sorted_shards(keys):
+    """what pass 1 cannot take - Zipf(1.1) keys, the reference README's auto-increment ids, one key with 5000 rows - in a
+    DISTRIBUTED plan: every rank learns of the failure through the barrier flags and all of them answer with the
+    direct-count path (owner reduction of the counters), exactly"""
+    n = 1 << 20
+    if keys == "zipf":
+        sa = [capi.GenSpec(kind=capi.GEN_ZIPF, lo=0, hi=(1 << 16) - 1, param=1.1, seed=21)]
+        sb = [capi.GenSpec(kind=capi.GEN_ZIPF, lo=0, hi=(1 << 16) - 1, param=1.1, seed=22)]
+    elif keys == "sorted":
+        sa = [capi.GenSpec(kind=capi.GEN_SEQUENCE, lo=1)]
+        sb = [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=n - 1, seed=23)]
+    else:
+        sa = [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=255, seed=24)]  # 4096 rows per key: 8-bit counters wrap
+        sb = [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=n - 1, seed=25)]
+    parts = sharded_join([0, 0], sa, sb, n)
+    assert all(p[2] == capi.PATH_DIRECT_COUNT for p in parts), [p[2] for p in parts]
+    check_against_oracle(parts, histogram=True)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_in_process_multi_gpu_exchange(world):
+    """one context per GPU in one process: the same exchange over real peer memory (NVLink)"""
+    if gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    n = 1 << 24
+    sa, sb = uniform_specs(n)
+    parts = sharded_join(list(range(world)), sa, sb, n)
+    assert all(p[2] == capi.PATH_RADIX_JOINCOUNT for p in parts)
+    check_against_oracle(parts)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_torchrun_nccl_ipc_exchange(world):
+    """one PROCESS per GPU (torchrun): NCCL rendezvous, arenas mapped with CUDA IPC - tests/dist_check.py"""
+    if gpu_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check.py"), "--log2-rows", "22"]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+    out = p.stdout.decode()
+    assert p.returncode == 0 and "DIST_CHECK OK world=%d" % world in out, out[-3000:]

@@ -250,7 +250,7 @@ def test_radix_joincount_fastpath(be, shape):
 def test_radix_joincount_ordered_keys(be, order):
     """auto-increment style ids (all keys of a tile fall into one or two partitions).  A sorted side without NULLs skips
     pass 1 and is counted straight from the column; with NULLs it is not eligible and, after the skew flag of pass 1,
-    the general operators answer.  Either way the result equals the oracle's"""
+    the direct-count path answers.  Either way the result equals the oracle's"""
     rng = np.random.default_rng(43)
     n = 1 << 20
     an = None
@@ -273,7 +273,7 @@ def test_radix_joincount_ordered_keys(be, order):
     grows, orows, _, st = run_both(be, [ga, gb], [oa, ob], joins=[((0, 0), (1, 0))], group=[(0, 0)],
                                    out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)])
     if order in ("sorted_with_nulls", "descending"):
-        assert st.path in (capi.PATH_RADIX_JOINCOUNT, capi.PATH_GENERAL)
+        assert st.path in (capi.PATH_RADIX_JOINCOUNT, capi.PATH_DIRECT_COUNT)
     else:
         assert st.path == capi.PATH_RADIX_JOINCOUNT
     assert helpers.canon(grows) == helpers.canon(orows)
@@ -289,7 +289,8 @@ def test_radix_joincount_ordered_keys(be, order):
 
 
 def test_radix_joincount_heavy_key_falls_back(be):
-    """more than 255 equal keys wrap a byte counter: detected by the checksum, redone by the general operators"""
+    """more than 255 equal keys wrap a byte counter: detected by the checksum, redone by the direct-count path (one 32-bit
+    counter per key value; no joined pair is materialised there either)"""
     rng = np.random.default_rng(41)
     n = 1 << 20
     a = rng.integers(0, 1 << 20, n)
@@ -300,7 +301,7 @@ def test_radix_joincount_heavy_key_falls_back(be):
     gb, ob = both_tables(be, [I], [b])
     grows, orows, _, st = run_both(be, [ga, gb], [oa, ob], joins=[((0, 0), (1, 0))], group=[(0, 0)],
                                    out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)])
-    assert st.path == capi.PATH_GENERAL
+    assert st.path == capi.PATH_DIRECT_COUNT
     assert helpers.canon(grows) == helpers.canon(orows)
     for t in (ga, gb):
         t.drop()
@@ -474,7 +475,7 @@ def test_join_with_unique_build_side(be, shape):
 
 @pytest.mark.parametrize("shape", ["all_match", "some_miss", "none_match", "null_keys", "snowflake", "tombstones", "wide_keys", "dups"])
 def test_fused_multiway_aggregate(be, shape, monkeypatch):
-    """opt-in path (MDBCU_FUSED_MULTIWAY=1): joins against duplicate-free narrow INT keys + WHERE + aggregates in one kernel
+    """default path for star / snowflake aggregates (MDBCU_FUSED_MULTIWAY=0 disables it): joins against duplicate-free narrow INT keys + WHERE + aggregates in one kernel
     over tables[0], no tuple arrays. Same answers as the oracle; plans outside the shape fall through to the general operators."""
     monkeypatch.setenv("MDBCU_FUSED_MULTIWAY", "1")
     rng = np.random.default_rng(131)
@@ -535,3 +536,96 @@ def test_fused_multiway_aggregate(be, shape, monkeypatch):
     assert [helpers.norm_row(r) for r in grows] == [helpers.norm_row(r) for r in orows]
     for t in (gf, gd, ge):
         t.drop()
+
+
+def zipf_keys(rng, n, domain, s=1.1):
+    """Zipf(s) over [0, domain): rank r has weight 1 / (r + 1)^s (BASELINE configs[3])"""
+    w = 1.0 / np.arange(1, domain + 1) ** s
+    return rng.choice(domain, size=n, p=w / w.sum()).astype(np.int64)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+def test_zipf_three_way_join_group_cache(be, fused, monkeypatch):
+    """config 4 shape at test scale: Zipf(1.1) foreign keys (12 % of the rows in one group: the per-CTA cache of hot groups
+    and the global accumulators both get traffic), two unique dimensions, WHERE on fact and dimension, SUM / AVG / COUNT.
+    General operators and the fused multiway kernel against the oracle: keys and counts exact, DOUBLE SUM / AVG 1e-9."""
+    monkeypatch.setenv("MDBCU_FUSED_MULTIWAY", "1" if fused else "0")
+    rng = np.random.default_rng(404)
+    n, nd = 1 << 18, 1 << 13
+    a_id = zipf_keys(rng, n, nd)
+    assert np.bincount(a_id).max() > n // 20  # the hot group really is hot
+    x = rng.random(n)
+    ga, oa = both_tables(be, [I, D], [a_id, x])
+    gb, ob = both_tables(be, [I, I], [rng.permutation(nd).astype(np.int64), rng.integers(0, 1000, nd)])
+    gc, oc = both_tables(be, [I, I], [rng.permutation(nd).astype(np.int64), rng.integers(0, 50, nd)])
+    kw = dict(joins=[((0, 0), (1, 0)), ((0, 0), (2, 0))],
+              pred=[("col", 0, 1), ("dbl", 0.25), ("cmp", 6), ("col", 1, 1), ("int", 500), ("cmp", 1), ("and",)],
+              group=[(0, 0)], out=[(OUT_COLUMN, 0, 0), (OUT_SUM, 0, 1), (OUT_AVG, 2, 1), (OUT_COUNT_STAR,)])
+    grows, orows, _, st = run_both(be, [ga, gb, gc], [oa, ob, oc], **kw)
+    assert st.path == (capi.PATH_FUSED_MULTIWAY if fused else capi.PATH_GENERAL)
+    assert len(orows) > 1000
+    assert helpers.canon_close(grows, orows, rel=1e-9)
+    # keys and counts are bit-exact
+    assert sorted((r[0], r[3]) for r in grows) == sorted((r[0], r[3]) for r in orows)
+    # Zipf keys on BOTH sides of the README query: heavy duplicates, the radix path must hand over or answer exactly
+    # (numpy histograms are the check: the oracle's hash join would visit every one of the 3 * 10^10 joined pairs)
+    za, zb = zipf_keys(rng, 1 << 20, 1 << 16), zipf_keys(rng, 1 << 20, 1 << 16)
+    gz, gy = be.create_table("z", [I]), be.create_table("y", [I])
+    gz.append_columns([za])
+    gy.append_columns([zb])
+    res = be.select(capi.make_plan([gz, gy], joins=[((0, 0), (1, 0))], group=[(0, 0)], out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)]))
+    assert be.stats().path == capi.PATH_DIRECT_COUNT  # no joined pair is materialised
+    (keys, cnts), _ = res.fetch_columns()
+    res.free()
+    prod = np.bincount(za, minlength=1 << 16) * np.bincount(zb, minlength=1 << 16)
+    assert np.array_equal(prod[keys], cnts) and keys.size == np.count_nonzero(prod) == np.unique(keys).size
+    assert int(cnts.sum()) > 1 << 32
+    for t in (ga, gb, gc, gz, gy):
+        t.drop()
+
+
+def test_scan_aggregate_double_sum_2p24(be):
+    """the 1e-9 claim for DOUBLE SUM / AVG at 2^24 rows (the block partials are folded in a fixed order): against the
+    oracle's sequential sum and against numpy's pairwise sum; COUNT / MIN / MAX bit-exact"""
+    rng = np.random.default_rng(2024)
+    n = 1 << 24
+    k = rng.integers(0, 2**31, n)
+    v = rng.random(n) * 1e6 - 3e5  # mixed signs: cancellation makes the tolerance meaningful
+    g, o = both_tables(be, [I, D], [k, v])
+    lo, hi = 2**29, 3 * 2**29 - 1
+    pred = [("col", 0, 0), ("int", lo), ("cmp", 6), ("col", 0, 0), ("int", hi), ("cmp", 5), ("and",)]
+    out = [(OUT_COUNT_STAR,), (OUT_SUM, 0, 1), (OUT_AVG, 0, 1), (OUT_MIN, 0, 1), (OUT_MAX, 0, 1)]
+    grows, orows, _, st = run_both(be, [g], [o], pred=pred, out=out)
+    assert st.path == capi.PATH_SCAN_AGG
+    assert helpers.rows_close(grows, [helpers.norm_row(r) for r in orows], rel=1e-9)
+    m = (k >= lo) & (k <= hi)
+    want_sum = float(np.sum(v[m]))
+    assert grows[0][0] == int(m.sum())
+    assert abs(grows[0][1] - want_sum) <= 1e-9 * abs(want_sum)
+    assert grows[0][3] == float(v[m].min()) and grows[0][4] == float(v[m].max())
+    # two runs give the same bits (deterministic reduction order)
+    g2, _, _, _ = run_both(be, [g], [o], pred=pred, out=out)
+    assert g2 == grows
+    g.drop()
+
+
+@pytest.mark.parametrize("log2_rows", [24, 26])
+def test_radix_joincount_large_against_numpy(be, log2_rows):
+    """README query at 2^24 and 2^26 rows per side, generated on the device: every (key, count) row against numpy histograms of
+    the mirrored columns (independent of the library and of the oracle), all keys accounted for"""
+    n = 1 << log2_rows
+    ta, tb = be.create_table("A", [I]), be.create_table("B", [I])
+    ta.generate(n, [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=n - 1, seed=31)])
+    tb.generate(n, [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=n - 1, seed=32)])
+    res = be.select(capi.make_plan([ta, tb], joins=[((0, 0), (1, 0))], group=[(0, 0)], out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)]))
+    assert be.stats().path == capi.PATH_RADIX_JOINCOUNT
+    (keys, cnts), _ = res.fetch_columns()
+    res.free()
+    a, _ = ta.read_column(0)
+    b, _ = tb.read_column(0)
+    expect = np.bincount(a, minlength=n) * np.bincount(b, minlength=n)
+    assert np.array_equal(expect[keys], cnts) and cnts.min() >= 1
+    assert np.unique(keys).size == keys.size == np.count_nonzero(expect)
+    assert int(cnts.sum()) == int(expect.sum())  # = the join's cardinality
+    ta.drop()
+    tb.drop()
