@@ -441,12 +441,32 @@ class Backend:
         self._check(self.L.mdbcu_event_elapsed_ms(self.ctx, a, b, C.byref(ms)))
         return ms.value
 
+    @staticmethod
+    def _prefer_bundled_nccl():
+        """a process that imports torch later must find the NCCL build torch was linked against, not the system one: load
+        the wheel's copy first (and tell the library where it is) when it exists"""
+        if os.environ.get("MDBCU_NCCL_LIB"):
+            return
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for base in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            path = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(path):
+                os.environ["MDBCU_NCCL_LIB"] = path
+                try:
+                    C.CDLL(path, mode=C.RTLD_GLOBAL)
+                except OSError:
+                    del os.environ["MDBCU_NCCL_LIB"]
+                return
+
     def comm_unique_id(self):
+        self._prefer_bundled_nccl()
         buf = (C.c_ubyte * 128)()
         self._check(self.L.mdbcu_comm_unique_id(self.ctx, buf))
         return bytes(buf)
 
     def comm_init(self, rank, world, unique_id):
+        self._prefer_bundled_nccl()
         buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
         self._check(self.L.mdbcu_comm_init(self.ctx, rank, world, buf))
 

@@ -49,10 +49,14 @@ static int load_nccl(mdbcu_ctx *ctx)
 {
 	if (g_nccl.handle)
 		return MDBCU_OK;
-	const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
-	void *h = nullptr;
-	for (int i = 0; names[i] && !h; i++)
-		h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+	// Order: an explicit path (MDBCU_NCCL_LIB; the Python binding points it at the NCCL wheel torch links against), a copy
+	// the process has loaded already (torch's), then the system library.  One process must not end up with two different
+	// NCCL builds behind the same SONAME: whoever loads second gets the first one's symbols.
+	const char *names[] = {getenv("MDBCU_NCCL_LIB"), "libnccl.so.2", "libnccl.so", nullptr};
+	void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+	for (int i = 0; i < 3 && !h; i++)
+		if (names[i] && names[i][0])
+			h = dlopen(names[i], RTLD_NOW | RTLD_LOCAL);
 	if (!h)
 		return mdb_fail(ctx, MDBCU_ECUDA, "cannot load libnccl.so.2: %s", dlerror());
 #define SYM(field, name)                                                                          \
@@ -154,6 +158,22 @@ extern "C" int mdbcu_comm_init_local(mdbcu_ctx *const *ctxs, int world)
 						cudaGetErrorString(e));
 			}
 			cudaGetLastError();
+			// query temporaries come from the stream-ordered pool, which peers cannot touch unless told so
+			// (the all-gather and the owner reduction read them through peer pointers)
+			cudaMemPool_t pool;
+			if (cudaDeviceGetDefaultMemPool(&pool, ctxs[r]->device) == cudaSuccess) {
+				cudaMemAccessDesc desc;
+				memset(&desc, 0, sizeof(desc));
+				desc.location.type = cudaMemLocationTypeDevice;
+				desc.location.id = ctxs[o]->device;
+				desc.flags = cudaMemAccessFlagsProtReadWrite;
+				e = cudaMemPoolSetAccess(pool, &desc, 1);
+				if (e != cudaSuccess) {
+					delete g;
+					return mdb_fail(ctxs[r], MDBCU_ECUDA, "cannot open GPU %d's memory pool to GPU %d: %s", ctxs[r]->device,
+							ctxs[o]->device, cudaGetErrorString(e));
+				}
+			}
 		}
 	}
 	for (int r = 0; r < world; r++) {

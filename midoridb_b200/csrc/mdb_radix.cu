@@ -6,7 +6,7 @@
 // result(k) = cntA[k] * cntB[k]; no candidate pair and no joined row is ever materialised.
 //
 //   pass 1  k_radix_partition   streams the 8-byte keys ONCE and appends 2-byte remainders to per-partition
-//                               streams (partition = high bits of key - kmin, <= 4096 partitions);
+//                               streams (partition = (key - kmin) / width, <= 4096 partitions of <= 65536 key values);
 //   (ship)  k_radix_ship        multi-GPU plans only: push the streams of the partitions a peer owns over NVLink;
 //   pass 2  k_radix_joincount   per partition: both sides' remainders -> packed 4- or 8-bit counters in shared
 //                               memory, checksum against the number of remainders, multiply, emit groups.
@@ -184,11 +184,9 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 			range = urange;
 		}
 	}
-	int bits = 0;
-	while ((1ull << bits) < range)
-		bits++;
-	int shift = std::max(0, bits - 12);
-	int nparts = (int)((range + (1ull << shift) - 1) >> shift);
+	// partitions of `width` consecutive key values (mdb_radix_types.cuh): all 4096 staging rows are used whatever the range
+	const uint32_t width = (uint32_t)std::max<unsigned long long>(2, (range + RJ_MAX_PART - 1) / RJ_MAX_PART);
+	const int nparts = (int)((range + width - 1) / width);
 
 	ctx->stats.path = MDBCU_PATH_RADIX_JOINCOUNT;
 	PhaseClock clock(ctx);
@@ -239,8 +237,8 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	sb.all_in_range = cb.imin >= kmin && cb.imax <= kmax;
 	pr.kmin = kmin;
 	pr.range = range;
-	pr.shift = shift;
-	pr.mask = (1u << shift) - 1u;
+	pr.width = width;
+	pr.magic = (uint32_t)((1ull << 32) / width);
 	pr.nparts = nparts;
 	pr.part_first = (int)rj_part_first((uint32_t)me, (uint32_t)nparts, (uint32_t)W);
 	pr.part_end = (int)rj_part_first((uint32_t)me + 1u, (uint32_t)nparts, (uint32_t)W);
@@ -378,7 +376,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	// (result columns are allocated here, after pass 1 is on its way, so that the GPU starts the query's first kernel as
 	// early as the host allows)
 	// upper bound of groups this rank can emit: one per key of the partitions it owns
-	uint64_t cap_groups = std::min<uint64_t>((uint64_t)(pr.part_end - pr.part_first) << shift, range);
+	uint64_t cap_groups = std::min<uint64_t>((uint64_t)(pr.part_end - pr.part_first) * width, range);
 	if (!dist)
 		cap_groups = std::min<uint64_t>(cap_groups, std::min<uint64_t>(ta->n_slots, tb->n_slots));
 	MDB_TRY(mdb_result_alloc(ctx, plan, res, 0, false));
@@ -401,7 +399,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 
 	// 4-bit counters (two CTAs per SM) when keys are mostly unique per side, 8-bit otherwise; a wrapped
 	// counter is detected by the checksum and the pass is repeated one width up before giving up
-	const uint64_t D = 1ull << shift;
+	const uint64_t D = ((uint64_t)width + 7) & ~7ull; // counters per side (whole 32-bit words of 4-bit fields)
 	const uint64_t rows_a = dist ? ta->global_slots : ta->n_slots, rows_b = dist ? tb->global_slots : tb->n_slots;
 	bool try4 = std::max(rows_a, rows_b) <= 2 * range;
 	uint64_t ngroups = 0;

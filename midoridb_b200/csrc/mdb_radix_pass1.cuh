@@ -2,7 +2,7 @@
 // per-partition streams (mdb_radix_types.cuh).  Included by mdb_radix.cu.
 //
 // One persistent 1024-thread CTA per SM.  Per round every thread takes 8 keys:
-//   insert   partition = (key - kmin) >> shift; ONE shared-memory atomic hands out a slot of the partition's
+//   insert   partition = (key - kmin) / width; ONE shared-memory atomic hands out a slot of the partition's
 //            40-byte staging row, ONE 2-byte shared store writes the remainder - nothing else per key.  A key that
 //            finds its row full (about 7 of 8192 per round) stays in its thread's register until the flush;
 //   barrier  (all remainders handed out this round are in shared memory)
@@ -110,6 +110,16 @@ __device__ __forceinline__ void rj_load_keys256(const void *p, uint32_t *lo, boo
 	lo[3] = t[6];
 }
 
+// d = key - kmin (< range <= 2^28) -> (partition << 16 | remainder).  q = __umulhi(d, floor(2^32 / width)) is d / width or
+// one less (d * magic / 2^32 > d / width - 1 because d < 2^32); one compare fixes it.  Exact for every width, and for a
+// power of two the correction never fires.  The remainder is the low half: STS.U16 stores it without masking.
+__device__ __forceinline__ uint32_t rj_pack(const RJParams &pr, uint32_t d)
+{
+	uint32_t q = __umulhi(d, pr.magic);
+	q += (d - q * pr.width >= pr.width) ? 1u : 0u;
+	return d + q * (65536u - pr.width); // = (q << 16) + (d - q * width)
+}
+
 // a single remainder as a tail sector of its own: [remainder, 14 unused, count = 1] (mdb_radix_types.cuh)
 // (out of line: cold, and the unrolled insert loop that calls it exists twice per kernel)
 __device__ __forceinline__ void rj_tail_single(uint32_t *tail_cursor, uint16_t *tail, uint32_t tail_cap, uint32_t *error_flag, uint32_t p, uint32_t rem)
@@ -137,8 +147,8 @@ __device__ __forceinline__ void rj_insert_one(const RJSide &s, RJP1Smem *sm, con
 		rj_tail_single(s.tail_cursor, s.tail, s.tail_cap, pr.error_flag, p, item & 0xffffu);
 }
 
-// 8 keys per thread.  PACKED: item = (partition << 16 | remainder), RJ_NONE = no key (generic kernel);
-// otherwise item = key - kmin and every item is a key (lean kernel).
+// 8 keys per thread, item = (partition << 16 | remainder) (rj_pack); ALL_VALID: every item is a key (lean kernel),
+// otherwise RJ_NONE = no key (generic kernel).
 // All slot requests of a thread are issued back to back (independent shared-memory atomics), then consumed.
 // Returns RJ_NONE, or (partition << 16 | remainder) of a key of THIS THREAD that found its row full (7 keys in 8192 do):
 // it stays in a register until the flush, which turns it into a tail sector.  Nothing warp-wide and no shared memory
@@ -147,26 +157,24 @@ __device__ __forceinline__ void rj_insert_one(const RJSide &s, RJP1Smem *sm, con
 // profiles/r02_lab3_*.txt).  A thread's second overflow in one round (about once per launch) goes to the tail directly.
 // kept_at: the key's position in its partition's tail stream - the global atomic is ISSUED here and its result is first
 // looked at after the flush, a thousand cycles later, so nobody ever waits for it.
-template <bool PACKED>
+template <bool ALL_VALID>
 __device__ __forceinline__ uint32_t rj_insert_items(const RJSide &s, RJP1Smem *sm, const RJParams &pr, const uint32_t *item, uint32_t half,
 		uint32_t &kept_at)
 {
-	constexpr bool ALL_MINE = !PACKED && RJ_SPLIT == 1; // every item is a key of a partition this CTA stages
-	const int pshift = PACKED ? 16 : pr.shift;
-	const uint32_t rmask = PACKED ? 0xffffu : pr.mask;
+	constexpr bool ALL_MINE = ALL_VALID && RJ_SPLIT == 1; // every item is a key of a partition this CTA stages
 	uint32_t pos[RJ_P1_KEYS];
 #pragma unroll
 	for (int k = 0; k < RJ_P1_KEYS; k++) {
-		const uint32_t p = item[k] >> pshift;
-		const bool mine = (!PACKED || item[k] != RJ_NONE) && (RJ_SPLIT == 1 || p % RJ_SPLIT == half);
+		const uint32_t p = item[k] >> 16;
+		const bool mine = (ALL_VALID || item[k] != RJ_NONE) && (RJ_SPLIT == 1 || p % RJ_SPLIT == half);
 		pos[k] = mine ? rj_fill_claim(sm, p / RJ_SPLIT) : RJ_NONE;
 	}
 	uint32_t worst = 0; // largest slot handed to this thread (+1 unless ALL_MINE, so that RJ_NONE counts as 0)
 #pragma unroll
 	for (int k = 0; k < RJ_P1_KEYS; k++) {
-		const uint32_t r = (item[k] >> pshift) / RJ_SPLIT;
+		const uint32_t r = (item[k] >> 16) / RJ_SPLIT;
 		if (pos[k] < RJ_CAP)
-			sm->stage[r * RJ_CAP + pos[k]] = (uint16_t)(item[k] & rmask);
+			sm->stage[r * RJ_CAP + pos[k]] = (uint16_t)item[k];
 		worst = max(worst, ALL_MINE ? pos[k] : pos[k] + 1u);
 	}
 	// rare (7 keys in 8192): some row was full
@@ -177,7 +185,7 @@ __device__ __forceinline__ uint32_t rj_insert_items(const RJSide &s, RJP1Smem *s
 #pragma unroll
 		for (int k = 0; k < RJ_P1_KEYS; k++) {
 			const bool over = pos[k] >= RJ_CAP && pos[k] != RJ_NONE;
-			kept = over ? (((item[k] >> pshift) << 16) | (item[k] & rmask)) : kept;
+			kept = over ? item[k] : kept;
 			n_over += over ? 1u : 0u;
 		}
 		if (kept != RJ_NONE)
@@ -193,7 +201,7 @@ __device__ __forceinline__ uint32_t rj_insert_items(const RJSide &s, RJP1Smem *s
 				if (pos[k] < RJ_CAP || pos[k] == RJ_NONE)
 					continue;
 				if (!last)
-					rj_tail_single(s.tail_cursor, s.tail, s.tail_cap, pr.error_flag, item[k] >> pshift, item[k] & rmask);
+					rj_tail_single(s.tail_cursor, s.tail, s.tail_cap, pr.error_flag, item[k] >> 16, item[k] & 0xffffu);
 				last = false;
 			}
 		}
@@ -328,9 +336,9 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition_fas
 		uint32_t item[RJ_P1_KEYS];
 #pragma unroll
 		for (int k = 0; k < RJ_P1_KEYS; k++)
-			item[k] = buf[k] - kmin_lo;
+			item[k] = rj_pack(pr, buf[k] - kmin_lo);
 		uint32_t kept_at = 0;
-		const uint32_t kept = rj_insert_items<false>(s, sm, pr, item, half, kept_at);
+		const uint32_t kept = rj_insert_items<true>(s, sm, pr, item, half, kept_at);
 		rj_round_end(s, pr, sm, kept, kept_at, half, rj_t_);
 	};
 	uint64_t tile = slot;
@@ -353,7 +361,7 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition_fas
 	if (slot == 0 && nfull * TILE != s.n) {
 		for (uint64_t r = nfull * TILE + tid; r < s.n; r += RJ_P1_THREADS) {
 			const uint32_t d = (uint32_t)(unsigned long long)s.keys[r] - kmin_lo;
-			rj_insert_one(s, sm, pr, ((d >> pr.shift) << 16) | (d & pr.mask), half);
+			rj_insert_one(s, sm, pr, rj_pack(pr, d), half);
 		}
 		rj_round_end(s, pr, sm, RJ_NONE, 0u, half, rj_t_);
 	}
@@ -411,10 +419,10 @@ __device__ static inline uint32_t rj_insert_tile(const RJSide &s, const RJParams
 			ok0 = ok0 && (pw & 1u);
 			ok1 = ok1 && (pw & 2u);
 		}
-		item[2 * j] = ok0 ? ((((uint32_t)d0 >> pr.shift) << 16) | ((uint32_t)d0 & pr.mask)) : RJ_NONE;
-		item[2 * j + 1] = ok1 ? ((((uint32_t)d1 >> pr.shift) << 16) | ((uint32_t)d1 & pr.mask)) : RJ_NONE;
+		item[2 * j] = ok0 ? rj_pack(pr, (uint32_t)d0) : RJ_NONE;
+		item[2 * j + 1] = ok1 ? rj_pack(pr, (uint32_t)d1) : RJ_NONE;
 	}
-	return rj_insert_items<true>(s, sm, pr, item, half, kept_at);
+	return rj_insert_items<false>(s, sm, pr, item, half, kept_at);
 }
 
 // Pass 1, generic variant (NULLs / tombstones / keys outside the partitioned range): same rounds as the lean

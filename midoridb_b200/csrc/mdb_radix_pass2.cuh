@@ -94,14 +94,15 @@ __device__ __forceinline__ uint32_t rj_histogram_run(const uint16_t *__restrict_
 
 // count the keys of rows [lo, hi) of a sorted column (all of them belong to the partition being counted)
 template <int BITS, int THREADS>
-__device__ __forceinline__ void rj_histogram_sorted(const int64_t *__restrict__ keys, uint64_t lo, uint64_t hi, uint32_t kmin_lo,
-		uint32_t mask, uint32_t *cnt)
+// (base_lo = low word of kmin + p * width: the remainder of a key of partition p is key - base)
+__device__ __forceinline__ void rj_histogram_sorted(const int64_t *__restrict__ keys, uint64_t lo, uint64_t hi, uint32_t base_lo,
+		uint32_t *cnt)
 {
 	const uint64_t a = min((uint64_t)((lo + 3) & ~3ull), hi), b = max(a, (uint64_t)(hi & ~3ull)); // [a, b): whole 32-byte quads
 	for (uint64_t i = lo + threadIdx.x; i < a; i += THREADS)
-		rj_count<BITS>(cnt, ((uint32_t)(unsigned long long)keys[i] - kmin_lo) & mask);
+		rj_count<BITS>(cnt, (uint32_t)(unsigned long long)keys[i] - base_lo);
 	for (uint64_t i = b + threadIdx.x; i < hi; i += THREADS)
-		rj_count<BITS>(cnt, ((uint32_t)(unsigned long long)keys[i] - kmin_lo) & mask);
+		rj_count<BITS>(cnt, (uint32_t)(unsigned long long)keys[i] - base_lo);
 	constexpr int MLP = 2;
 	const uint64_t q0 = a / 4, nq = (b - a) / 4;
 	for (uint64_t v0 = threadIdx.x; v0 < nq; v0 += THREADS * MLP) {
@@ -115,7 +116,7 @@ __device__ __forceinline__ void rj_histogram_sorted(const int64_t *__restrict__ 
 				continue;
 #pragma unroll
 			for (int j = 0; j < 4; j++)
-				rj_count<BITS>(cnt, (w[u][2 * j] - kmin_lo) & mask);
+				rj_count<BITS>(cnt, w[u][2 * j] - base_lo);
 		}
 	}
 }
@@ -129,7 +130,7 @@ __device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, const RJP
 {
 	if (r.nsrc == 0) {
 		const uint64_t lo = r.sorted_bnd[p], hi = r.sorted_bnd[p + 1];
-		rj_histogram_sorted<BITS, THREADS>(r.sorted_keys, lo, hi, (uint32_t)(unsigned long long)pr.kmin, pr.mask, cnt);
+		rj_histogram_sorted<BITS, THREADS>(r.sorted_keys, lo, hi, (uint32_t)(unsigned long long)pr.kmin + p * pr.width, cnt);
 		return (uint32_t)(hi - lo);
 	}
 	uint32_t total = 0, in_tails = 0;
@@ -184,8 +185,7 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 	constexpr int KPW = 32 / BITS;
 	constexpr int NWARPS = THREADS / 32;
 	constexpr uint32_t FIELD = (1u << BITS) - 1u;
-	const int D = 1 << pr.shift;
-	const int words = D >= KPW ? D / KPW : 1;
+	const int words = (int)((pr.width + KPW - 1) / KPW); // counters of one side (the fields beyond `width` stay zero)
 	uint32_t *cntA = reinterpret_cast<uint32_t*>(smem_raw);
 	uint32_t *cntB = cntA + words;
 	__shared__ uint32_t s_part, s_sumA, s_sumB, s_tailA, s_tailB;
@@ -262,7 +262,7 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 		// ---- emit: one counter position at a time, matching lanes write consecutive rows (coalesced runs)
 		const uint32_t total = s_warp[NWARPS];
 		if (total && s_base + total <= out.cap) {
-			const long long key_base = pr.kmin + (long long)((unsigned long long)p << pr.shift);
+			const long long key_base = pr.kmin + (long long)((unsigned long long)p * pr.width);
 			const unsigned long long row0 = s_base + s_warp[warp];
 			int64_t *const key_col = out.cells[LAYOUT == 2 ? 1 : 0] + row0, *const cnt_col = out.cells[LAYOUT == 2 ? 0 : 1] + row0;
 			uint32_t pos = 0; // rows this warp has written for this partition

@@ -28,13 +28,13 @@ __global__ void k_is_sorted(const int64_t *__restrict__ keys, uint64_t n, uint32
 		atomicOr(descents, 1u);
 }
 
-// bnd[p] = first row whose key is >= kmin + (p << shift), p = 0 .. nparts (bnd[nparts]: first row beyond the range)
+// bnd[p] = first row whose key is >= kmin + p * width, p = 0 .. nparts (bnd[nparts]: first row beyond the range)
 __global__ void k_sorted_bounds(const int64_t *__restrict__ keys, uint64_t n, RJParams pr, uint64_t *__restrict__ bnd)
 {
 	const int p = blockIdx.x * blockDim.x + threadIdx.x;
 	if (p > pr.nparts)
 		return;
-	const unsigned long long off = p == pr.nparts ? pr.range : ((unsigned long long)p << pr.shift);
+	const unsigned long long off = p == pr.nparts ? pr.range : (unsigned long long)p * pr.width;
 	uint64_t lo = 0, hi = n;
 	while (lo < hi) {
 		const uint64_t mid = lo + (hi - lo) / 2;

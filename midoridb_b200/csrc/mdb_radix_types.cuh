@@ -12,6 +12,11 @@
 #define RJ_P1_THREADS (1024 / RJ_SPLIT)
 #define RJ_ROWS (RJ_MAX_PART / RJ_SPLIT) // staging rows per CTA
 #define RJ_NONE 0xffffffffu
+
+// The key range is cut into nparts = ceil(range / width) <= 4096 partitions of `width` = ceil(range / 4096) key values
+// each - NOT into power-of-two blocks: a range a little above a power of two would otherwise use only half of the 4096
+// staging rows of pass 1, every row would receive twice the keys per round and overflow ten times as often
+// (profiles/r02: 2049 partitions, flags "stream full" + "clustered keys" on plain uniform keys).
 #define RJ_MAX_RANKS 8
 #define RJ_CUR_STRIDE 2            // 32-bit words per partition in the cursor array: [main cursor, tail cursor].  (One 128-byte
                                    // line per partition was measured 5% SLOWER: the atomics like their few hot L2 lines.)
@@ -60,8 +65,8 @@ struct RJRuns {
 struct RJParams {
 	long long kmin;
 	unsigned long long range;  // keys in [kmin, kmin + range) can match
-	int shift;                 // remainder bits
-	uint32_t mask;             // (1 << shift) - 1
+	uint32_t width;            // key values per partition (2 .. 65536): partition = (key - kmin) / width, remainder = the rest
+	uint32_t magic;            // floor(2^32 / width): __umulhi(d, magic) is d / width or one less (rj_pack corrects it)
 	int nparts;
 	int part_first, part_end;  // pass 2 handles partitions [part_first, part_end) (all of them on one GPU)
 	uint32_t *error_flag;

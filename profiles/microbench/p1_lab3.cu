@@ -46,8 +46,8 @@ int main(int argc, char **argv)
 	memset(&pr, 0, sizeof(pr));
 	pr.kmin = 0;
 	pr.range = n;
-	pr.shift = lg - 12;
-	pr.mask = (1u << pr.shift) - 1u;
+	pr.width = 1u << (lg - 12);
+	pr.magic = (uint32_t)((1ull << 32) / pr.width);
 	pr.nparts = 4096;
 	pr.part_end = 4096;
 	pr.error_flag = flag;
