@@ -42,6 +42,7 @@ struct mdbcu_ctx {
 	cudaStream_t side_stream = nullptr; // multi-GPU: the push of one join side runs here while pass 1 of the other side runs
 	cudaEvent_t side_ev[2] = {};
 	uint32_t arena_queries = 0; // distributed queries so far: alternate queries use alternate halves of the arena
+	bool radix_attr_done = false; // dynamic shared-memory limits of the radix kernels raised on this context's device
 	bool radix_gave_up = false; // the radix join handed the running query back because of its DATA (duplicates, skew)
 	// reusable scratch: pinned host word for small D2H reads
 	uint64_t *h_scalar = nullptr; // pinned, 64 entries

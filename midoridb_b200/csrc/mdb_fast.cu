@@ -368,6 +368,27 @@ __global__ void k_scan_aggregate_final(SASpec sp, const SAPartial *__restrict__ 
 	}
 }
 
+// one rank's block partials folded (in block order) into a single partial: what a distributed plan exchanges
+__global__ void k_scan_aggregate_fold(SASpec sp, const SAPartial *__restrict__ partials, int nparts, SAPartial *__restrict__ dst)
+{
+	if (threadIdx.x != 0 || blockIdx.x != 0)
+		return;
+	SAState<SA_MAX_AGGS> tot;
+	SASpec full = sp;
+	for (int a = sp.naggs; a < SA_MAX_AGGS; a++) {
+		full.aggs[a].kind = MDBCU_OUT_COUNT_STAR;
+		full.aggs[a].col = -1;
+	}
+	sa_init<SA_MAX_AGGS>(full, tot);
+	for (int b = 0; b < nparts; b++)
+		sa_merge<SA_MAX_AGGS>(full, tot, partials[b].rows, partials[b].nn, partials[b].acc);
+	dst->rows = tot.rows;
+	for (int a = 0; a < SA_MAX_AGGS; a++) {
+		dst->nn[a] = tot.nn[a];
+		dst->acc[a] = tot.acc[a];
+	}
+}
+
 template <int NC>
 static void launch_scan_agg(mdbcu_ctx *ctx, int grid, const SASpec &sp, uint64_t n, SAPartial *partials)
 {
@@ -505,13 +526,20 @@ static bool pred_to_ranges(const mdbcu_plan *plan, SASpec *sp, int *col_of /* ta
 
 int mdb_select_scan_agg(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res)
 {
-	if (plan->n_tables != 1 || plan->n_group != 0 || plan->n_out > SA_MAX_AGGS || (plan->flags & MDBCU_PLAN_DISTRIBUTED))
+	if (plan->n_tables != 1 || plan->n_group != 0 || plan->n_out > SA_MAX_AGGS)
 		return MDBCU_EUNSUPPORTED;
+	// Distributed plan ("C2: embarrassingly parallel scan + a small reduce"): every rank scans ITS shard, the
+	// ranks' partials are all-gathered and folded in rank order (deterministic DOUBLE sums for a given number of ranks),
+	// rank 0 returns the row and the other ranks return no row, so that the ranks' results concatenate to the answer.
+	// Every decision below depends on the plan and the schema only: all ranks take this path or none does.
+	const bool dist = (plan->flags & MDBCU_PLAN_DISTRIBUTED) != 0;
+	if (dist && !mdb_comm_ready(ctx))
+		return mdb_fail(ctx, MDBCU_EERROR, "MDBCU_PLAN_DISTRIBUTED needs mdbcu_comm_init first");
 	const mdbcu_table *t = plan->tables[0];
 	for (int o = 0; o < plan->n_out; o++)
 		if (plan->out[o].kind == MDBCU_OUT_COLUMN)
 			return MDBCU_EUNSUPPORTED;
-	if (t->n_slots < (1u << 16))
+	if (!dist && t->n_slots < (1u << 16))
 		return MDBCU_EUNSUPPORTED; // tiny tables: the general operators are just as good and keep row order logic in one place
 
 	SASpec sp;
@@ -547,6 +575,7 @@ int mdb_select_scan_agg(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *re
 	}
 	sp.naggs = plan->n_out;
 	// COUNT(*) with tombstones but no column constraint would count dead rows: let the general path do it
+	// (live_checked is false only when no column is referenced at all, which the next test rejects on every rank alike)
 	if (!t->all_live && !live_checked)
 		return MDBCU_EUNSUPPORTED;
 	if (sp.ncols == 0) {
@@ -588,7 +617,21 @@ int mdb_select_scan_agg(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *re
 		launch_scan_agg<3>(ctx, grid, sp, t->n_slots, partials);
 	cudaEventRecord(k1, ctx->stream);
 	clock.begin(4);
-	MDB_LAUNCH(ctx, k_scan_aggregate_final, 1, 32, 0, sp, (const SAPartial*)partials, grid, out, d_rows);
+	const int W = dist ? ctx->world : 1;
+	if (W > 1) {
+		// this rank's block partials -> one partial; all ranks' partials -> every rank; rank 0 folds them in rank order
+		SAPartial *mine, *all;
+		MDB_TRY(tmp.alloc(&mine, 1));
+		MDB_TRY(tmp.alloc(&all, W));
+		MDB_LAUNCH(ctx, k_scan_aggregate_fold, 1, 32, 0, sp, (const SAPartial*)partials, grid, mine);
+		clock.begin(6);
+		MDB_TRY(mdb_comm_allgather_bytes(ctx, mine, all, sizeof(SAPartial)));
+		ctx->stats.exchange_bytes = (uint64_t)(W - 1) * sizeof(SAPartial);
+		clock.begin(4);
+		MDB_LAUNCH(ctx, k_scan_aggregate_final, 1, 32, 0, sp, (const SAPartial*)all, W, out, d_rows);
+	} else {
+		MDB_LAUNCH(ctx, k_scan_aggregate_final, 1, 32, 0, sp, (const SAPartial*)partials, grid, out, d_rows);
+	}
 	cudaError_t e = cudaGetLastError();
 	clock.finish();
 	float kms = 0.f;
@@ -600,8 +643,8 @@ int mdb_select_scan_agg(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *re
 
 	uint64_t rows = 0;
 	MDB_TRY(mdb_read_u64(ctx, (const uint64_t*)d_rows, &rows));
-	if (rows == 0)
-		res->nrows = 0; // nothing qualified: the reference returns no row (handle_countonly_case keeps zero rows)
+	if (rows == 0 || (W > 1 && ctx->rank != 0))
+		res->nrows = 0; // nothing qualified: the reference returns no row (handle_countonly_case keeps zero rows); rank > 0: rank 0 has it
 
 	ctx->stats.algorithmic_bytes = 8ull * t->n_slots * sp.ncols + 8ull * plan->n_out;
 	ctx->stats.dominant_ms = kms;

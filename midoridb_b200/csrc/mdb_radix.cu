@@ -322,8 +322,8 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		fill(&ship_b, &rb, lb, half_off + la.bytes * (size_t)W);
 	}
 
-	static bool attr_done = false;
-	if (!attr_done) {
+	// (per context: the attribute belongs to the device, and one process may drive several)
+	if (!ctx->radix_attr_done) {
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
@@ -340,7 +340,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
 		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<8, 1024, 2, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 65536));
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_ship, cudaFuncAttributeMaxDynamicSharedMemorySize, RJ_SHIP_SMEM));
-		attr_done = true;
+		ctx->radix_attr_done = true;
 	}
 
 	clock.begin(1);

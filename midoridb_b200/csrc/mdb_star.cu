@@ -326,6 +326,66 @@ __global__ void k_star_emit(StarSpec sp, StarOut out)
 	}
 }
 
+// distributed plan: the ranks' direct tables ([range entries | flag word] each) -> the whole dimension's table
+__global__ void k_star_merge_tables(const unsigned int *__restrict__ all, int world, uint32_t range, unsigned int *__restrict__ table,
+		unsigned int *__restrict__ flags)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i == 0) {
+		unsigned int f = 0;
+		for (int r = 0; r < world; r++)
+			f |= all[(size_t)r * (range + 1) + range];
+		if (f)
+			atomicOr(flags, f);
+	}
+	if (i >= range)
+		return;
+	unsigned int v = 0xffffffffu;
+	for (int r = 0; r < world; r++) {
+		const unsigned int x = all[(size_t)r * (range + 1) + i];
+		if (x == 0xffffffffu)
+			continue;
+		if (v != 0xffffffffu)
+			atomicOr(flags, 4u); // the key is in two shards: duplicate dimension key
+		v = x;
+	}
+	table[i] = v;
+}
+
+// distributed plan: all ranks' accumulator blocks folded into sp.g_* in rank order (layout: mdb_select_direct_star)
+__global__ void k_star_merge_acc(StarSpec sp, const unsigned char *__restrict__ all, int world, size_t rows_bytes, size_t block_bytes)
+{
+	const uint32_t G = sp.ngroups;
+	for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < G; g += gridDim.x * blockDim.x) {
+		unsigned int rows = 0;
+		for (int r = 0; r < world; r++)
+			rows += reinterpret_cast<const unsigned int*>(all + (size_t)r * block_bytes)[g];
+		sp.g_rows[g] = rows;
+		for (int a = 0; a < sp.naggs; a++) {
+			const int kind = sp.aggs[a].kind;
+			const bool dsum = (kind == MDBCU_OUT_SUM || kind == MDBCU_OUT_AVG) && sp.aggs[a].is_dbl;
+			long long acc = kind == MDBCU_OUT_MIN ? INT64_MAX : kind == MDBCU_OUT_MAX ? INT64_MIN : 0;
+			double dacc = 0.0;
+			unsigned long long nn = 0;
+			for (int r = 0; r < world; r++) {
+				const unsigned char *blk = all + (size_t)r * block_bytes + rows_bytes;
+				const long long x = reinterpret_cast<const long long*>(blk)[(size_t)a * G + g];
+				nn += reinterpret_cast<const unsigned long long*>(blk + (size_t)sp.naggs * G * 8)[(size_t)a * G + g];
+				if (kind == MDBCU_OUT_MIN)
+					acc = x < acc ? x : acc;
+				else if (kind == MDBCU_OUT_MAX)
+					acc = x > acc ? x : acc;
+				else if (dsum)
+					dacc += __longlong_as_double(x);
+				else
+					acc = (long long)((unsigned long long)acc + (unsigned long long)x);
+			}
+			sp.g_acc[(size_t)a * G + g] = dsum ? __double_as_longlong(dacc) : acc;
+			sp.g_nn[(size_t)a * G + g] = nn;
+		}
+	}
+}
+
 __global__ void k_star_init_acc(StarSpec sp)
 {
 	const uint32_t G = sp.ngroups;
@@ -338,12 +398,9 @@ __global__ void k_star_init_acc(StarSpec sp)
 template <int NC>
 static void st_launch_probe(mdbcu_ctx *ctx, int grid, size_t smem, int na, const StarSpec &sp, const unsigned int *table, uint64_t n)
 {
-	static bool attr_done[5] = {};
 	auto launch = [&](auto kernel) {
-		if (!attr_done[na]) {
-			cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 195 * 1024);
-			attr_done[na] = true;
-		}
+		// (set on every launch: the limit belongs to the current device, one process may drive several, and the call is cheap)
+		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 195 * 1024);
 		MDB_LAUNCH(ctx, kernel, grid, ST_THREADS, smem, sp, table, n);
 	};
 	if (na <= 1)
@@ -357,8 +414,17 @@ static void st_launch_probe(mdbcu_ctx *ctx, int grid, size_t smem, int na, const
 int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res)
 {
 	if (plan->n_tables != 2 || plan->n_joins != 1 || plan->joins[0].cross || plan->n_pred != 0 || plan->n_group != 1 ||
-			plan->n_out < 1 || plan->n_out > MDBCU_MAX_OUT || (plan->flags & MDBCU_PLAN_DISTRIBUTED))
+			plan->n_out < 1 || plan->n_out > MDBCU_MAX_OUT)
 		return MDBCU_EUNSUPPORTED;
+	// Distributed plan ("C5: replicate the small dimension, shard the fact - no all-to-all"): every rank holds a
+	// shard of BOTH tables; the ranks' direct tables (<= 256 KiB each) are all-gathered and merged into the whole dimension,
+	// every rank probes it with its fact shard, the per-group accumulators (<= 64 KiB per rank) are all-gathered and folded
+	// in rank order on rank 0, which returns the groups; the other ranks return no row.  All decisions use the plan and
+	// the GLOBAL statistics (mdbcu_table_sync_stats): the ranks take this path together or not at all.
+	const bool dist = (plan->flags & MDBCU_PLAN_DISTRIBUTED) != 0;
+	if (dist && !mdb_comm_ready(ctx))
+		return mdb_fail(ctx, MDBCU_EERROR, "MDBCU_PLAN_DISTRIBUTED needs mdbcu_comm_init first");
+	const int W = dist ? ctx->world : 1;
 	const mdbcu_join &jn = plan->joins[0];
 	if (jn.left.tbl == jn.right.tbl || jn.left.tbl < 0 || jn.left.tbl > 1 || jn.right.tbl < 0 || jn.right.tbl > 1)
 		return MDBCU_EUNSUPPORTED;
@@ -372,10 +438,22 @@ int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result 
 	if (dk < 0 || dk >= D->ncols || fk < 0 || fk >= F->ncols || gc < 0 || gc >= D->ncols)
 		return MDBCU_EUNSUPPORTED;
 	auto intlike = [](int type) { return type == MDBCU_CT_INTEGER || type == MDBCU_CT_DATE || type == MDBCU_CT_DATETIME || type == MDBCU_CT_TINYINT; };
-	const DevColumn &ck = D->cols[dk], &cg = D->cols[gc], &cf = F->cols[fk];
-	if (!intlike(ck.type) || !intlike(cg.type) || !intlike(cf.type) || !ck.stats_ok || !cg.stats_ok)
+	DevColumn ck = D->cols[dk], cg = D->cols[gc]; // copies: a distributed plan uses the bounds over all shards
+	const DevColumn &cf = F->cols[fk];
+	if (!intlike(ck.type) || !intlike(cg.type) || !intlike(cf.type))
 		return MDBCU_EUNSUPPORTED;
-	if (F->n_slots < (1ull << 20) || D->n_slots == 0 || D->n_slots > (1ull << 22))
+	if (dist) {
+		if (!ck.gstats_ok || !cg.gstats_ok || !D->global_slots || !F->global_slots)
+			return mdb_fail(ctx, MDBCU_EERROR, "distributed plan: call mdbcu_table_sync_stats on every sharded table first");
+		ck.imin = ck.gmin;
+		ck.imax = ck.gmax;
+		cg.imin = cg.gmin;
+		cg.imax = cg.gmax;
+	} else if (!ck.stats_ok || !cg.stats_ok) {
+		return MDBCU_EUNSUPPORTED;
+	}
+	const uint64_t f_rows = dist ? F->global_slots : F->n_slots, d_rows = dist ? D->global_slots : D->n_slots;
+	if (f_rows < (1ull << 20) || d_rows == 0 || d_rows > (1ull << 22))
 		return MDBCU_EUNSUPPORTED; // small inputs: general operators (they also return the reference's row order)
 	if (ck.imin > ck.imax || cg.imin > cg.imax)
 		return MDBCU_EUNSUPPORTED;
@@ -449,9 +527,15 @@ int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result 
 	MDB_TRY(tmp.alloc(&d_table, (size_t)range));
 	MDB_TRY(tmp.alloc(&d_flags, 1));
 	MDB_TRY(tmp.alloc(&d_nrows, 1));
-	MDB_TRY(tmp.alloc(&sp.g_rows, (size_t)ngroups));
-	MDB_TRY(tmp.alloc(&sp.g_acc, (size_t)na * ngroups));
-	MDB_TRY(tmp.alloc(&sp.g_nn, (size_t)na * ngroups));
+	// the accumulators of all groups in ONE block [joined rows u32 x G, padded | acc i64 x na x G | non-NULL counts u64 x na x G]:
+	// it is what a distributed plan exchanges
+	const size_t rows_bytes = ((size_t)ngroups * sizeof(unsigned int) + 7) & ~(size_t)7;
+	const size_t block_bytes = rows_bytes + 2 * (size_t)na * ngroups * 8;
+	unsigned char *acc_block;
+	MDB_TRY(tmp.alloc(&acc_block, block_bytes));
+	sp.g_rows = reinterpret_cast<unsigned int*>(acc_block);
+	sp.g_acc = reinterpret_cast<long long*>(acc_block + rows_bytes);
+	sp.g_nn = reinterpret_cast<unsigned long long*>(acc_block + rows_bytes + (size_t)na * ngroups * 8);
 	CUDA_TRY(ctx, cudaMemsetAsync(d_table, 0xff, range * sizeof(unsigned int), ctx->stream)); // 0xffffffff: (uint16_t) = ST_EMPTY
 	CUDA_TRY(ctx, cudaMemsetAsync(d_flags, 0, sizeof(unsigned int), ctx->stream));
 	CUDA_TRY(ctx, cudaMemsetAsync(d_nrows, 0, sizeof(unsigned long long), ctx->stream));
@@ -467,6 +551,22 @@ int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result 
 			(const int64_t*)ck.data, st_all_present(D, dk) ? (const uint32_t*)nullptr : (const uint32_t*)ck.present, (const int64_t*)cg.data,
 			st_all_present(D, gc) ? (const uint32_t*)nullptr : (const uint32_t*)cg.present, (uint64_t)D->n_slots, (long long)ck.imin, (uint32_t)range,
 			(long long)cg.imin, (uint32_t)ngroups, d_table, d_flags);
+	if (W > 1) {
+		// [table | flags] of every rank -> every rank; the merged table is the whole dimension (a key present in two shards
+		// is a duplicate), the merged flags make all ranks take the same decision
+		unsigned int *mine, *all;
+		const size_t words = (size_t)range + 1;
+		MDB_TRY(tmp.alloc(&mine, words));
+		MDB_TRY(tmp.alloc(&all, words * W));
+		CUDA_TRY(ctx, cudaMemcpyAsync(mine, d_table, range * sizeof(unsigned int), cudaMemcpyDeviceToDevice, ctx->stream));
+		CUDA_TRY(ctx, cudaMemcpyAsync(mine + range, d_flags, sizeof(unsigned int), cudaMemcpyDeviceToDevice, ctx->stream));
+		clock.begin(6);
+		MDB_TRY(mdb_comm_allgather_bytes(ctx, mine, all, words * sizeof(unsigned int)));
+		ctx->stats.exchange_bytes += (uint64_t)(W - 1) * words * sizeof(unsigned int);
+		clock.begin(2);
+		MDB_LAUNCH(ctx, k_star_merge_tables, std::max(1, (int)((range + 255) / 256)), 256, 0, (const unsigned int*)all, W, (uint32_t)range,
+				d_table, d_flags);
+	}
 	uint64_t flags64 = 0;
 	{
 		// (4-byte flag word read through the 8-byte helper: the next word belongs to d_nrows' allocation or padding)
@@ -491,6 +591,15 @@ int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result 
 	else
 		st_launch_probe<3>(ctx, ctx->num_sms, smem, na, sp, d_table, F->n_slots);
 	cudaEventRecord(k1, ctx->stream);
+	if (W > 1) {
+		unsigned char *all;
+		MDB_TRY(tmp.alloc(&all, block_bytes * W));
+		clock.begin(6);
+		MDB_TRY(mdb_comm_allgather_bytes(ctx, acc_block, all, block_bytes));
+		ctx->stats.exchange_bytes += (uint64_t)(W - 1) * block_bytes;
+		// rank order, starting from rank 0's block: the same fold on every run
+		MDB_LAUNCH(ctx, k_star_merge_acc, 8, 256, 0, sp, (const unsigned char*)all, W, rows_bytes, block_bytes);
+	}
 
 	// ---- emit
 	clock.begin(4);
@@ -513,7 +622,7 @@ int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result 
 	cudaEventDestroy(k1);
 	if (e != cudaSuccess)
 		return mdb_fail(ctx, MDBCU_ECUDA, "star join launch failed: %s", cudaGetErrorString(e));
-	res->nrows = nrows;
+	res->nrows = (W > 1 && ctx->rank != 0) ? 0 : nrows; // distributed: rank 0 returns the groups
 	(void)naggs_real;
 
 	ctx->stats.path = MDBCU_PATH_DIRECT_STAR;

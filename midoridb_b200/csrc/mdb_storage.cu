@@ -276,28 +276,42 @@ int mdb_table_reserve(mdbcu_table *tt, uint64_t rows)
 
 	size_t old_words = t->cap ? bitmap_words(t->cap) : 0, new_words = bitmap_words(ncap);
 
-	for (auto &c : t->cols) {
-		int64_t *nd = nullptr;
-		uint32_t *np = nullptr;
-		MDB_TRY(mdb_alloc(ctx, &nd, ncap));
-		MDB_TRY(mdb_alloc(ctx, &np, new_words));
-		CUDA_TRY(ctx, cudaMemsetAsync(np, 0, new_words * sizeof(uint32_t), ctx->stream));
-		if (t->n_slots) {
-			CUDA_TRY(ctx, cudaMemcpyAsync(nd, c.data, t->n_slots * sizeof(int64_t), cudaMemcpyDeviceToDevice,
-					ctx->stream));
-			CUDA_TRY(ctx, cudaMemcpyAsync(np, c.present, old_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
-					ctx->stream));
-		}
-		mdb_free(ctx, c.data);
-		mdb_free(ctx, c.present);
-		c.data = nd;
-		c.present = np;
-	}
+	// every new buffer is allocated and filled BEFORE any pointer of the table changes: a failure half-way (out of memory)
+	// frees what was allocated here and leaves the table exactly as it was
+	std::vector<int64_t*> nd(t->cols.size(), nullptr);
+	std::vector<uint32_t*> np(t->cols.size(), nullptr);
 	uint32_t *nl = nullptr;
-	MDB_TRY(mdb_alloc(ctx, &nl, new_words));
-	CUDA_TRY(ctx, cudaMemsetAsync(nl, 0, new_words * sizeof(uint32_t), ctx->stream));
-	if (t->n_slots)
-		CUDA_TRY(ctx, cudaMemcpyAsync(nl, t->live, old_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+	auto grow = [&]() -> int {
+		for (size_t i = 0; i < t->cols.size(); i++) {
+			MDB_TRY(mdb_alloc(ctx, &nd[i], ncap));
+			MDB_TRY(mdb_alloc(ctx, &np[i], new_words));
+			CUDA_TRY(ctx, cudaMemsetAsync(np[i], 0, new_words * sizeof(uint32_t), ctx->stream));
+			if (t->n_slots) {
+				CUDA_TRY(ctx, cudaMemcpyAsync(nd[i], t->cols[i].data, t->n_slots * sizeof(int64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+				CUDA_TRY(ctx, cudaMemcpyAsync(np[i], t->cols[i].present, old_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+			}
+		}
+		MDB_TRY(mdb_alloc(ctx, &nl, new_words));
+		CUDA_TRY(ctx, cudaMemsetAsync(nl, 0, new_words * sizeof(uint32_t), ctx->stream));
+		if (t->n_slots)
+			CUDA_TRY(ctx, cudaMemcpyAsync(nl, t->live, old_words * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+		return MDBCU_OK;
+	};
+	const int grc = grow();
+	if (grc != MDBCU_OK) {
+		for (size_t i = 0; i < t->cols.size(); i++) {
+			mdb_free(ctx, nd[i]);
+			mdb_free(ctx, np[i]);
+		}
+		mdb_free(ctx, nl);
+		return grc;
+	}
+	for (size_t i = 0; i < t->cols.size(); i++) {
+		mdb_free(ctx, t->cols[i].data);
+		mdb_free(ctx, t->cols[i].present);
+		t->cols[i].data = nd[i];
+		t->cols[i].present = np[i];
+	}
 	mdb_free(ctx, t->live);
 	t->live = nl;
 	t->cap = ncap;

@@ -445,6 +445,26 @@ bool parse_time(const std::string &s, enum COLUMN_TYPE type, time_t *out)
 	return true;
 }
 
+// Would store_literal accept this literal for this column?  INSERT and UPDATE check EVERY value with this before they touch
+// the first row, as the reference does in its semantic phase (semantic_insert.c check_value_types, semantic_update.c): a
+// statement that fails must leave the table - and the device mirror, which only sees pages marked dirty - untouched.
+bool literal_fits(const struct column *col, const Literal &l)
+{
+	if (l.kind == K_NULL)
+		return col->nullable;
+	switch (col->type) {
+	case CT_INTEGER: return l.kind == K_INT;
+	case CT_DOUBLE: return l.kind == K_FLOAT || l.kind == K_INT;
+	case CT_TINYINT: return l.kind == K_BOOL || l.kind == K_INT;
+	case CT_DATE: case CT_DATETIME: {
+		time_t tv;
+		return l.kind == K_STR && parse_time(l.s, col->type, &tv);
+	}
+	case CT_VARCHAR: return l.kind == K_STR && (int)l.s.size() + 1 <= col->precision;
+	}
+	return false;
+}
+
 // write one literal into a row cell; false on a type mismatch (semantic_insert.c's check_value_types)
 bool store_literal(const struct column *col, int idx, const Literal &l, struct row *row, size_t off)
 {
@@ -561,11 +581,19 @@ int exec_insert(Catalog *cat, const std::vector<std::string> &toks, struct query
 	}
 	size_t rs = row_size_of(t);
 	std::vector<char> buf(rs);
+	// semantic phase first: a multi-row INSERT with one bad tuple inserts nothing
 	for (const auto &tup : tuples) {
 		if (tup.size() != order.size()) {
 			set_err(out, "semantic phase: number of values doesn't match number of columns\n");
 			return -MIDORIDB_ERROR;
 		}
+		for (size_t k = 0; k < order.size(); k++)
+			if (!literal_fits(&t->columns[order[k]], tup[k])) {
+				set_err(out, "semantic phase: value for column '%s' has the wrong type\n", t->columns[order[k]].name);
+				return -MIDORIDB_ERROR;
+			}
+	}
+	for (const auto &tup : tuples) {
 		struct row *row = (struct row*)buf.data();
 		memset(row, 0, rs);
 		// build_row, executor_insert.c:60-134: every column starts NULL, supplied values clear the bit
@@ -1003,6 +1031,11 @@ int exec_update(Catalog *cat, const std::vector<std::string> &toks, struct query
 			set_err(out, "execution phase: UPDATE of VARCHAR columns is not supported\n");
 			return -MIDORIDB_ERROR;
 		}
+		// checked BEFORE the scan: a row must never be half-updated (NULL bit cleared, cell zeroed) by a statement that fails
+		if (!literal_fits(&t->columns[tg.col], tg.lit)) {
+			set_err(out, "semantic phase: value for column '%s' has the wrong type\n", t->columns[tg.col].name);
+			return -MIDORIDB_ERROR;
+		}
 		targets.push_back(tg);
 	}
 	int rc = scan_rows(ht, [&](struct row *row, size_t page, size_t) -> int {
@@ -1011,6 +1044,8 @@ int exec_update(Catalog *cat, const std::vector<std::string> &toks, struct query
 			return -MIDORIDB_ERROR;
 		if (!hit)
 			return 0;
+		if (page < ht->mirror_pages)
+			ht->dirty.insert(page); // (before the first byte changes: whatever happens below, the mirror reloads this page)
 		for (const Target &tg : targets) {
 			// set_field_to_value, executor_update.c:394-431: clear the NULL bit, write the cell in place
 			row->null_bitmap[tg.col / 8] &= (char)~(1 << (tg.col % 8));

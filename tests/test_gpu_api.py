@@ -126,3 +126,27 @@ def test_readme_query_large_through_sql_api():
     keys = np.flatnonzero((ca > 0) & (cb > 0))
     want = sorted(zip(keys.tolist(), (ca * cb)[keys].tolist()))
     assert sorted(rows) == want
+
+
+def test_failing_dml_leaves_table_and_mirror_untouched():
+    """a statement the semantic phase rejects must not change a single row: host pages (read by DELETE / UPDATE WHERE) and the
+    device mirror (read by SELECT) stay in agreement.  The reference rejects such statements before its executor runs
+    (semantic_insert.c check_value_types, semantic_update.c)."""
+    with mdb.Database() as db:
+        db.execute("CREATE TABLE T (k INT, v DOUBLE);")
+        db.execute("INSERT INTO T VALUES (1, 0.5), (2, 1.5), (3, 2.5);")
+        assert db.query("SELECT k, v FROM T;")[1] == [(1, 0.5), (2, 1.5), (3, 2.5)]  # the mirror exists now
+        # multi-row INSERT whose LAST tuple is bad: nothing is inserted
+        with pytest.raises(mdb.QueryError):
+            db.execute("INSERT INTO T VALUES (4, 3.5), (5, 4.5), ('x', 1.0);")
+        assert db.query("SELECT COUNT(*) FROM T;")[1] == [(3,)]
+        # UPDATE with a literal of the wrong type: no row loses its value (the first matching row used to be zeroed)
+        with pytest.raises(mdb.QueryError):
+            db.execute("UPDATE T SET k = 'x' WHERE k >= 1;")
+        assert db.query("SELECT k, v FROM T;")[1] == [(1, 0.5), (2, 1.5), (3, 2.5)]
+        # host pages and mirror agree: a DELETE (host-side WHERE) finds what a SELECT (device) shows
+        assert db.execute("DELETE FROM T WHERE k = 1;") == 1
+        assert db.query("SELECT k, v FROM T;")[1] == [(2, 1.5), (3, 2.5)]
+        # a good UPDATE still works and reaches the mirror
+        assert db.execute("UPDATE T SET v = 9.0 WHERE k = 3;") == 1
+        assert db.query("SELECT k, v FROM T;")[1] == [(2, 1.5), (3, 9.0)]

@@ -54,9 +54,8 @@ def run_ranks(devices, body):
         if not any(alive):
             b.close()
     assert not any(alive), "a rank hung"
-    for r, e in enumerate(err):
-        if e is not None:
-            raise AssertionError("rank %d: %r" % (r, e))
+    failed = ["rank %d: %r" % (r, e) for r, e in enumerate(err) if e is not None]
+    assert not failed, "; ".join(failed)
     return out
 
 
@@ -212,3 +211,82 @@ def test_torchrun_nccl_ipc_exchange(world):
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
     out = p.stdout.decode()
     assert p.returncode == 0 and "DIST_CHECK OK world=%d" % world in out, out[-3000:]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_loopback_scan_aggregate(world):
+    """config 2 shape as a distributed plan: every rank scans its shard, the partials are all-gathered and folded in rank
+    order, rank 0 returns the row.  COUNT / integer SUM / MIN / MAX exact, DOUBLE SUM / AVG 1e-9; two runs give the same bits."""
+    n = 3 * (1 << 18)
+    n_local = n // world
+    lo, hi = 1 << 29, 3 * (1 << 29) - 1
+    kw = dict(pred=[("col", 0, 0), ("int", lo), ("cmp", 6), ("col", 0, 0), ("int", hi), ("cmp", 5), ("and",)],
+              out=[(OUT_COUNT_STAR,), (OUT_SUM, 0, 1), (capi.OUT_AVG, 0, 1), (OUT_MIN, 0, 1), (OUT_MAX, 0, 1), (OUT_SUM, 0, 0)])
+    specs = [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=(1 << 31) - 1, seed=41),
+             capi.GenSpec(kind=capi.GEN_UNIFORM_DBL, seed=42, null_permille=30)]
+
+    def body(rank, be):
+        t = be.create_table("T", [I, D])
+        t.generate(n_local, specs, row_offset=rank * n_local)
+        t.sync_stats()
+        rows = []
+        for _ in range(2):
+            res = be.select(capi.make_plan([t], flags=PLAN_DISTRIBUTED, **kw))
+            rows.append(res.rows())
+            res.free()
+        path = be.stats().path
+        k, kv = t.read_column(0)
+        v, vv = t.read_column(1)
+        t.drop()
+        return rows, path, k, v, vv
+
+    parts = run_ranks([0] * world, body)
+    assert all(p[1] == capi.PATH_SCAN_AGG for p in parts)
+    assert all(p[0][0] == p[0][1] for p in parts)  # deterministic
+    assert all(p[0][0] == [] for p in parts[1:]) and len(parts[0][0][0]) == 1  # rank 0 has the row
+    k = np.concatenate([p[2] for p in parts])
+    v = np.concatenate([p[3] for p in parts])
+    vv = np.concatenate([p[4] for p in parts])
+    ot = oracle.OracleTable([I, D])
+    ot.append_columns([k, v], [None, (vv == 0).astype(np.uint8)])
+    _, cells, nulls = oracle.select(capi.make_plan([ot], **kw))
+    want = oracle.rows_of(cells, nulls)
+    assert helpers.rows_close(parts[0][0][0], [helpers.norm_row(r) for r in want], rel=1e-9)
+    assert parts[0][0][0][0][0] == want[0][0] and parts[0][0][0][0][5] == want[0][5]  # COUNT and the integer SUM are exact
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_loopback_star_join(world):
+    """config 5 shape as a distributed plan: BOTH tables sharded; the ranks' direct tables are merged into the whole dimension,
+    every rank probes with its fact shard, rank 0 folds the accumulators and returns the groups"""
+    nf, nd = 1 << 21, 1 << 14
+    dspecs = [capi.GenSpec(kind=capi.GEN_PERMUTATION, lo=0, hi=nd - 1, seed=51), capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=499, seed=52)]
+    fspecs = [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=nd + 99, seed=53),  # some foreign keys have no partner
+              capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=-(1 << 40), hi=1 << 40, seed=54, null_permille=20),
+              capi.GenSpec(kind=capi.GEN_UNIFORM_DBL, seed=55)]
+    kw = dict(joins=[((0, 0), (1, 0))], group=[(0, 1)],
+              out=[(OUT_COLUMN, 0, 1), (OUT_MIN, 1, 1), (OUT_MAX, 1, 1), (OUT_COUNT_STAR,), (OUT_SUM, 1, 2)])
+
+    def body(rank, be):
+        td, tf = be.create_table("D", [I, I]), be.create_table("F", [I, I, D])
+        td.generate(nd // world, dspecs, row_offset=rank * (nd // world))
+        tf.generate(nf // world, fspecs, row_offset=rank * (nf // world))
+        td.sync_stats()
+        tf.sync_stats()
+        res = be.select(capi.make_plan([td, tf], flags=PLAN_DISTRIBUTED, **kw))
+        rows, path, sent = res.rows(), be.stats().path, be.stats().exchange_bytes
+        res.free()
+        cols = [td.read_column(0), td.read_column(1), tf.read_column(0), tf.read_column(1), tf.read_column(2)]
+        td.drop()
+        tf.drop()
+        return rows, path, sent, cols
+
+    parts = run_ranks([0] * world, body)
+    assert all(p[1] == capi.PATH_DIRECT_STAR for p in parts) and all(p[2] > 0 for p in parts)
+    assert all(p[0] == [] for p in parts[1:]) and len(parts[0][0]) > 100
+    cat = lambda i, j: np.concatenate([p[3][i][j] for p in parts])  # noqa: E731
+    od, of = oracle.OracleTable([I, I]), oracle.OracleTable([I, I, D])
+    od.append_columns([cat(0, 0), cat(1, 0)])
+    of.append_columns([cat(2, 0), cat(3, 0), cat(4, 0)], [None, (cat(3, 1) == 0).astype(np.uint8), None])
+    _, cells, nulls = oracle.select(capi.make_plan([od, of], **kw))
+    assert helpers.canon_close(parts[0][0], oracle.rows_of(cells, nulls), rel=1e-9)
