@@ -49,6 +49,8 @@ extern "C" {
 #define MDBCU_MAX_PRED       64
 #define MDBCU_MAX_OUT        32
 #define MDBCU_MAX_GROUP      2
+#define MDBCU_MAX_HAVING     16
+#define MDBCU_MAX_ORDER      4
 
 typedef struct mdbcu_ctx mdbcu_ctx;
 typedef struct mdbcu_table mdbcu_table;
@@ -140,6 +142,7 @@ int mdbcu_table_column_device_ptr(mdbcu_table *t, int col, const void **cells, u
 #define MDBCU_P_IN      11 /* arg = n: pop n values then the probe; true if ANY equal (SQL; see DESIGN.md on D4) */
 #define MDBCU_P_NOTIN   12 /* arg = n: true if ALL differ               */
 #define MDBCU_P_BOOL    13 /* push boolean literal ival                 */
+#define MDBCU_P_OUT     14 /* HAVING programs only: push result column `col` (an index into plan.out) of the candidate row */
 
 struct mdbcu_pred_op {
 	int32_t op;
@@ -194,6 +197,22 @@ struct mdbcu_plan {
 	int32_t n_out;
 	struct mdbcu_out out[MDBCU_MAX_OUT];
 	uint32_t flags;
+	/* Tail operators on the result rows.  The reference's grammar accepts them (DISTINCT midorisql.y:203, HAVING :180,
+	 * ORDER BY :183-191, LIMIT :193-196) and its semantic phase validates them (semantic_select.c:1895,2004), but its
+	 * executor never runs them (`TODO process distinct`, executor_select.c:1723): there is no reference
+	 * behaviour to match, the semantics are SQL's as sqlite3 implements them (the oracle is anchored on it).  Applied in
+	 * this order: HAVING, DISTINCT, ORDER BY, LIMIT.  All-zero = none.  Not available in MDBCU_PLAN_DISTRIBUTED plans. */
+	int32_t distinct;                               /* SELECT DISTINCT: one row per distinct combination of ALL output columns (NULL = NULL) */
+	int32_t n_having;                               /* HAVING: postfix program over the result row, columns pushed with MDBCU_P_OUT */
+	struct mdbcu_pred_op having[MDBCU_MAX_HAVING];
+	int32_t n_order;                                /* ORDER BY: result columns, most significant first; NULLs first when ascending, */
+	struct mdbcu_order {                            /* last when descending; ties keep no particular order                              */
+		int32_t out_col;                        /* index into plan.out */
+		int32_t desc;
+	} order[MDBCU_MAX_ORDER];
+	int32_t has_limit;                              /* LIMIT [offset,] count */
+	int32_t _pad2;
+	int64_t limit, offset;
 };
 
 /* replaces: executor_run_select_stmt's data path (proc_from_clause :1345, proc_where_clause :1435,

@@ -16,9 +16,9 @@ LIB_PATH = os.path.join(HERE, "libmidoridb_cuda.so")
 OK, EERROR, EINTERNAL, ENOMEM, EUNSUPPORTED, ECUDA = 0, -1, -2, -3, -16, -17
 CT_VARCHAR, CT_INTEGER, CT_TINYINT, CT_DOUBLE, CT_DATE, CT_DATETIME = range(6)
 PAGE_SIZE, ROW_HEADER = 4096, 24
-MAX_TABLES, MAX_PRED, MAX_OUT, MAX_GROUP = 4, 64, 32, 2
+MAX_TABLES, MAX_PRED, MAX_OUT, MAX_GROUP, MAX_HAVING, MAX_ORDER = 4, 64, 32, 2, 16, 4
 
-P_COL, P_INT, P_DBL, P_NULL, P_CMP, P_AND, P_OR, P_XOR, P_ISNULL, P_ISNOTNULL, P_IN, P_NOTIN, P_BOOL = range(1, 14)
+P_COL, P_INT, P_DBL, P_NULL, P_CMP, P_AND, P_OR, P_XOR, P_ISNULL, P_ISNOTNULL, P_IN, P_NOTIN, P_BOOL, P_OUT = range(1, 15)
 CMP_LT, CMP_GT, CMP_NE, CMP_EQ, CMP_LE, CMP_GE = 1, 2, 3, 4, 5, 6
 OUT_COLUMN, OUT_COUNT_STAR, OUT_COUNT_COL, OUT_SUM, OUT_MIN, OUT_MAX, OUT_AVG = range(7)
 PLAN_DISTRIBUTED, PLAN_NO_FASTPATH = 1, 2
@@ -60,13 +60,20 @@ class Out(C.Structure):
     _fields_ = [("kind", C.c_int32), ("ref", ColRef)]
 
 
+class Order(C.Structure):
+    _fields_ = [("out_col", C.c_int32), ("desc", C.c_int32)]
+
+
 class Plan(C.Structure):
     _fields_ = [("n_tables", C.c_int32), ("tables", C.c_void_p * MAX_TABLES),
                 ("n_joins", C.c_int32), ("joins", Join * (MAX_TABLES - 1)),
                 ("n_pred", C.c_int32), ("pred", PredOp * MAX_PRED),
                 ("n_group", C.c_int32), ("group", ColRef * MAX_GROUP),
                 ("n_out", C.c_int32), ("out", Out * MAX_OUT),
-                ("flags", C.c_uint32)]
+                ("flags", C.c_uint32),
+                ("distinct", C.c_int32), ("n_having", C.c_int32), ("having", PredOp * MAX_HAVING),
+                ("n_order", C.c_int32), ("order", Order * MAX_ORDER),
+                ("has_limit", C.c_int32), ("_pad2", C.c_int32), ("limit", C.c_int64), ("offset", C.c_int64)]
 
 
 class Stats(C.Structure):
@@ -478,8 +485,10 @@ def comm_init_local(backends):
     backends[0]._check(backends[0].L.mdbcu_comm_init_local(arr, len(backends)))
 
 
-def make_plan(tables, joins=(), pred=(), group=(), out=(), flags=0):
+def make_plan(tables, joins=(), pred=(), group=(), out=(), flags=0, distinct=False, having=(), order=(), limit=None, offset=0):
     """Build a `struct mdbcu_plan`.
+    having: postfix program like `pred` with ("out", i) = result column i;  order: list of (result column, descending);
+    limit / offset: LIMIT [offset,] count
     tables: list of handles (Table objects, raw pointers or oracle tables exposing `.handle`)
     joins:  list of ((ltbl, lcol), (rtbl, rcol)) or "cross"
     pred:   postfix list of tuples: ("col", tbl, col) ("int", v) ("dbl", v) ("null",) ("bool", v)
@@ -499,19 +508,33 @@ def make_plan(tables, joins=(), pred=(), group=(), out=(), flags=0):
             p.joins[i].left = ColRef(lt, lc)
             p.joins[i].right = ColRef(rt, rc)
     names = {"col": P_COL, "int": P_INT, "dbl": P_DBL, "null": P_NULL, "bool": P_BOOL, "cmp": P_CMP, "and": P_AND,
-             "or": P_OR, "xor": P_XOR, "isnull": P_ISNULL, "isnotnull": P_ISNOTNULL, "in": P_IN, "notin": P_NOTIN}
-    p.n_pred = len(pred)
-    for i, op in enumerate(pred):
-        o = p.pred[i]
+             "or": P_OR, "xor": P_XOR, "isnull": P_ISNULL, "isnotnull": P_ISNOTNULL, "in": P_IN, "notin": P_NOTIN, "out": P_OUT}
+
+    def fill(o, op):
         o.op = names[op[0]]
         if op[0] == "col":
             o.tbl, o.col = op[1], op[2]
+        elif op[0] == "out":
+            o.col = int(op[1])
         elif op[0] in ("int", "bool"):
             o.ival = int(op[1])
         elif op[0] == "dbl":
             o.dval = float(op[1])
         elif op[0] in ("cmp", "in", "notin"):
             o.arg = int(op[1])
+
+    p.n_pred = len(pred)
+    for i, op in enumerate(pred):
+        fill(p.pred[i], op)
+    p.distinct = 1 if distinct else 0
+    p.n_having = len(having)
+    for i, op in enumerate(having):
+        fill(p.having[i], op)
+    p.n_order = len(order)
+    for i, (c, desc) in enumerate(order):
+        p.order[i] = Order(int(c), 1 if desc else 0)
+    if limit is not None:
+        p.has_limit, p.limit, p.offset = 1, int(limit), int(offset)
     p.n_group = len(group)
     for i, (t, c) in enumerate(group):
         p.group[i] = ColRef(t, c)

@@ -347,6 +347,10 @@ int mdb_comm_allgather_u64(mdbcu_ctx *ctx, const uint64_t *send, uint64_t *recv,
 bool mdb_comm_ready(const mdbcu_ctx *ctx);
 int mdb_comm_reduce_owned_u32(mdbcu_ctx *ctx, uint32_t *buf, uint64_t n, int nsides, uint64_t *bytes_sent);
 int mdb_select_direct_count(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res, bool forced);
+// tail operators on the finished result (mdb_tail.cu): HAVING, DISTINCT, ORDER BY, LIMIT
+bool mdb_plan_has_tail(const mdbcu_plan *plan);
+int mdb_validate_tail(mdbcu_ctx *ctx, const mdbcu_plan *plan);
+int mdb_apply_tail(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res);
 
 // phase clock: events are only recorded while the query runs; one synchronise at the end
 struct PhaseClock {

@@ -53,6 +53,7 @@ extern "C" int mdbcu_select(mdbcu_ctx *ctx, const struct mdbcu_plan *plan, mdbcu
 	*out = nullptr;
 	cudaSetDevice(ctx->device);
 	MDB_TRY(validate_plan(ctx, plan));
+	MDB_TRY(mdb_validate_tail(ctx, plan));
 
 	mdbcu_result *res = new (std::nothrow) mdbcu_result();
 	if (!res)
@@ -98,6 +99,8 @@ extern "C" int mdbcu_select(mdbcu_ctx *ctx, const struct mdbcu_plan *plan, mdbcu
 			rc = mdb_select_general(ctx, plan, res);
 		}
 	}
+	if (rc == MDBCU_OK)
+		rc = mdb_apply_tail(ctx, plan, res); // HAVING, DISTINCT, ORDER BY, LIMIT on the device-resident result
 	ctx->stats.total_kernel_launches = ctx->total_launches;
 	ctx->stats.kernel_launches = ctx->total_launches - total_before;
 	mdb_scratch_settle(ctx);

@@ -23,6 +23,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <functional>
 #include <map>
 #include <memory>
 #include <set>
@@ -740,6 +741,7 @@ bool build_tree(Arena &ar, const std::vector<std::string> &toks, size_t first, s
 			Node *a = pop(st);
 			if (!a) goto malformed;
 			n->kids = {a};
+			n->i = atoi(rest.c_str()); // 1 = DESC (opt_asc_desc, midorisql.y:175-178)
 		} else if (starts(t, "ORDERBYLIST", &rest)) {
 			n = ar.make(K_ORDERBY);
 			int cnt = atoi(rest.c_str());
@@ -1289,10 +1291,9 @@ int exec_select(Catalog *cat, const std::vector<std::string> &toks, struct query
 	std::vector<Node*> st;
 	std::string err, rest;
 	size_t sel_tok = toks.size();
-	int nitems = 0;
+	int nitems = 0, distinct = 0;
 	for (size_t k = 0; k < toks.size(); k++) {
 		if (starts(toks[k], "SELECT", &rest)) {
-			int distinct = 0;
 			if (sscanf(rest.c_str(), "%d %d", &distinct, &nitems) != 2) {
 				set_err(out, "error while running syntax analysis on query\n");
 				return -MIDORIDB_ERROR;
@@ -1307,13 +1308,17 @@ int exec_select(Catalog *cat, const std::vector<std::string> &toks, struct query
 
 	// split the SELECT node's children (midorisql.y:157-160)
 	std::vector<Node*> items, froms;
-	Node *where = nullptr, *groupby = nullptr;
+	// HAVING / ORDER BY / LIMIT / DISTINCT: the reference parses and validates them and its executor ignores them (SURVEY.md D6,
+	// executor_select.c:1723); here they run on the device as tail operators of the plan (include/midoridb_cuda.h)
+	Node *where = nullptr, *groupby = nullptr, *having = nullptr, *orderby = nullptr, *limit = nullptr;
 	for (Node *n : st) {
 		switch (n->kind) {
 		case K_TABLE: case K_JOIN: froms.push_back(n); break;
 		case K_WHERE: where = n; break;
 		case K_GROUPBY: groupby = n; break;
-		case K_HAVING: case K_ORDERBY: case K_LIMIT: break; // parsed, validated, not executed - like the reference (D6)
+		case K_HAVING: having = n; break;
+		case K_ORDERBY: orderby = n; break;
+		case K_LIMIT: limit = n; break;
 		default: items.push_back(n); break;
 		}
 	}
@@ -1470,6 +1475,103 @@ int exec_select(Catalog *cat, const std::vector<std::string> &toks, struct query
 		plan.n_out++;
 		names.push_back(key);
 		is_count.push_back(it->second.kind == MDBCU_OUT_COUNT_STAR || it->second.kind == MDBCU_OUT_COUNT_COL);
+	}
+
+	// ---- tail operators: expressions name RESULT columns (a selected column or aggregate), found by their scaffold key
+	auto result_key = [&](const Node *e, std::string *key) -> bool {
+		int t, c;
+		if (e->kind == K_COUNT) {
+			*key = "COUNT(*)";
+			return true;
+		}
+		if (e->kind == K_AGG) {
+			if (!is_colref(e->kids[0]) || !rs.resolve(e->kids[0], &t, &c))
+				return false;
+			*key = e->s + "(" + rs.fq(t, c) + ")";
+			return true;
+		}
+		if (is_colref(e) && rs.resolve(e, &t, &c)) {
+			*key = rs.fq(t, c);
+			return true;
+		}
+		return false;
+	};
+	auto result_col = [&](const Node *e) -> int {
+		std::string key;
+		if (!result_key(e, &key))
+			return -1;
+		for (size_t i = 0; i < names.size(); i++)
+			if (names[i] == key)
+				return (int)i;
+		return -1;
+	};
+	plan.distinct = (distinct & 2) != 0; // select_opts, midorisql.y:203
+	std::function<bool(const Node*)> emit_having = [&](const Node *n) -> bool {
+		auto push = [&](int op, int arg, int col, long long iv, double dv) {
+			if (plan.n_having >= MDBCU_MAX_HAVING)
+				return false;
+			struct mdbcu_pred_op &o = plan.having[plan.n_having++];
+			memset(&o, 0, sizeof(o));
+			o.op = op;
+			o.arg = arg;
+			o.col = col;
+			o.ival = iv;
+			o.dval = dv;
+			return true;
+		};
+		switch (n->kind) {
+		case K_NAME: case K_FIELD: case K_COUNT: case K_AGG: {
+			int c = result_col(n);
+			return c >= 0 && push(MDBCU_P_OUT, 0, c, 0, 0);
+		}
+		case K_INT: return push(MDBCU_P_INT, 0, 0, n->i, 0);
+		case K_BOOL: return push(MDBCU_P_INT, 0, 0, n->i != 0, 0);
+		case K_FLOAT: return push(MDBCU_P_DBL, 0, 0, 0, n->d);
+		case K_NULL: return push(MDBCU_P_NULL, 0, 0, 0, 0);
+		case K_CMP: return emit_having(n->kids[0]) && emit_having(n->kids[1]) && push(MDBCU_P_CMP, (int)n->i, 0, 0, 0);
+		case K_AND: case K_OR: case K_XOR:
+			return emit_having(n->kids[0]) && emit_having(n->kids[1]) &&
+			       push(n->kind == K_AND ? MDBCU_P_AND : n->kind == K_OR ? MDBCU_P_OR : MDBCU_P_XOR, 0, 0, 0, 0);
+		case K_ISNULL: case K_ISNOTNULL:
+			return emit_having(n->kids[0]) && push(n->kind == K_ISNULL ? MDBCU_P_ISNULL : MDBCU_P_ISNOTNULL, 0, 0, 0, 0);
+		case K_IN: case K_NOTIN:
+			for (const Node *k : n->kids)
+				if (!emit_having(k))
+					return false;
+			return push(n->kind == K_IN ? MDBCU_P_IN : MDBCU_P_NOTIN, (int)n->kids.size() - 1, 0, 0, 0);
+		default: return false;
+		}
+	};
+	if (having && !emit_having(having->kids[0])) {
+		set_err(out, "semantic phase: HAVING may compare selected columns / aggregates with literals (at most %d operations)\n", MDBCU_MAX_HAVING);
+		return -MIDORIDB_ERROR;
+	}
+	if (orderby) {
+		if (orderby->kids.size() > MDBCU_MAX_ORDER) {
+			set_err(out, "execution phase: at most %d ORDER BY expressions\n", MDBCU_MAX_ORDER);
+			return -MIDORIDB_ERROR;
+		}
+		for (const Node *it : orderby->kids) {
+			int c = it->kind == K_ORDERITEM ? result_col(it->kids[0]) : -1;
+			if (c < 0) {
+				set_err(out, "semantic phase: ORDER BY expressions must appear in the select list\n");
+				return -MIDORIDB_ERROR;
+			}
+			plan.order[plan.n_order].out_col = c;
+			plan.order[plan.n_order].desc = it->i != 0;
+			plan.n_order++;
+		}
+	}
+	if (limit) {
+		// LIMIT count | LIMIT offset, count (opt_limit, midorisql.y:193-196)
+		for (const Node *k : limit->kids)
+			if (k->kind != K_INT || k->i < 0) {
+				set_err(out, "semantic phase: LIMIT needs non-negative integer literals\n");
+				return -MIDORIDB_ERROR;
+			}
+		plan.has_limit = 1;
+		plan.limit = limit->kids.back()->i;
+		plan.offset = limit->kids.size() == 2 ? limit->kids[0]->i : 0;
 	}
 
 	for (size_t t = 0; t < rs.tables.size(); t++) {

@@ -585,6 +585,204 @@ static int group_key(const struct mdbcu_plan *plan, const struct tuples *ts, siz
 	return 0;
 }
 
+
+/* ------------------------------------------------------------------ tail operators: HAVING, DISTINCT, ORDER BY, LIMIT
+ * The reference parses and validates them (src/parser/midorisql.y:180-196,203; semantic_select.c:1895,2004) and never
+ * executes them (executor_select.c:1723): PARITY UNPINNED BY THE REFERENCE.  The semantics restated here
+ * are SQL's as sqlite3 implements them - tests/test_oracle.py checks this code against sqlite3 itself:
+ *   HAVING    filters result rows; a comparison with a NULL operand is not true;
+ *   DISTINCT  one row per combination of ALL result columns, NULL equal to NULL, -0.0 equal to 0.0;
+ *   ORDER BY  NULLs first ascending / last descending; ties in no particular order (this code: stable);
+ *   LIMIT     [offset,] count, applied last. */
+static struct val res_val(const struct orc_result *r, int c, size_t row)
+{
+	struct val v;
+	memset(&v, 0, sizeof(v));
+	if (r->nulls[c][row]) {
+		v.kind = 2;
+	} else if (is_dbl_type(r->types[c])) {
+		v.kind = 1;
+		memcpy(&v.d, &r->cells[c][row], 8);
+	} else {
+		v.kind = 0;
+		v.i = r->cells[c][row];
+	}
+	return v;
+}
+
+static int eval_having(const struct mdbcu_plan *plan, const struct orc_result *r, size_t row)
+{
+	struct val st[MDBCU_MAX_HAVING + 1];
+	int sp = 0;
+	for (int k = 0; k < plan->n_having; k++) {
+		const struct mdbcu_pred_op *op = &plan->having[k];
+		struct val v;
+		memset(&v, 0, sizeof(v));
+		v.kind = 3;
+		switch (op->op) {
+		case MDBCU_P_OUT: st[sp++] = res_val(r, op->col, row); break;
+		case MDBCU_P_INT: v.kind = 0; v.i = op->ival; st[sp++] = v; break;
+		case MDBCU_P_DBL: v.kind = 1; v.d = op->dval; st[sp++] = v; break;
+		case MDBCU_P_NULL: v.kind = 2; st[sp++] = v; break;
+		case MDBCU_P_BOOL: v.i = op->ival != 0; st[sp++] = v; break;
+		case MDBCU_P_CMP: {
+			struct val b = st[--sp], a = st[--sp];
+			v.i = cmp_vals(op->arg, a, b);
+			st[sp++] = v;
+			break;
+		}
+		case MDBCU_P_AND: case MDBCU_P_OR: case MDBCU_P_XOR: {
+			struct val b = st[--sp], a = st[--sp];
+			int x = a.i != 0, y = b.i != 0;
+			v.i = op->op == MDBCU_P_AND ? (x && y) : (op->op == MDBCU_P_OR ? (x || y) : (x != y));
+			st[sp++] = v;
+			break;
+		}
+		case MDBCU_P_ISNULL: case MDBCU_P_ISNOTNULL: {
+			struct val a = st[--sp];
+			v.i = (a.kind == 2) != (op->op == MDBCU_P_ISNOTNULL);
+			st[sp++] = v;
+			break;
+		}
+		case MDBCU_P_IN: case MDBCU_P_NOTIN: {
+			int n = op->arg, any = 0, all_diff = 1;
+			struct val probe = st[sp - n - 1];
+			for (int j = 0; j < n; j++) {
+				any = any || cmp_vals(4, probe, st[sp - n + j]);
+				all_diff = all_diff && cmp_vals(3, probe, st[sp - n + j]);
+			}
+			sp -= n + 1;
+			v.i = op->op == MDBCU_P_IN ? any : all_diff;
+			st[sp++] = v;
+			break;
+		}
+		}
+	}
+	return sp == 1 && st[0].i != 0;
+}
+
+/* three-way comparison of two result cells of column c: NULL sorts before every value */
+static int cmp_cells(const struct orc_result *r, int c, size_t a, size_t b)
+{
+	int na = r->nulls[c][a], nb = r->nulls[c][b];
+	if (na || nb)
+		return nb - na; /* NULL < value; NULL = NULL */
+	if (is_dbl_type(r->types[c])) {
+		double x, y;
+		memcpy(&x, &r->cells[c][a], 8);
+		memcpy(&y, &r->cells[c][b], 8);
+		return x < y ? -1 : (x > y ? 1 : 0);
+	}
+	return r->cells[c][a] < r->cells[c][b] ? -1 : (r->cells[c][a] > r->cells[c][b] ? 1 : 0);
+}
+
+struct sort_spec {
+	const struct orc_result *r;
+	int ncols;
+	int col[MDBCU_MAX_OUT];
+	int desc[MDBCU_MAX_OUT];
+};
+
+static int cmp_rows(const struct sort_spec *sp, size_t a, size_t b)
+{
+	for (int k = 0; k < sp->ncols; k++) {
+		int c = cmp_cells(sp->r, sp->col[k], a, b);
+		if (c)
+			return sp->desc[k] ? -c : c; /* descending: values reversed, NULLs last */
+	}
+	return 0;
+}
+
+/* stable merge sort of row numbers */
+static int sort_rows(const struct sort_spec *sp, size_t *idx, size_t n)
+{
+	size_t *tmp = malloc((n ? n : 1) * sizeof(*tmp));
+	if (!tmp)
+		return -1;
+	for (size_t w = 1; w < n; w *= 2) {
+		for (size_t lo = 0; lo < n; lo += 2 * w) {
+			size_t mid = lo + w < n ? lo + w : n, hi = lo + 2 * w < n ? lo + 2 * w : n, i = lo, j = mid, k = lo;
+			while (i < mid && j < hi)
+				tmp[k++] = cmp_rows(sp, idx[j], idx[i]) < 0 ? idx[j++] : idx[i++];
+			while (i < mid)
+				tmp[k++] = idx[i++];
+			while (j < hi)
+				tmp[k++] = idx[j++];
+		}
+		memcpy(idx, tmp, n * sizeof(*idx));
+	}
+	free(tmp);
+	return 0;
+}
+
+static int apply_tail(const struct mdbcu_plan *plan, struct orc_result *r)
+{
+	size_t n = r->nrows, m = 0;
+	size_t *idx = malloc((n ? n : 1) * sizeof(*idx));
+	struct sort_spec sp;
+	if (!idx)
+		return -1;
+	for (size_t i = 0; i < n; i++)
+		if (plan->n_having == 0 || eval_having(plan, r, i))
+			idx[m++] = i;
+	n = m;
+	memset(&sp, 0, sizeof(sp));
+	sp.r = r;
+	if (plan->distinct && n > 1) {
+		sp.ncols = r->ncols;
+		for (int c = 0; c < r->ncols; c++)
+			sp.col[c] = c;
+		if (sort_rows(&sp, idx, n)) {
+			free(idx);
+			return -1;
+		}
+		m = 1;
+		for (size_t i = 1; i < n; i++)
+			if (cmp_rows(&sp, idx[i], idx[m - 1]) != 0)
+				idx[m++] = idx[i];
+		n = m;
+	}
+	if (plan->n_order > 0) {
+		memset(&sp, 0, sizeof(sp));
+		sp.r = r;
+		sp.ncols = plan->n_order;
+		for (int k = 0; k < plan->n_order; k++) {
+			sp.col[k] = plan->order[k].out_col;
+			sp.desc[k] = plan->order[k].desc != 0;
+		}
+		if (sort_rows(&sp, idx, n)) {
+			free(idx);
+			return -1;
+		}
+	}
+	size_t first = 0, count = n;
+	if (plan->has_limit) {
+		first = (size_t)plan->offset < n ? (size_t)plan->offset : n;
+		count = (size_t)plan->limit < n - first ? (size_t)plan->limit : n - first;
+	}
+	for (int c = 0; c < r->ncols; c++) {
+		int64_t *nc = malloc((count ? count : 1) * 8);
+		uint8_t *nn = malloc(count ? count : 1);
+		if (!nc || !nn) {
+			free(nc);
+			free(nn);
+			free(idx);
+			return -1;
+		}
+		for (size_t i = 0; i < count; i++) {
+			nc[i] = r->cells[c][idx[first + i]];
+			nn[i] = r->nulls[c][idx[first + i]];
+		}
+		free(r->cells[c]);
+		free(r->nulls[c]);
+		r->cells[c] = nc;
+		r->nulls[c] = nn;
+	}
+	r->nrows = count;
+	free(idx);
+	return 0;
+}
+
 void orc_result_free(struct orc_result *res);
 
 int orc_select(const struct mdbcu_plan *plan, struct orc_result **out_res)
@@ -723,6 +921,9 @@ int orc_select(const struct mdbcu_plan *plan, struct orc_result **out_res)
 			emit_row(plan, &cur, i, st, res, i);
 	}
 
+	if (plan->distinct || plan->n_having > 0 || plan->n_order > 0 || plan->has_limit)
+		if (apply_tail(plan, res))
+			goto nomem;
 	*out_res = res;
 	res = NULL;
 	rc = MDBCU_OK;

@@ -629,3 +629,71 @@ def test_radix_joincount_large_against_numpy(be, log2_rows):
     assert int(cnts.sum()) == int(expect.sum())  # = the join's cardinality
     ta.drop()
     tb.drop()
+
+
+def _tail_cases():
+    from tests.test_oracle import TAIL_CASES
+    return TAIL_CASES
+
+
+@pytest.mark.parametrize("case", _tail_cases(), ids=[c[0] for c in _tail_cases()])
+def test_tail_operators_match_oracle(be, case):
+    """HAVING / DISTINCT / ORDER BY / LIMIT on the device-resident result (mdb_tail.cu) against the oracle, whose semantics
+    are pinned to sqlite3 (tests/test_oracle.py); ordered cases are compared row by row, in order"""
+    from tests.test_oracle import tail_tables
+    name, kw, _, ordered = case
+    a_rows, b_rows = tail_tables()
+
+    def cols(rows, dbl):
+        k = np.array([r[0] for r in rows], dtype=np.int64)
+        v = np.array([0 if r[1] is None else r[1] for r in rows], dtype=np.float64 if dbl else np.int64)
+        return [k, v], [None, np.array([r[1] is None for r in rows], dtype=np.uint8)]
+
+    (ca, na), (cb, nb) = cols(a_rows, True), cols(b_rows, False)
+    ga, oa = both_tables(be, [I, D], ca, na)
+    gb, ob = both_tables(be, [I, I], cb, nb)
+    gt, ot = ([ga, gb], [oa, ob]) if kw.get("joins") else ([ga], [oa])
+    for flags in (0, PLAN_NO_FASTPATH):
+        grows, orows, pages, st = run_both(be, gt, ot, flags=flags, **kw)
+        if ordered:
+            assert helpers.rows_close([helpers.norm_row(r) for r in grows], [helpers.norm_row(r) for r in orows])
+            # the page images carry the same order (what query_cur_step walks)
+            cells, nulls = capi.unpack_pages(pages, len(kw["out"]))
+            assert cells.shape[0] == len(orows)
+        else:
+            assert helpers.canon_close(grows, orows)
+    for t in (ga, gb):
+        t.drop()
+
+
+def test_tail_operators_large_result(be):
+    """ORDER BY / LIMIT / DISTINCT / HAVING on a 2^20-row result of the radix path: top-k by count, then by key"""
+    rng = np.random.default_rng(123)
+    n = 1 << 20
+    a, b = rng.integers(0, n // 4, n), rng.integers(0, n // 4, n)
+    ga, gb = be.create_table("A", [I]), be.create_table("B", [I])
+    ga.append_columns([a])
+    gb.append_columns([b])
+    base = dict(joins=[((0, 0), (1, 0))], group=[(0, 0)], out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)])
+    ca, cb = np.bincount(a, minlength=n // 4), np.bincount(b, minlength=n // 4)
+    prod = ca * cb
+    keys = np.flatnonzero(prod)
+    res = be.select(capi.make_plan([ga, gb], order=[(1, True), (0, False)], limit=1000, **base))
+    assert be.stats().path == capi.PATH_RADIX_JOINCOUNT
+    (k, c), _ = res.fetch_columns()
+    res.free()
+    order = np.lexsort((keys, -prod[keys]))[:1000]
+    assert np.array_equal(k, keys[order]) and np.array_equal(c, prod[keys][order])
+    # HAVING COUNT(*) >= 40 ORDER BY key DESC
+    res = be.select(capi.make_plan([ga, gb], having=[("out", 1), ("int", 40), ("cmp", 6)], order=[(0, True)], **base))
+    (k, c), _ = res.fetch_columns()
+    res.free()
+    want = keys[prod[keys] >= 40][::-1]
+    assert np.array_equal(k, want) and np.array_equal(c, prod[want])
+    # DISTINCT over the counts alone
+    res = be.select(capi.make_plan([ga, gb], joins=base["joins"], group=base["group"], out=[(OUT_COUNT_STAR,)], distinct=True, order=[(0, False)]))
+    (c,), _ = res.fetch_columns()
+    res.free()
+    assert np.array_equal(c, np.unique(prod[keys]))
+    for t in (ga, gb):
+        t.drop()
