@@ -12,6 +12,8 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "_ref", "libmidoridb_ref.so")
+# the same reference objects with executor_run_select_stmt redirected to this repo's CUDA backend (oracle/ref_gpu_bridge.c)
+GPU_LIB_PATH = os.path.join(HERE, "_ref", "libmidoridb_ref_gpu.so")
 
 # enum COLUMN_TYPE, include/primitive/column.h:17-25
 CT_VARCHAR, CT_INTEGER, CT_TINYINT, CT_DOUBLE, CT_DATE, CT_DATETIME = range(6)
@@ -19,17 +21,21 @@ CT_VARCHAR, CT_INTEGER, CT_TINYINT, CT_DOUBLE, CT_DATE, CT_DATETIME = range(6)
 ST_OK_WITH_RESULTS, ST_OK_EXECUTED, ST_ERROR = range(3)
 MIDORIDB_OK, MIDORIDB_ROW = 0, 4
 
-_lib = None
+_libs = {}
 
 
 def available():
     return os.path.exists(LIB_PATH)
 
 
-def lib():
-    global _lib
+def gpu_bridge_available():
+    return os.path.exists(GPU_LIB_PATH)
+
+
+def lib(path=LIB_PATH):
+    _lib = _libs.get(path)
     if _lib is None:
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         vp = C.c_void_p
         L.refh_database_new.restype = vp
         L.refh_database_free.argtypes = [vp]
@@ -72,7 +78,9 @@ def lib():
         L.refh_output_table.argtypes = [vp]
         L.refh_output_results.restype = vp
         L.refh_output_results.argtypes = [vp]
-        _lib = L
+        if path == GPU_LIB_PATH:
+            L.refh_select_backend.restype = C.c_char_p
+        _libs[path] = _lib = L
     return _lib
 
 
@@ -93,8 +101,9 @@ class RefResult:
 class RefDatabase:
     """The reference engine behind its own public C API."""
 
-    def __init__(self):
-        self.L = lib()
+    def __init__(self, gpu_bridge=False):
+        """gpu_bridge: the reference with its SELECT executor replaced by libmidoridb_cuda.so (oracle/ref_gpu_bridge.c)"""
+        self.L = lib(GPU_LIB_PATH if gpu_bridge else LIB_PATH)
         self.db = self.L.refh_database_new()
         if not self.db:
             raise RuntimeError("database_open failed")
