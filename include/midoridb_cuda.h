@@ -292,14 +292,15 @@ int mdbcu_comm_init_local(mdbcu_ctx *const *ctxs, int world);
 int mdbcu_table_sync_stats(mdbcu_table *t);
 
 /* How a distributed radix join (join + GROUP BY join key + COUNT(*)) lays out its exchange; pure host arithmetic, usable
- * without a device (tests).  Rank r owns partitions [part_first[r], part_first[r + 1]); every rank's arena holds, per
- * join side, one slot per source rank with the streams of the partitions the arena's owner owns. */
+ * without a device (tests).  Rank r owns partitions [part_first[r], part_first[r + 1]).  Every rank's arena holds, per
+ * query half and join side, the streams pass 1 produced from the rank's own shard for ALL partitions; the owner of a
+ * partition reads them from every rank's arena. */
 struct mdbcu_dist_layout {
-	uint32_t part_first[9];       /* world + 1 entries */
+	uint32_t part_first[9];        /* world + 1 entries */
 	uint32_t stream_cap, tail_cap; /* entries per partition in the main / tail stream (identical on every rank) */
-	uint32_t owned_max;           /* partitions a slot has room for */
-	uint64_t slot_main_off, slot_tail_off, slot_cursor_off, slot_tail_cursor_off, slot_bytes;
-	uint64_t arena_half_bytes;    /* one of the two halves alternate queries use */
+	uint32_t _pad;
+	uint64_t region_main_off, region_tail_off, region_cursor_off, region_bytes; /* one join side inside an arena half */
+	uint64_t arena_half_bytes;     /* one of the two halves alternate queries use */
 };
 int mdbcu_dist_describe(int nparts, int world, uint64_t global_rows, int sms, struct mdbcu_dist_layout *out);
 int mdbcu_dist_owner(uint32_t partition, int nparts, int world); /* rank that owns `partition`, -1 if out of range */

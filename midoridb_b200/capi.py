@@ -84,9 +84,9 @@ class Stats(C.Structure):
 
 
 class DistLayout(C.Structure):
-    _fields_ = [("part_first", C.c_uint32 * 9), ("stream_cap", C.c_uint32), ("tail_cap", C.c_uint32), ("owned_max", C.c_uint32),
-                ("slot_main_off", C.c_uint64), ("slot_tail_off", C.c_uint64), ("slot_cursor_off", C.c_uint64),
-                ("slot_tail_cursor_off", C.c_uint64), ("slot_bytes", C.c_uint64), ("arena_half_bytes", C.c_uint64)]
+    _fields_ = [("part_first", C.c_uint32 * 9), ("stream_cap", C.c_uint32), ("tail_cap", C.c_uint32), ("_pad", C.c_uint32),
+                ("region_main_off", C.c_uint64), ("region_tail_off", C.c_uint64), ("region_cursor_off", C.c_uint64),
+                ("region_bytes", C.c_uint64), ("arena_half_bytes", C.c_uint64)]
 
 
 def dist_describe(nparts, world, global_rows, sms=148):

@@ -9,8 +9,8 @@
 //   * mdbcu_comm_init        one process per GPU; NCCL for the plumbing, CUDA IPC maps the arenas;
 //   * mdbcu_comm_init_local  several contexts of ONE process (one host thread each), on different GPUs or - the
 //                            loop-back mode of SURVEY.md 4.3 - all on the same GPU: a host rendezvous replaces NCCL and
-//                            the peers' arenas are ordinary pointers.  The exchange kernels (k_radix_ship, k_arena_barrier,
-//                            the multi-source pass 2, k_reduce_add_u32) are exactly the ones a multi-process run uses,
+//                            the peers' arenas are ordinary pointers.  The exchange kernels (k_arena_barrier, the multi-source
+//                            pass 2 reading peer arenas, k_reduce_add_u32) are exactly the ones a multi-process run uses,
 //                            so a single-GPU test box exercises them.
 #include "mdb_common.cuh"
 
@@ -273,7 +273,7 @@ int mdb_comm_allgather_bytes(mdbcu_ctx *ctx, const void *send, void *recv, size_
 // space with CUDA IPC, so a kernel can store straight into the owner GPU's memory over NVLink / NVSwitch.
 // COLLECTIVE: every rank calls it with the same size; the mapping is cached until a larger one is needed.
 
-#define MDB_ARENA_HEADER 256 // bytes in front of every arena: one barrier flag word per source rank
+#define MDB_ARENA_HEADER 256 // bytes in front of every arena: two barrier flag words per source rank (k_arena_barrier)
 
 static void arena_release(mdbcu_ctx *ctx)
 {
@@ -366,11 +366,18 @@ __global__ void k_arena_barrier(ArenaBarrierArgs a, const uint32_t *__restrict__
 	if (r >= a.world)
 		return;
 	const uint32_t mine = (a.epoch << 4) | ((err ? *err : MDB_PEER_ABORT) & 0xfu);
-	__threadfence_system(); // everything this GPU wrote into peer memory before this kernel is visible first
-	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_hdr[r] + a.self), "r"(mine) : "memory");
-	if (!all)
-		return; // abort notice only (mdb_comm_arena_abort): do not wait for anybody
-	const uint32_t *slot = a.peer_hdr[a.self] + r;
+	// two words per source rank, used by alternate epochs: a rank that is already at its NEXT barrier writes the other word,
+	// so the word (and the error bits) of THIS epoch stay readable until every peer has passed it
+	const uint32_t word = (a.epoch & 1u) * MDB_MAX_RANKS;
+	__threadfence_system(); // everything this GPU wrote before this kernel is visible first
+	if (!all) {
+		// abort notice (mdb_comm_arena_abort): both words, and do not wait for anybody
+		asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_hdr[r] + a.self), "r"(mine) : "memory");
+		asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_hdr[r] + MDB_MAX_RANKS + a.self), "r"(mine) : "memory");
+		return;
+	}
+	asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.peer_hdr[r] + word + a.self), "r"(mine) : "memory");
+	const uint32_t *slot = a.peer_hdr[a.self] + word + r;
 	uint32_t v;
 	unsigned long long t0 = 0, now = 0;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -395,19 +402,27 @@ static void arena_barrier_args(mdbcu_ctx *ctx, ArenaBarrierArgs *a)
 	a->timeout_ns = limit_ms * 1000000ull;
 }
 
-int mdb_comm_arena_barrier(mdbcu_ctx *ctx, const uint32_t *d_err, uint32_t *d_all)
+int mdb_comm_arena_barrier_on(mdbcu_ctx *ctx, cudaStream_t stream, const uint32_t *d_err, uint32_t *d_all)
 {
 	if (!ctx->arena_local)
 		return mdb_fail(ctx, MDBCU_EERROR, "arena barrier without an arena");
 	ArenaBarrierArgs a;
 	arena_barrier_args(ctx, &a);
-	MDB_LAUNCH(ctx, k_arena_barrier, 1, 32, 0, a, d_err, d_all);
+	k_arena_barrier<<<1, 32, 0, stream>>>(a, d_err, d_all);
+	ctx->stats.kernel_launches++;
+	ctx->total_launches++;
 	return MDBCU_OK;
 }
 
-// This rank gives up on a distributed query AFTER its peers may have started to wait for it: take the query's barrier
-// epoch anyway and publish MDB_PEER_ABORT in its place, so that the peers' barrier kernels return at once (their pass 2
-// sees the flag and the query fails on every rank) and the epoch counters stay in step for the next query.
+int mdb_comm_arena_barrier(mdbcu_ctx *ctx, const uint32_t *d_err, uint32_t *d_all)
+{
+	return mdb_comm_arena_barrier_on(ctx, ctx->stream, d_err, d_all);
+}
+
+// This rank gives up on a distributed query AFTER its peers may have started to wait for it: publish MDB_PEER_ABORT with the
+// LARGEST epoch in place of every barrier this rank will not reach, so that the peers' barrier kernels return at once (their
+// pass 2 sees the flag, the query fails on every rank) - now and in every later query: like an NCCL communicator after a
+// rank failure, the communicator is unusable from here on, but nobody hangs.
 void mdb_comm_arena_abort(mdbcu_ctx *ctx)
 {
 	if (!ctx->arena_local || ctx->world < 2)
@@ -416,6 +431,8 @@ void mdb_comm_arena_abort(mdbcu_ctx *ctx)
 	cudaGetLastError();
 	ArenaBarrierArgs a;
 	arena_barrier_args(ctx, &a);
+	a.epoch = 0x0fffffffu;
+	ctx->arena_epoch = 0x0ffffff0u;
 	k_arena_barrier<<<1, 32, 0, ctx->stream>>>(a, nullptr, nullptr);
 	cudaStreamSynchronize(ctx->stream);
 	cudaGetLastError();

@@ -34,12 +34,13 @@ struct mdbcu_ctx {
 	int rank = 0, world = 1;
 	void *nccl_comm = nullptr;
 	struct mdb_local_group *local_group = nullptr; // in-process communicator (mdbcu_comm_init_local), see mdb_comm.cu
-	// exchange arena of the multi-GPU radix join: own block + every peer's block mapped with CUDA IPC
+	// exchange arena of the multi-GPU radix join (pass 1 writes its streams here, the peers' pass 2 reads them): own block +
+	// every peer's block (CUDA IPC between processes, plain pointers inside one process)
 	void *arena_local = nullptr;
 	size_t arena_bytes = 0;
 	void *arena_peer[MDB_MAX_RANKS] = {};
 	uint32_t arena_epoch = 0;  // barriers passed on the arena's flag words (mdb_comm_arena_barrier)
-	cudaStream_t side_stream = nullptr; // multi-GPU: the push of one join side runs here while pass 1 of the other side runs
+	cudaStream_t side_stream = nullptr; // multi-GPU: side A's streams are fetched from the peers here while pass 1 of side B runs
 	cudaEvent_t side_ev[2] = {};
 	uint32_t arena_queries = 0; // distributed queries so far: alternate queries use alternate halves of the arena
 	bool radix_attr_done = false; // dynamic shared-memory limits of the radix kernels raised on this context's device
@@ -341,6 +342,7 @@ void mdb_comm_destroy(mdbcu_ctx *ctx);
 int mdb_comm_allgather_bytes(mdbcu_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);
 int mdb_comm_arena(mdbcu_ctx *ctx, size_t bytes, void **bases);
 int mdb_comm_arena_barrier(mdbcu_ctx *ctx, const uint32_t *d_err, uint32_t *d_all);
+int mdb_comm_arena_barrier_on(mdbcu_ctx *ctx, cudaStream_t stream, const uint32_t *d_err, uint32_t *d_all);
 void mdb_comm_arena_destroy(mdbcu_ctx *ctx);
 void mdb_comm_arena_abort(mdbcu_ctx *ctx);
 int mdb_comm_allgather_u64(mdbcu_ctx *ctx, const uint64_t *send, uint64_t *recv, size_t count);

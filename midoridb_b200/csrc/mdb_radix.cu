@@ -7,7 +7,8 @@
 //
 //   pass 1  k_radix_partition   streams the 8-byte keys ONCE and appends 2-byte remainders to per-partition
 //                               streams (partition = (key - kmin) / width, <= 4096 partitions of <= 65536 key values);
-//   (ship)  k_radix_ship        multi-GPU plans only: push the streams of the partitions a peer owns over NVLink;
+//   (barrier)                   multi-GPU plans only: the streams live in an arena every peer has mapped; pass 2 of the rank
+//                               that owns a partition reads all ranks' streams of it over NVLink (mdb_radix_dist.cuh);
 //   pass 2  k_radix_joincount   per partition: both sides' remainders -> packed 4- or 8-bit counters in shared
 //                               memory, checksum against the number of remainders, multiply, emit groups.
 //
@@ -30,8 +31,8 @@ static bool col_all_present(const mdbcu_table *t, int col)
 #include "mdb_radix_dist.cuh"
 #include "mdb_radix_sorted.cuh"
 
-// dynamic shared memory the side-stream push asks for: it is not used, it makes a push CTA own its SM so that the
-// push takes push_sms SMs and pass 1 of the other side gets all the others
+// dynamic shared memory the push kernel asks for: it is not used, it makes a push CTA own its SM, so that the push takes
+// push_sms SMs and pass 1 of the other side gets all the others
 #define RJ_SHIP_SMEM (160 * 1024)
 
 // entries one partition's main stream can hold: twice the average (uniform keys fill half of it; a partition that
@@ -43,9 +44,18 @@ static uint32_t rj_stream_cap(uint64_t rows, int nparts)
 	return (uint32_t)std::min<uint64_t>(cap, 0x7fffffc0ull);
 }
 
+// tail sectors (16 entries each) a partition has room for: one per CTA for the partial staging rows at the end of pass 1, one
+// per key that found its staging row full (about 1 in 1000 on uniform keys): 1/16 of the main capacity on top
+static uint32_t rj_tail_cap(int grid, uint32_t cap)
+{
+	return ((uint32_t)grid * RJ_FLUSH + cap / 16 + 15u) & ~15u;
+}
+
 // cursors: RJ_MAX_PART * RJ_CUR_STRIDE zeroed words inside the query's control block
+// `region` != nullptr (multi-GPU plans): the streams and the cursors live in this rank's exchange arena, at the offsets of
+// rj_region_layout, where the peers' pass 2 reads them over NVLink; otherwise they are query temporaries.
 static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_table *t, int col, int grid, int nparts, uint32_t cap,
-		uint32_t *cursors)
+		uint32_t *cursors, char *region = nullptr)
 {
 	memset(s, 0, sizeof(*s));
 	s->keys = t->cols[col].data;
@@ -54,14 +64,20 @@ static int rj_side_setup(mdbcu_ctx *ctx, DevTemp &tmp, RJSide *s, const mdbcu_ta
 	static const uint32_t hints = getenv("MDBCU_P1_HINTS") ? (uint32_t)atoi(getenv("MDBCU_P1_HINTS")) : RJ_HINT_DEFAULT;
 	s->hints = hints;
 	s->cap = cap;
-	// tail sectors (16 entries each): one per CTA and partition for the partial staging rows at the end of pass 1, one
-	// per key that found its staging row full (about 1 in 1000 on uniform keys): 1/16 of the main capacity on top
-	s->tail_cap = ((uint32_t)grid * RJ_FLUSH + cap / 16 + 15u) & ~15u;
+	s->tail_cap = rj_tail_cap(grid, cap);
 	if ((uint64_t)nparts * cap >= (1ull << 40))
 		return MDBCU_EUNSUPPORTED;
-	MDB_TRY(tmp.alloc(&s->stream, (size_t)nparts * cap));
-	MDB_TRY(tmp.alloc(&s->tail, (size_t)nparts * s->tail_cap));
-	s->cursor = cursors;
+	if (region) {
+		const RJRegionLayout l = rj_region_layout((uint32_t)nparts, cap, s->tail_cap);
+		s->stream = (uint16_t*)(region + l.main);
+		s->tail = (uint16_t*)(region + l.tail);
+		s->cursor = (uint32_t*)(region + l.cursor);
+		CUDA_TRY(ctx, cudaMemsetAsync(s->cursor, 0, (size_t)RJ_MAX_PART * RJ_CUR_STRIDE * sizeof(uint32_t), ctx->stream));
+	} else {
+		MDB_TRY(tmp.alloc(&s->stream, (size_t)nparts * cap));
+		MDB_TRY(tmp.alloc(&s->tail, (size_t)nparts * s->tail_cap));
+		s->cursor = cursors;
+	}
 	s->tail_cursor = s->cursor + 1;
 	return MDBCU_OK;
 }
@@ -229,10 +245,34 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	CUDA_TRY(ctx, cudaMemsetAsync(ctl, 0, (ctl_head + 2 * cursor_words) * sizeof(uint32_t), ctx->stream));
 	memset(&sa, 0, sizeof(sa));
 	memset(&sb, 0, sizeof(sb));
+	// Multi-GPU plans: every rank partitions ITS shard into streams inside its own exchange arena (one cudaMalloc block per
+	// rank, mapped into all peers: CUDA IPC between processes, plain pointers inside one process); after ONE cross-rank
+	// barrier the owner of a partition has side A's runs in local slots (pushed by the peers' k_radix_ship on a few SMs while
+	// pass 1 of side B still ran) and reads side B's runs out of all W arenas in pass 2 itself - every byte crosses
+	// NVLink under cover of some computation (mdb_radix_dist.cuh).  Alternate queries use alternate halves of the arena: a peer that is still reading this query's streams is never overtaken by the
+	// next query's pass 1 (the barrier after pass 2 orders query k before query k + 2).
+	void *bases[MDB_MAX_RANKS] = {};
+	size_t half_off = 0, side_b_off = 0, slots_off = 0;
+	const bool multi_gpu = dist && W > 1;
+	const uint32_t pown = (uint32_t)((nparts + W - 1) / W) + 1; // partitions a rank owns at most
+	if (multi_gpu) {
+		// one half of the arena: [side A's streams | side B's streams | W slots that receive the peers' side-A runs]
+		const uint32_t tc_a = rj_tail_cap(grid1, cap_a), tc_b = rj_tail_cap(grid1, cap_b);
+		const RJRegionLayout la = rj_region_layout((uint32_t)nparts, cap_a, tc_a), lb = rj_region_layout((uint32_t)nparts, cap_b, tc_b);
+		const RJSlotLayout ls = rj_slot_layout(pown, cap_a, tc_a);
+		const size_t half_bytes = la.bytes + lb.bytes + ls.bytes * (size_t)W;
+		MDB_TRY(mdb_comm_arena(ctx, 2 * half_bytes, bases));
+		guard.armed = true; // (the arena exists from here on, if it did not before)
+		half_off = (arena_query & 1u) ? half_bytes : 0;
+		side_b_off = la.bytes;
+		slots_off = la.bytes + lb.bytes;
+	}
 	if (!sorted_a)
-		MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, nparts, cap_a, ctl + ctl_head));
+		MDB_TRY(rj_side_setup(ctx, tmp, &sa, ta, jn.left.col, grid1, nparts, cap_a, ctl + ctl_head,
+				multi_gpu ? (char*)bases[me] + half_off : nullptr));
 	if (!sorted_b)
-		MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, nparts, cap_b, ctl + ctl_head + cursor_words));
+		MDB_TRY(rj_side_setup(ctx, tmp, &sb, tb, jn.right.col, grid1, nparts, cap_b, ctl + ctl_head + cursor_words,
+				multi_gpu ? (char*)bases[me] + half_off + side_b_off : nullptr));
 	sa.all_in_range = ca.imin >= kmin && ca.imax <= kmax;
 	sb.all_in_range = cb.imin >= kmin && cb.imax <= kmax;
 	pr.kmin = kmin;
@@ -242,7 +282,7 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	pr.nparts = nparts;
 	pr.part_first = (int)rj_part_first((uint32_t)me, (uint32_t)nparts, (uint32_t)W);
 	pr.part_end = (int)rj_part_first((uint32_t)me + 1u, (uint32_t)nparts, (uint32_t)W);
-	unsigned long long *d_cursor = reinterpret_cast<unsigned long long*>(ctl); // [0] groups emitted, [1] bytes pushed to peers
+	unsigned long long *d_cursor = reinterpret_cast<unsigned long long*>(ctl); // [0] groups emitted, [1] bytes read from peers
 	uint32_t *d_flags = ctl + 4;                                                // [0] error flags, [1] partition counter
 	pr.error_flag = d_flags;
 	pr.peer_flags = nullptr;
@@ -271,55 +311,48 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	};
 	MDB_TRY(runs_of(&ra, sa, sorted_a, ta, jn.left.col));
 	MDB_TRY(runs_of(&rb, sb, sorted_b, tb, jn.right.col));
-	RJShip ship_a, ship_b;
-	if (dist && W > 1) {
-		// arena of every rank: [side A: W slots][side B: W slots]; slot s receives what rank s pushes
-		const uint32_t pown = (uint32_t)((nparts + W - 1) / W) + 1;
-		const RJSlotLayout la = rj_slot_layout(pown, sa.cap, sa.tail_cap), lb = rj_slot_layout(pown, sb.cap, sb.tail_cap);
-		// two halves used by alternate queries: a peer that is already pushing for the next query writes into the
-		// half this rank is NOT reading, so one cross-rank barrier per query (after the push) is enough
-		void *bases[MDB_MAX_RANKS];
-		const size_t half_bytes = (la.bytes + lb.bytes) * (size_t)W;
-		MDB_TRY(mdb_comm_arena(ctx, 2 * half_bytes, bases));
-		guard.armed = true; // (the arena exists from here on, if it did not before)
-		const size_t half_off = (arena_query & 1u) ? half_bytes : 0;
-		auto fill = [&](RJShip *sh, RJRuns *r, const RJSlotLayout &l, size_t side_off) {
-			memset(sh, 0, sizeof(*sh));
-			sh->world = W;
-			sh->self = me;
-			sh->nparts = nparts;
-			sh->shipped_bytes = d_cursor + 1;
-			const uint16_t *own_stream = r->stream[0], *own_tail = r->tail[0]; // rj_runs_local put them at index 0
-			const uint32_t *own_cursor = r->cursor[0], *own_tail_cursor = r->tail_cursor[0];
-			r->nsrc = W;
-			for (int o = 0; o < W; o++) {
-				// slot [me] of rank o's arena: where this rank pushes to
-				char *dst = (char*)bases[o] + side_off + (size_t)me * l.bytes;
-				sh->main[o] = (uint16_t*)(dst + l.main);
-				sh->tail[o] = (uint16_t*)(dst + l.tail);
-				sh->cursor[o] = (uint32_t*)(dst + l.cursor);
-				sh->tail_cursor[o] = (uint32_t*)(dst + l.tail_cursor);
-				if (o == me) { // source `me` of pass 2 = the local streams, indexed by p
-					r->stream[o] = own_stream;
-					r->tail[o] = own_tail;
-					r->cursor[o] = own_cursor;
-					r->tail_cursor[o] = own_tail_cursor;
-					r->first[o] = 0;
-					r->cur_stride[o] = RJ_CUR_STRIDE;
-					continue;
-				}
-				// slot [o] of this rank's arena: what rank o pushed here
-				const char *src = (const char*)bases[me] + side_off + (size_t)o * l.bytes;
-				r->stream[o] = (const uint16_t*)(src + l.main);
-				r->tail[o] = (const uint16_t*)(src + l.tail);
-				r->cursor[o] = (const uint32_t*)(src + l.cursor);
-				r->tail_cursor[o] = (const uint32_t*)(src + l.tail_cursor);
-				r->first[o] = (uint32_t)pr.part_first;
-				r->cur_stride[o] = 1;
-			}
-		};
-		fill(&ship_a, &ra, la, half_off);
-		fill(&ship_b, &rb, lb, half_off + la.bytes * (size_t)W);
+	RJShip ship;
+	memset(&ship, 0, sizeof(ship));
+	if (multi_gpu) {
+		const RJRegionLayout lb = rj_region_layout((uint32_t)nparts, sb.cap, sb.tail_cap);
+		const RJSlotLayout ls = rj_slot_layout(pown, sa.cap, sa.tail_cap);
+		// side A: source o = the slot of THIS rank's arena that rank o's k_radix_ship fills (partition q = p - first), source
+		// `me` = this rank's own streams; side B: source o = rank o's streams in ITS arena, read over NVLink by pass 2
+		ra.nsrc = rb.nsrc = W;
+		ra.self = rb.self = me;
+		ship.world = W;
+		ship.self = me;
+		ship.nparts = nparts;
+		ship.shipped_bytes = d_cursor + 1;
+		for (int o = 0; o < W; o++) {
+			const char *peer_b = (const char*)bases[o] + half_off + side_b_off;
+			char *there = (char*)bases[o] + half_off + slots_off + (size_t)me * ls.bytes; // slot [me] of rank o's arena: where this rank pushes
+			const char *here = (const char*)bases[me] + half_off + slots_off + (size_t)o * ls.bytes; // slot [o] of this rank's arena
+			rb.stream[o] = (const uint16_t*)(peer_b + lb.main);
+			rb.tail[o] = (const uint16_t*)(peer_b + lb.tail);
+			rb.cursor[o] = (const uint32_t*)(peer_b + lb.cursor);
+			rb.tail_cursor[o] = rb.cursor[o] + 1;
+			rb.first[o] = 0;
+			rb.cur_stride[o] = RJ_CUR_STRIDE;
+			ship.main[o] = (uint16_t*)(there + ls.main);
+			ship.tail[o] = (uint16_t*)(there + ls.tail);
+			ship.cursor[o] = (uint32_t*)(there + ls.cursor);
+			ship.tail_cursor[o] = (uint32_t*)(there + ls.tail_cursor);
+			ra.stream[o] = (const uint16_t*)(here + ls.main);
+			ra.tail[o] = (const uint16_t*)(here + ls.tail);
+			ra.cursor[o] = (const uint32_t*)(here + ls.cursor);
+			ra.tail_cursor[o] = (const uint32_t*)(here + ls.tail_cursor);
+			ra.first[o] = (uint32_t)pr.part_first;
+			ra.cur_stride[o] = 1;
+		}
+		ra.stream[me] = sa.stream;
+		ra.tail[me] = sa.tail;
+		ra.cursor[me] = sa.cursor;
+		ra.tail_cursor[me] = sa.tail_cursor;
+		ra.first[me] = 0;
+		ra.cur_stride[me] = RJ_CUR_STRIDE;
+		ra.pulled_bytes = nullptr; // (side A's bytes are counted by the push kernel)
+		rb.pulled_bytes = d_cursor + 1;
 	}
 
 	// (per context: the attribute belongs to the device, and one process may drive several)
@@ -346,9 +379,10 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	clock.begin(1);
 	if (!sorted_a)
 		launch_partition(ctx, grid1, sa, pr);
-	if (dist && W > 1) {
-		// Side A's streams are pushed to their owners by a few SMs WHILE pass 1 of side B runs on the others (pass 1
-		// is bound by shared memory, not by the SM count: giving up 1/9 of the SMs costs it 12 %, the push of A is free)
+	if (multi_gpu) {
+		// second stream: push side A's streams to their owners.  It takes a few SMs (CTAs that own their SM through a dynamic
+		// shared-memory request) WHILE pass 1 of side B runs on the others: pass 1 is bound by shared memory, not by the SM
+		// count, and loses about an eighth for it
 		if (!ctx->side_stream) {
 			CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->side_stream, cudaStreamNonBlocking));
 			CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->side_ev[0], cudaEventDisableTiming));
@@ -357,17 +391,15 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		const int push_sms = std::max(4, ctx->num_sms / 9);
 		CUDA_TRY(ctx, cudaEventRecord(ctx->side_ev[0], ctx->stream));
 		CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->side_stream, ctx->side_ev[0], 0));
-		k_radix_ship<<<push_sms, 1024, RJ_SHIP_SMEM, ctx->side_stream>>>(sa, ship_a); // one CTA per SM (see RJ_SHIP_SMEM)
+		k_radix_ship<<<push_sms, 1024, RJ_SHIP_SMEM, ctx->side_stream>>>(sa, ship); // one CTA per SM (see RJ_SHIP_SMEM)
 		ctx->stats.kernel_launches++;
 		ctx->total_launches++;
 		CUDA_TRY(ctx, cudaEventRecord(ctx->side_ev[1], ctx->side_stream));
 		launch_partition(ctx, grid1 - push_sms, sb, pr);
-		clock.begin(6);
-		MDB_LAUNCH(ctx, k_radix_ship, ctx->num_sms * 2, 1024, 0, sb, ship_b);
-		CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->side_ev[1], 0));
-		// all pushes have landed once every rank's ship kernels have completed.  The error flags travel with this
-		// barrier and stay on the device: pass 2 checks them itself, the host reads them with the result count
+		// ONE barrier: this rank's side A has landed in the owners' slots and its side B is partitioned.  The error flags
+		// travel with it and stay on the device: pass 2 checks them itself, the host reads them with the result count
 		clock.begin(7);
+		CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->side_ev[1], 0));
 		MDB_TRY(mdb_comm_arena_barrier(ctx, d_flags, d_peer_flags));
 		guard.armed = false; // the barrier is in the stream: the peers get this rank's word
 	} else if (!sorted_b) {
@@ -498,9 +530,9 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 }
 
 // Host-side description of how a distributed radix join lays its exchange out (no device needed): which partitions every
-// rank owns and where a side's streams sit inside an arena slot.  The numbers come from the functions the kernels and
-// mdb_select_radix_joincount use (rj_part_first / rj_owner_of / rj_stream_cap / rj_slot_layout), so the CPU test of the
-// multi-rank arithmetic (tests/test_dist_cpu.py, world_size 2 over gloo) checks the shipped code, not a copy of it.
+// rank owns and where a join side's streams sit inside a rank's arena half.  The numbers come from the functions the kernels
+// and mdb_select_radix_joincount use (rj_part_first / rj_owner_of / rj_stream_cap / rj_tail_cap / rj_region_layout), so the CPU
+// test of the multi-rank arithmetic (tests/test_dist_cpu.py, world_size 2 over gloo) checks the shipped code, not a copy of it.
 extern "C" int mdbcu_dist_describe(int nparts, int world, uint64_t global_rows, int sms, struct mdbcu_dist_layout *out)
 {
 	if (!out || nparts < 1 || nparts > RJ_MAX_PART || world < 1 || world > RJ_MAX_RANKS || sms < 1)
@@ -509,15 +541,13 @@ extern "C" int mdbcu_dist_describe(int nparts, int world, uint64_t global_rows, 
 	for (int r = 0; r <= world; r++)
 		out->part_first[r] = rj_part_first((uint32_t)r, (uint32_t)nparts, (uint32_t)world);
 	out->stream_cap = rj_stream_cap((global_rows + world - 1) / world, nparts);
-	out->tail_cap = ((uint32_t)sms * RJ_FLUSH + out->stream_cap / 16 + 15u) & ~15u;
-	out->owned_max = (uint32_t)((nparts + world - 1) / world) + 1;
-	const RJSlotLayout l = rj_slot_layout(out->owned_max, out->stream_cap, out->tail_cap);
-	out->slot_main_off = l.main;
-	out->slot_tail_off = l.tail;
-	out->slot_cursor_off = l.cursor;
-	out->slot_tail_cursor_off = l.tail_cursor;
-	out->slot_bytes = l.bytes;
-	out->arena_half_bytes = 2 * l.bytes * (size_t)world; // both sides, one slot per source rank (equal row counts per side)
+	out->tail_cap = rj_tail_cap(sms, out->stream_cap);
+	const RJRegionLayout l = rj_region_layout((uint32_t)nparts, out->stream_cap, out->tail_cap);
+	out->region_main_off = l.main;
+	out->region_tail_off = l.tail;
+	out->region_cursor_off = l.cursor;
+	out->region_bytes = l.bytes;
+	out->arena_half_bytes = 2 * l.bytes; // both join sides (equal row counts per side)
 	return MDBCU_OK;
 }
 

@@ -1,21 +1,27 @@
 // mdb_radix_dist.cuh - multi-GPU exchange of the radix join+count (included by mdb_radix.cu).
 //
-// One process per GPU.  Every rank partitions ITS shard of both join sides with pass 1 over the same global key
-// range (mdbcu_table_sync_stats), so partition p means the same key interval everywhere.  Rank r owns the
-// contiguous partition block [r*P/W, (r+1)*P/W): key ranges are disjoint, so after the exchange every rank
-// runs pass 2 on its own partitions and the per-rank results simply concatenate - no merge step.
+// One process (or one context) per GPU.  Every rank partitions ITS shard of both join sides with pass 1 over the same
+// global key range (mdbcu_table_sync_stats), so partition p means the same key interval everywhere.  Rank r owns the
+// contiguous partition block [r*P/W, (r+1)*P/W): key ranges are disjoint, so every rank runs pass 2 on its own
+// partitions and the per-rank results simply concatenate - no merge step.
 //
-// The exchange is a PUSH over NVLink / NVSwitch: every rank's arena (one cudaMalloc block, mapped into all peers
-// with CUDA IPC, mdb_comm.cu) has one slot per source rank; k_radix_ship copies the streams of the partitions a
-// peer owns straight into that peer's slot with 256-bit stores (a warp writes 1 KiB of contiguous remote memory per
-// instruction) together with their entry counts.  What crosses the link is the 2-byte remainders, never the 8-byte keys.
-// The cross-rank barrier (pushes landed + every rank's error flags) is a flag word per source rank in the arena header
-// (k_arena_barrier, mdb_comm.cu); alternate queries use alternate halves of the arena, so one barrier per exchange suffices.
+// The exchange is a PULL over NVLink / NVSwitch: pass 1 writes its streams into the rank's own arena (one cudaMalloc
+// block, mapped into all peers: mdb_comm.cu); after one cross-rank barrier (a flag word per source rank in the arena
+// header, k_arena_barrier) the pass 2 of the rank that owns partition p reads p's runs from all W arenas with the same
+// 256-bit loads it uses locally, all runs of a partition in one index space so that the remote latency is paid once per
+// partition, not once per run (rj_histogram_multi).  What crosses the link is the 2-byte remainders, never the 8-byte keys.
 //
-// Measured on 2 B200s (profiles/): writing every flushed 32-byte sector directly into the owner's memory from inside
-// pass 1 (the first version of this exchange) ran pass 1 at half speed - remote 32-byte stores are bound by the
-// number of stores in flight, not by the link - and a staged NCCL send/recv of gathered chunks took 2-3 ms;
-// the bulk push below moves the same bytes at link speed after a pass 1 that runs at its single-GPU speed.
+// History, all measured on B200s (profiles/): (1) pass 1 storing every flushed 32-byte sector directly into the owner's
+// memory ran at half speed (remote 32-byte stores are bound by the number of stores in flight); (2) a staged NCCL grouped
+// send/recv of gathered chunks took 2-3 ms; (3) a push kernel after pass 1 (one warp per stream, 1 KiB of contiguous
+// remote memory per store instruction) moved the bytes at 450-650 GB/s but stayed exposed on the critical path - 0.135 ms
+// of a 0.70 ms step at 8 GPUs - and cost pass 1 an eighth of the SMs while it overlapped (profiles/r02_scale_push_design_n*.json);
+// (4) everything pulled by pass 2 itself: no copy kernel at all, but pass 2 becomes NVLink-bound (0.57 ms for 281 MB at 2 GPUs)
+// and nothing overlaps pass 1 any more (profiles/r02_pull_n2.json); (5) side A FETCHED by a copy kernel on 16 SMs while pass 1
+// of side B runs: remote loads wait for their round trip, 155 GB/s, the step got slower (profiles/r02_hybrid_fetch_n2.json);
+// (6) this version: side A is PUSHED into the owners' slots by k_radix_ship on 16 SMs while pass 1 of side B runs (stores do
+// not wait: 650 GB/s), side B is PULLED by pass 2 itself - every byte crosses the link under cover of some computation, and
+// one cross-rank barrier per query (after pass 1 of side B) is enough.
 #pragma once
 
 // Partition ownership, the one piece of arithmetic every rank (host and device) must agree on: rank r owns the contiguous
@@ -29,7 +35,25 @@ __host__ __device__ static inline uint32_t rj_owner_of(uint32_t p, uint32_t npar
 	return (uint32_t)((((uint64_t)p + 1) * world - 1) / nparts);
 }
 
-// byte layout of one side inside an arena slot (identical on every rank)
+// byte layout of ONE join side's streams inside a rank's arena half (identical on every rank: stream capacities come from
+// the global row counts): main streams of all partitions, tail streams, then the [main, tail] cursor pairs
+struct RJRegionLayout {
+	size_t main, tail, cursor, bytes;
+};
+
+static RJRegionLayout rj_region_layout(uint32_t nparts, uint32_t cap, uint32_t tail_cap)
+{
+	auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+	RJRegionLayout l;
+	l.main = 0;
+	l.tail = up(l.main + (size_t)nparts * cap * sizeof(uint16_t));
+	l.cursor = up(l.tail + (size_t)nparts * tail_cap * sizeof(uint16_t));
+	l.bytes = up(l.cursor + (size_t)RJ_MAX_PART * RJ_CUR_STRIDE * sizeof(uint32_t));
+	return l;
+}
+
+// Side A's runs of the partitions a rank owns, pushed into its arena by the peers while pass 1 of side B runs: slot o of a
+// rank's arena holds rank o's streams of the partitions the arena's owner owns (partition q = p - first), counts included.
 struct RJSlotLayout {
 	size_t main, tail, cursor, tail_cursor, bytes;
 };
@@ -46,7 +70,7 @@ static RJSlotLayout rj_slot_layout(uint32_t pown, uint32_t cap, uint32_t tail_ca
 	return l;
 }
 
-// where this rank's streams go: for every destination rank the slot [self] of that rank's arena
+// where this rank's side-A streams go: for every destination rank the slot [self] of that rank's arena
 struct RJShip {
 	int world, self, nparts;
 	uint16_t *main[RJ_MAX_RANKS];
@@ -80,9 +104,11 @@ __device__ __forceinline__ void rj_copy_vectors(char *dst, const char *src, uint
 	}
 }
 
-// one WARP per partition owned by a peer (grid-stride over warps: with 8 GPUs a partition's stream is 16 KiB, a CTA
-// per partition would be latency-bound): push its main and tail stream and their counts.  Launched either over the
-// whole GPU or - with enough dynamic shared memory to own an SM - on a handful of SMs next to pass 1 of the other side.
+// one WARP per partition owned by a peer (grid-stride over warps: with 8 GPUs a partition's stream is 16 KiB, a CTA per
+// partition would be latency-bound): push its main and tail stream and their counts into the owner's slot - 256-bit stores,
+// a warp writes 1 KiB of contiguous remote memory per instruction, and stores (unlike loads) do not wait for the round trip:
+// 16 SMs move 650 GB/s this way where the same kernel READING from the peers reached 155 GB/s (profiles/r02_hybrid_fetch_n2.json).
+// Launched with enough dynamic shared memory to own its SMs, next to pass 1 of side B on the others.
 __global__ void __launch_bounds__(1024) k_radix_ship(RJSide s, RJShip sh)
 {
 	const uint32_t warps = blockDim.x >> 5, gw = blockIdx.x * warps + (threadIdx.x >> 5), nw = gridDim.x * warps;

@@ -153,6 +153,90 @@ __device__ __forceinline__ uint32_t rj_histogram_side(const RJRuns &r, const RJP
 	return total;
 }
 
+// Multi-GPU plans: a partition's remainders sit in 2 W short runs per side (main + tail stream of every source rank; with 8
+// GPUs about 16 KiB each).  Walking them one after the other makes every run a round trip of its own - 32 dependent
+// latencies per side and partition, which is what pass 2 cost at 8 GPUs (0.146 ms where 0.08 was its share).  Here the
+// runs of a side are ONE index space: vector g belongs to the run whose prefix interval contains it, so all loads of a
+// thread are independent and MLP of them are in flight whatever run they fall into.
+struct RJRunList {
+	const uint16_t *ptr[2 * RJ_MAX_RANKS];
+	uint32_t end[2 * RJ_MAX_RANKS]; // exclusive prefix end, in 32-byte vectors
+	uint32_t is_tail;               // bit r: run r is a tail stream (count in entry 15 of every sector)
+	uint32_t n;
+};
+
+// (one thread) the runs of partition p on one side, from the counts fetched by rj_fetch_counts; returns the main-stream entries
+__device__ __forceinline__ uint32_t rj_build_run_list(const RJRuns &r, uint32_t p, const uint32_t (*counts)[2], RJRunList *l)
+{
+	uint32_t n = 0, acc = 0, total_main = 0, tails = 0, remote = 0;
+	for (int s = 0; s < r.nsrc; s++) {
+		const uint32_t q = p - r.first[s];
+		const uint32_t n_main = counts[s][0], n_tail = counts[s][1];
+		if (s != r.self)
+			remote += n_main + n_tail;
+		if (n_main) {
+			l->ptr[n] = r.stream[s] + (size_t)q * r.cap;
+			acc += (n_main + 15u) / 16u;
+			l->end[n++] = acc;
+			total_main += n_main;
+		}
+		if (n_tail) {
+			l->ptr[n] = r.tail[s] + (size_t)q * r.tail_cap;
+			acc += (n_tail + 15u) / 16u;
+			tails |= 1u << n;
+			l->end[n++] = acc;
+		}
+	}
+	l->n = n;
+	l->is_tail = tails;
+	if (remote && r.pulled_bytes)
+		atomicAdd(r.pulled_bytes, 2ull * remote);
+	return total_main;
+}
+
+template <int BITS, int THREADS>
+__device__ __forceinline__ void rj_histogram_multi(const RJRunList &l, uint32_t *cnt, uint32_t *tail_total)
+{
+	constexpr int MLP = 4;
+	const uint32_t total = l.n ? l.end[l.n - 1] : 0u;
+	uint32_t in_tails = 0;
+	for (uint32_t g0 = threadIdx.x; g0 < total; g0 += THREADS * MLP) {
+		uint32_t w[MLP][8];
+		uint32_t tail_of[MLP];
+#pragma unroll
+		for (int u = 0; u < MLP; u++) {
+			const uint32_t g = min(g0 + u * THREADS, total - 1u); // clamped: keeps the vectors in registers
+			uint32_t run = 0;
+			while (g >= l.end[run])
+				run++;
+			const uint32_t first = run ? l.end[run - 1] : 0u;
+			tail_of[u] = (l.is_tail >> run) & 1u;
+			rj_load256(l.ptr[run] + (size_t)(g - first) * 16u, w[u]);
+		}
+#pragma unroll
+		for (int u = 0; u < MLP; u++) {
+			if (g0 + u * THREADS >= total)
+				continue;
+			if (!tail_of[u]) {
+#pragma unroll
+				for (int j = 0; j < 8; j++) {
+					rj_count<BITS>(cnt, w[u][j] & 0xffffu);
+					rj_count<BITS>(cnt, w[u][j] >> 16);
+				}
+			} else {
+				const uint32_t valid = min(15u, w[u][7] >> 16);
+				in_tails += valid;
+#pragma unroll
+				for (int j = 0; j < 15; j++)
+					if ((uint32_t)j < valid)
+						rj_count<BITS>(cnt, (w[u][j >> 1] >> ((j & 1) * 16)) & 0xffffu);
+			}
+		}
+	}
+	if (in_tails)
+		atomicAdd(tail_total, in_tails);
+}
+
 // one thread per (source, main | tail): with 8 GPUs a partition has 16 streams per side, and 16 dependent cursor loads
 // in a row would cost more than counting the streams
 __device__ __forceinline__ void rj_fetch_counts(const RJRuns &r, uint32_t p, uint32_t (*counts)[2], uint32_t t)
@@ -190,6 +274,8 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 	uint32_t *cntB = cntA + words;
 	__shared__ uint32_t s_part, s_sumA, s_sumB, s_tailA, s_tailB;
 	__shared__ uint32_t s_counts[2][RJ_MAX_RANKS][2]; // [side][source][main | tail] entries of the current partition
+	__shared__ RJRunList s_list[2];                   // multi-GPU plans: the runs of the current partition, per side
+	__shared__ uint32_t s_main[2];
 	__shared__ uint32_t s_warp[NWARPS + 1];
 	__shared__ unsigned long long s_base;
 	const int tid = threadIdx.x;
@@ -213,11 +299,24 @@ k_radix_joincount(RJRuns a_param, RJRuns b_param, RJParams pr, RJOut out, uint32
 			else if (tid < 4 * RJ_MAX_RANKS)
 				rj_fetch_counts(b, p, s_counts[1], tid - 2 * RJ_MAX_RANKS);
 			__syncthreads();
+			if (tid == 0)
+				s_main[0] = rj_build_run_list(a, p, s_counts[0], &s_list[0]);
+			else if (tid == 32)
+				s_main[1] = rj_build_run_list(b, p, s_counts[1], &s_list[1]);
+			__syncthreads();
 		}
 
 		// ---- count both sides
-		const uint32_t totA = rj_histogram_side<BITS, THREADS, MULTI>(a, pr, p, cntA, s_counts[0], &s_tailA);
-		const uint32_t totB = rj_histogram_side<BITS, THREADS, MULTI>(b, pr, p, cntB, s_counts[1], &s_tailB);
+		uint32_t totA, totB;
+		if (MULTI) {
+			rj_histogram_multi<BITS, THREADS>(s_list[0], cntA, &s_tailA);
+			rj_histogram_multi<BITS, THREADS>(s_list[1], cntB, &s_tailB);
+			totA = s_main[0];
+			totB = s_main[1];
+		} else {
+			totA = rj_histogram_side<BITS, THREADS, MULTI>(a, pr, p, cntA, s_counts[0], &s_tailA);
+			totB = rj_histogram_side<BITS, THREADS, MULTI>(b, pr, p, cntB, s_counts[1], &s_tailB);
+		}
 		__syncthreads();
 
 		// ---- checksum + number of groups of this partition

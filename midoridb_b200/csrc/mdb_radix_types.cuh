@@ -46,11 +46,13 @@ struct RJSide {
 	uint32_t cap, tail_cap;    // entries per partition (multiples of 16)
 };
 
-// What pass 2 reads for one side: for every source rank the streams of the partitions this GPU owns.  Source
-// `self` is this GPU's own RJSide (indexed by p); the others are the arena slots the peers pushed into over
-// NVLink (indexed by p - first).
+// What pass 2 reads for one side: for every source rank its streams of the partitions this GPU owns.  Single-GPU
+// plans have one source (the local streams); in multi-GPU plans source o is rank o's arena, read over NVLink (peer-mapped
+// memory, same layout on every rank), source `self` being this GPU's own.
 struct RJRuns {
 	int nsrc;                  // 0: the side is a sorted column, see sorted_keys
+	int self;                  // multi-GPU plans: index of this rank among the sources
+	unsigned long long *pulled_bytes; // statistics: bytes of remainders read from OTHER ranks (nullptr: not counted)
 	const int64_t *sorted_keys; // sorted column: partition p = rows [sorted_bnd[p], sorted_bnd[p + 1]) (mdb_radix_sorted.cuh)
 	const uint64_t *sorted_bnd;
 	uint32_t cap, tail_cap;

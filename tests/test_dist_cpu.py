@@ -66,25 +66,24 @@ LAYOUT_WORKER = textwrap.dedent("""
             lay = capi.dist_describe(nparts, W, rows)
             first = list(lay.part_first)[:W + 1]
             assert first[0] == 0 and first[W] == nparts and all(a <= b for a, b in zip(first, first[1:]))
-            assert max(b - a for a, b in zip(first, first[1:])) <= lay.owned_max
             # the push kernel's owner-of-partition formula agrees with the ranges (every partition, every rank)
             for p in list(range(min(nparts, 300))) + [nparts - 1, nparts // 2]:
                 o = capi.dist_owner(p, nparts, W)
                 assert first[o] <= p < first[o + 1], (p, o, first)
             assert capi.dist_owner(nparts, nparts, W) == -1
-            # a slot holds the streams of owned_max partitions, 256-byte aligned sections in the order main, tail, cursors
-            assert lay.slot_main_off == 0 and lay.slot_tail_off >= lay.owned_max * lay.stream_cap * 2
-            assert lay.slot_cursor_off >= lay.slot_tail_off + lay.owned_max * lay.tail_cap * 2
-            assert lay.slot_bytes >= lay.slot_tail_cursor_off + lay.owned_max * 4
-            assert all(x %% 256 == 0 for x in (lay.slot_tail_off, lay.slot_cursor_off, lay.slot_tail_cursor_off, lay.slot_bytes))
-            assert lay.arena_half_bytes == 2 * W * lay.slot_bytes
+            # a side's region holds the streams of ALL partitions: 256-byte aligned sections in the order main, tail, cursor pairs
+            assert lay.region_main_off == 0 and lay.region_tail_off >= nparts * lay.stream_cap * 2
+            assert lay.region_cursor_off >= lay.region_tail_off + nparts * lay.tail_cap * 2
+            assert lay.region_bytes >= lay.region_cursor_off + 4096 * 2 * 4
+            assert all(x %% 256 == 0 for x in (lay.region_tail_off, lay.region_cursor_off, lay.region_bytes))
+            assert lay.arena_half_bytes == 2 * lay.region_bytes
             assert lay.stream_cap %% 64 == 0 and lay.tail_cap %% 16 == 0
     # both ranks of THIS world derive the same layout and disjoint, covering ownership
     lay = capi.dist_describe(4096, world, 1 << 28)
-    mine = torch.tensor([lay.part_first[rank], lay.part_first[rank + 1], lay.stream_cap, lay.tail_cap, lay.slot_bytes], dtype=torch.int64)
+    mine = torch.tensor([lay.part_first[rank], lay.part_first[rank + 1], lay.stream_cap, lay.tail_cap, lay.region_bytes], dtype=torch.int64)
     everyone = [torch.zeros(5, dtype=torch.int64) for _ in range(world)]
     td.all_gather(everyone, mine)
-    assert all(int(e[2]) == lay.stream_cap and int(e[3]) == lay.tail_cap and int(e[4]) == lay.slot_bytes for e in everyone)
+    assert all(int(e[2]) == lay.stream_cap and int(e[3]) == lay.tail_cap and int(e[4]) == lay.region_bytes for e in everyone)
     assert int(everyone[0][0]) == 0 and int(everyone[-1][1]) == 4096
     assert all(int(everyone[r][1]) == int(everyone[r + 1][0]) for r in range(world - 1))
     d.close()
