@@ -303,10 +303,26 @@ struct DPredOp {
 	double dval;
 };
 
+// one `<column> <cmp> <literal>` term of a conjunction (see DPredProgram::n_terms)
+struct DPredTerm {
+	int32_t tbl, cmp;
+	int32_t as_dbl;  // compare as doubles (DOUBLE column or DOUBLE literal), else as int64
+	int32_t col_dbl; // the column holds doubles (raw bits)
+	const int64_t *data;
+	const uint32_t *present;
+	int64_t ilit;
+	double dlit;
+};
+
+#define PRED_MAX_TERMS 8
+
 struct DPredProgram {
 	int32_t n;
-	int32_t _pad;
+	// > 0: the program is a conjunction of n_terms `<column> <cmp> <literal>` terms (the common WHERE shape: BASELINE configs 2
+	// and 4), compiled on the host; the kernels evaluate the terms directly - no operand stack in local memory, no decoding
+	int32_t n_terms;
 	DPredOp ops[MDBCU_MAX_PRED];
+	DPredTerm terms[PRED_MAX_TERMS];
 };
 
 struct PVal {
@@ -359,6 +375,26 @@ struct StarRows {
 template <typename Rows>
 __device__ static bool eval_program(const DPredProgram *__restrict__ prog, const Rows &rows)
 {
+	if (prog->n_terms > 0) {
+		for (int k = 0; k < prog->n_terms; k++) {
+			const DPredTerm &t = prog->terms[k];
+			const uint32_t r = rows(t.tbl);
+			if (t.present && !mdb_bit(t.present, r))
+				return false; // NULL operand: the comparison is not true (executor_select.c:629-631)
+			const long long v = t.data[r];
+			bool ok;
+			if (t.as_dbl) {
+				const double x = t.col_dbl ? __longlong_as_double(v) : (double)v, y = t.dlit;
+				ok = t.cmp == 1 ? x < y : t.cmp == 2 ? x > y : t.cmp == 3 ? x != y : t.cmp == 4 ? x == y : t.cmp == 5 ? x <= y : x >= y;
+			} else {
+				const long long y = t.ilit;
+				ok = t.cmp == 1 ? v < y : t.cmp == 2 ? v > y : t.cmp == 3 ? v != y : t.cmp == 4 ? v == y : t.cmp == 5 ? v <= y : v >= y;
+			}
+			if (!ok)
+				return false;
+		}
+		return true;
+	}
 	PVal st[PRED_STACK];
 	int sp = 0;
 	for (int k = 0; k < prog->n; k++) {
@@ -455,11 +491,67 @@ static bool col_all_present(const mdbcu_table *t, int col)
 	return t->all_live && !t->cols[col].has_nulls;
 }
 
+// Is the postfix program `t1 t2 AND t3 AND ...` (any association) with every t = <column> <literal> CMP or <literal> <column> CMP?
+// Then fill h->terms.  (A host-side stack of "what kind of thing is on the operand stack" walks the program once.)
+static void compile_conjunction(DPredProgram *h)
+{
+	enum { COL, LIT, CONJ };
+	struct Item {
+		int kind, op;
+	} st[PRED_STACK + 1];
+	int sp = 0, nt = 0;
+	DPredTerm terms[PRED_MAX_TERMS];
+	for (int k = 0; k < h->n; k++) {
+		const DPredOp &o = h->ops[k];
+		switch (o.op) {
+		case MDBCU_P_COL:
+			st[sp++] = {COL, k};
+			break;
+		case MDBCU_P_INT: case MDBCU_P_DBL:
+			st[sp++] = {LIT, k};
+			break;
+		case MDBCU_P_CMP: {
+			if (sp < 2 || nt == PRED_MAX_TERMS)
+				return;
+			const Item b = st[--sp], a = st[--sp];
+			if (!((a.kind == COL && b.kind == LIT) || (a.kind == LIT && b.kind == COL)))
+				return;
+			const DPredOp &c = h->ops[a.kind == COL ? a.op : b.op], &l = h->ops[a.kind == COL ? b.op : a.op];
+			static const int flipped[7] = {0, 2, 1, 3, 4, 6, 5}; // literal on the left: a < b  <=>  b > a
+			DPredTerm &t = terms[nt++];
+			t.tbl = c.tbl;
+			t.cmp = a.kind == COL ? o.arg : flipped[o.arg];
+			t.col_dbl = c.is_dbl;
+			t.as_dbl = c.is_dbl || l.op == MDBCU_P_DBL;
+			t.data = c.data;
+			t.present = c.present;
+			t.ilit = l.ival;
+			t.dlit = l.op == MDBCU_P_DBL ? l.dval : (double)l.ival;
+			st[sp++] = {CONJ, 0};
+			break;
+		}
+		case MDBCU_P_AND: {
+			if (sp < 2 || st[sp - 1].kind != CONJ || st[sp - 2].kind != CONJ)
+				return;
+			sp--;
+			break;
+		}
+		default:
+			return;
+		}
+	}
+	if (sp != 1 || st[0].kind != CONJ || nt == 0)
+		return;
+	for (int k = 0; k < nt; k++)
+		h->terms[k] = terms[k];
+	h->n_terms = nt;
+}
+
 static int build_pred(mdbcu_ctx *ctx, const mdbcu_plan *plan, DPredProgram *h)
 {
 	int depth = 0;
 	h->n = plan->n_pred;
-	h->_pad = 0;
+	h->n_terms = 0;
 	if (plan->n_pred < 0 || plan->n_pred > MDBCU_MAX_PRED)
 		return mdb_fail(ctx, MDBCU_EERROR, "predicate program too long");
 	for (int k = 0; k < plan->n_pred; k++) {
@@ -512,6 +604,7 @@ static int build_pred(mdbcu_ctx *ctx, const mdbcu_plan *plan, DPredProgram *h)
 	}
 	if (plan->n_pred && depth != 1)
 		return mdb_fail(ctx, MDBCU_EERROR, "malformed predicate program");
+	compile_conjunction(h);
 	return MDBCU_OK;
 }
 
@@ -1448,6 +1541,11 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 			need_first = true;
 	if (need_first && !sp.pack_ok)
 		return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "plain columns under GROUP BY need row ids that pack into 64 bits");
+	// The first row of every group (one 64-bit atomicMin per input row) serves two purposes: plain columns under GROUP BY, and
+	// the reference's row order for results small enough to be ordered at all.  Above 2^24 input rows - sizes the reference
+	// itself could never run - the order is not kept, so without plain columns the atomic is dropped.
+	if (!need_first && n_in > (1ull << 24))
+		sp.pack_ok = 0;
 
 	if (n_in == 0)
 		return mdb_result_alloc(ctx, plan, res, 0, false); // no qualifying row: no result row (executor keeps zero rows)
