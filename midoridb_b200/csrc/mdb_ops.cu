@@ -1613,8 +1613,12 @@ static int aggregate_tuples(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples
 	for (int o = 0; o < plan->n_out; o++)
 		n_agg += sp.out[o].kind != MDBCU_OUT_COLUMN;
 	const size_t entry_bytes = 8 * (2 + 2 * (size_t)n_agg);
+	// (MDBCU_GROUP_CACHE_KB: A/B switch.  The kernel needs 32 registers, so shared memory decides how many CTAs an SM holds -
+	// 48 KiB: 1024 threads, 24 KiB: 2048 - but config 4 runs 2.82 / 2.84 / 2.94 ms with 48 / 24 / 12 KiB: occupancy is not
+	// what limits it, the hit rate of the cache matters a little)
+	static const size_t cache_kb = getenv("MDBCU_GROUP_CACHE_KB") ? (size_t)atoi(getenv("MDBCU_GROUP_CACHE_KB")) : 48;
 	uint32_t cache_entries = 2048;
-	while (cache_entries >= 256 && cache_entries * entry_bytes > 48 * 1024)
+	while (cache_entries >= 256 && cache_entries * entry_bytes > cache_kb * 1024)
 		cache_entries >>= 1;
 	if (cache_entries < 256 || getenv("MDBCU_NO_GROUP_CACHE")) // the switch is for A/B measurements
 		cache_entries = 0;
