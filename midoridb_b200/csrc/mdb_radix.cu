@@ -132,7 +132,13 @@ static void launch_partition(mdbcu_ctx *ctx, int grid, const RJSide &s, const RJ
 	if (s.present)
 		MDB_LAUNCH(ctx, k_radix_partition<true>, grid * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
 	else if (s.all_in_range && pr.range <= 0xffffffffull && ((uintptr_t)s.keys & 31u) == 0)
-		MDB_LAUNCH(ctx, k_radix_partition_fast, grid * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
+	{
+		static const bool no_w16 = getenv("MDBCU_P1_NO_W16") != nullptr; // (A/B measurements)
+		if (pr.width == 65536u && !no_w16)
+			MDB_LAUNCH(ctx, k_radix_partition_fast<true>, grid * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
+		else
+			MDB_LAUNCH(ctx, k_radix_partition_fast<false>, grid * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
+	}
 	else
 		MDB_LAUNCH(ctx, k_radix_partition<false>, grid * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem), s, pr);
 }
@@ -287,6 +293,8 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	pr.error_flag = d_flags;
 	pr.peer_flags = nullptr;
 	pr.n_peer_flags = 0;
+	static const int plain_emit = getenv("MDBCU_P2_PLAIN_EMIT") ? atoi(getenv("MDBCU_P2_PLAIN_EMIT")) : 0;
+	pr.plain_emit = plain_emit;
 	uint32_t *d_peer_flags = nullptr, *d_peer_flags2 = nullptr;
 	if (dist && W > 1) {
 		d_peer_flags = ctl + 8;
@@ -359,7 +367,8 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 	if (!ctx->radix_attr_done) {
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
-		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
+		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
+		CUDA_TRY(ctx, cudaFuncSetAttribute(k_radix_partition_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
 		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
 		CUDA_TRY(ctx, cudaFuncSetAttribute((k_radix_joincount<4, 512, 1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));

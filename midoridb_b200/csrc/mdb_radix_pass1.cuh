@@ -42,7 +42,13 @@ __device__ unsigned long long rj_timeline[4][8];
 #define RJ_P1_KEYS 8               // keys per thread per round
 #define RJ_WARP_PARTS (RJ_ROWS / RJ_P1_WARPS) // staging rows one warp flushes
 
-#define RJ_HINT_PREFETCH 1u        // prefetch.global.L2 two tiles ahead
+#ifndef RJ_LOAD_AT
+#define RJ_LOAD_AT 1               // where in the round the next tile's keys are requested (k_radix_partition_fast)
+#endif
+#ifndef RJ_PF_DIST
+#define RJ_PF_DIST 2               // tiles between a CTA's load and its L2 prefetch
+#endif
+#define RJ_HINT_PREFETCH 1u        // prefetch.global.L2 RJ_PF_DIST tiles ahead
 #define RJ_HINT_LOAD_EVICT_FIRST 2u
 #define RJ_HINT_STORE_EVICT_LAST 4u
 #define RJ_HINT_DEFAULT 0u         // (MDBCU_P1_HINTS overrides; none of them pays once the L1 is large enough)
@@ -214,8 +220,15 @@ __device__ __forceinline__ uint32_t rj_insert_items(const RJSide &s, RJP1Smem *s
 // first threads of the CTA they put one more global-atomic latency on warp 0's path to the second barrier, and every
 // cooperative way of listing them made one warp late at the first: profiles/r02_lab3_*.txt.)
 // kept: this thread's key that found its row full, or RJ_NONE; kept_at: its tail position (rj_insert_items)
-__device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, RJP1Smem *sm, uint32_t kept, uint32_t kept_at, uint32_t half,
-		long long &rj_t_)
+struct RJNoHook {
+	__device__ __forceinline__ void operator()() const {}
+};
+
+// after_scan / after_flush: called by every thread once the warp's worklist is built / once its sectors are stored (the lean
+// kernel requests the next tile's keys at one of these points)
+template <class AfterScan = RJNoHook, class AfterFlush = RJNoHook>
+__device__ __forceinline__ void rj_round_end(const RJSide &s, const RJParams &pr, RJP1Smem *sm, uint32_t kept, uint32_t kept_at, uint32_t half,
+		long long &rj_t_, AfterScan after_scan = AfterScan(), AfterFlush after_flush = AfterFlush())
 {
 	const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
 	uint16_t *wl = sm->worklist[warp];
@@ -240,6 +253,7 @@ __device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, 
 		__syncwarp();
 	}
 	RJ_STAMP(4);
+	after_scan();
 	const bool evict_last = (s.hints & RJ_HINT_STORE_EVICT_LAST) != 0;
 	for (uint32_t w = lane; w < wl_n; w += 32) {
 		const uint32_t r = wl[w], p = r * RJ_SPLIT + half;
@@ -265,6 +279,7 @@ __device__ static inline void rj_round_end(const RJSide &s, const RJParams &pr, 
 		else
 			atomicOr(pr.error_flag, RJ_ERR_STREAM);
 	}
+	after_flush();
 	RJ_STAMP(2);
 	__syncthreads();
 	RJ_STAMP(3);
@@ -305,8 +320,19 @@ __device__ static inline void rj_smem_init(RJP1Smem *sm)
 }
 
 // Pass 1, lean variant: column without NULLs/tombstones whose [min, max] lies inside the partitioned range and
-// key - kmin < 2^32: no per-key validity test, 32-bit arithmetic on the low words, 256-bit key loads
-// (double-buffered in registers: 8 registers per tile in flight).  The ragged tail (< one tile) goes through CTA 0.
+// key - kmin < 2^32: no per-key validity test, 32-bit arithmetic on the low words, 256-bit key loads.
+// The ragged tail (< one tile) goes through CTA 0.
+//
+// WHEN the next tile is requested decides a seventh of this kernel's time (profiles/r02_lab3_r.txt, r02_lab3_s.txt).  A tile
+// is 64 KiB per SM; the L1 accepts such a burst over about a thousand cycles, and a warp's shared-memory instructions
+// queue behind its own pending loads.  Requested at the top of the round (double-buffered, the obvious software
+// pipeline) the loads sit in front of every warp's slot atomics: insert phase 3300 cycles.  Requested by each warp when
+// ITS keys have been handed to shared memory - into the same registers, one buffer - they are accepted while the warp
+// waits at the barrier and arrive during the flush: insert phase 2100 cycles, 0.756 -> 0.649 ms per launch.  Behind the
+// barrier (after the counter scan) they delay the flush instead: 0.727 ms.  RJ_LOAD_AT selects the point (lab only).
+// W16: the partitions are exactly 2^16 key values wide (key ranges of 2^28 - 65535 .. 2^28, the headline workload's):
+// key - kmin IS (partition << 16 | remainder), the seven instructions of rj_pack per key disappear.
+template <bool W16>
 __global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition_fast(RJSide s, RJParams pr)
 {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -319,44 +345,51 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition_fas
 	const uint64_t nfull = s.n / TILE;
 	const uint32_t kmin_lo = (uint32_t)(unsigned long long)pr.kmin;
 	const bool pf = (s.hints & RJ_HINT_PREFETCH) != 0, evict_first = (s.hints & RJ_HINT_LOAD_EVICT_FIRST) != 0;
-	uint32_t buf_a[RJ_P1_KEYS], buf_b[RJ_P1_KEYS];
+	uint32_t buf[RJ_P1_KEYS];
 	long long rj_t_ = (RJ_LAB & 8) ? clock64() : 0; // (timeline experiments only)
-	auto load = [&](uint64_t tile, uint32_t *dst) {
-		if (pf) {
-			// pull the tile this CTA will load two rounds from now into L2 (one 128-byte line per thread)
-			const uint64_t pf_first = (tile + 2ull * nslots) * TILE + (uint64_t)tid * 16;
-			if (tid < TILE / 16 && pf_first + 16 <= s.n)
-				asm volatile("prefetch.global.L2 [%0];" ::"l"(s.keys + pf_first));
-		}
-		const char *t = reinterpret_cast<const char*>(s.keys + tile * TILE) + tid * 32u;
-		rj_load_keys256(t, dst, evict_first);
-		rj_load_keys256(t + RJ_P1_THREADS * 32u, dst + 4, evict_first);
-	};
-	auto round = [&](const uint32_t *buf) {
+	uint64_t tile = slot;
+	const char *src = reinterpret_cast<const char*>(s.keys + tile * TILE) + tid * 32u;
+	if (tile < nfull) {
+		rj_load_keys256(src, buf, evict_first);
+		rj_load_keys256(src + RJ_P1_THREADS * 32u, buf + 4, evict_first);
+	}
+	while (tile < nfull) {
 		uint32_t item[RJ_P1_KEYS];
 #pragma unroll
 		for (int k = 0; k < RJ_P1_KEYS; k++)
-			item[k] = rj_pack(pr, buf[k] - kmin_lo);
+			item[k] = W16 ? buf[k] - kmin_lo : rj_pack(pr, buf[k] - kmin_lo);
 		uint32_t kept_at = 0;
 		const uint32_t kept = rj_insert_items<true>(s, sm, pr, item, half, kept_at);
-		rj_round_end(s, pr, sm, kept, kept_at, half, rj_t_);
-	};
-	uint64_t tile = slot;
-	if (tile < nfull)
-		load(tile, buf_a);
-	while (tile < nfull) {
-		uint64_t next = tile + nslots;
-		if (next < nfull)
-			load(next, buf_b);
-		round(buf_a);
-		tile = next;
-		if (tile >= nfull)
-			break;
-		next = tile + nslots;
-		if (next < nfull)
-			load(next, buf_a);
-		round(buf_b);
-		tile = next;
+		tile += nslots;
+		src += (size_t)nslots * TILE * sizeof(int64_t);
+		const bool more = tile < nfull;
+		if (pf) {
+			// pull the tile this CTA will load RJ_PF_DIST rounds from now into L2 (one 128-byte line per thread)
+			const uint64_t pf_first = (tile + (uint64_t)RJ_PF_DIST * nslots) * TILE + (uint64_t)tid * 16;
+			if (tid < TILE / 16 && pf_first + 16 <= s.n)
+				asm volatile("prefetch.global.L2 [%0];" ::"l"(s.keys + pf_first));
+		}
+		auto load_lo = [&]() {
+			if (more)
+				rj_load_keys256(src, buf, evict_first);
+		};
+		auto load_hi = [&]() {
+			if (more)
+				rj_load_keys256(src + RJ_P1_THREADS * 32u, buf + 4, evict_first);
+		};
+		if (RJ_LOAD_AT == 1) { // both 256-bit loads when this warp's keys are in shared memory, ahead of the first barrier
+			load_lo();
+			load_hi();
+			rj_round_end(s, pr, sm, kept, kept_at, half, rj_t_);
+		} else if (RJ_LOAD_AT == 2) { // second load after the flush, ahead of the second barrier
+			load_lo();
+			rj_round_end(s, pr, sm, kept, kept_at, half, rj_t_, RJNoHook(), load_hi);
+		} else if (RJ_LOAD_AT == 3) { // both behind the first barrier, after the scan of the slot counters
+			rj_round_end(s, pr, sm, kept, kept_at, half, rj_t_, [&]() { load_lo(); load_hi(); });
+		} else { // second load after the scan
+			load_lo();
+			rj_round_end(s, pr, sm, kept, kept_at, half, rj_t_, load_hi);
+		}
 	}
 	if (slot == 0 && nfull * TILE != s.n) {
 		for (uint64_t r = nfull * TILE + tid; r < s.n; r += RJ_P1_THREADS) {
@@ -395,14 +428,13 @@ __device__ static inline void rj_load_tile(const RJSide &s, uint64_t tile, int4 
 	}
 }
 
-// generic insert phase: range test, NULL/tombstone bitmap, ragged last tile.  FULL: every row of the tile exists
+// generic decode: range test, NULL/tombstone bitmap, ragged last tile -> item = (partition << 16 | remainder) or RJ_NONE.
+// FULL: every row of the tile exists
 template <bool HAS_PRESENT, bool FULL>
-__device__ static inline uint32_t rj_insert_tile(const RJSide &s, const RJParams &pr, RJP1Smem *sm, const int4 *buf, uint64_t tile,
-		uint32_t half, uint32_t &kept_at)
+__device__ static inline void rj_decode_tile(const RJSide &s, const RJParams &pr, const int4 *buf, uint64_t tile, uint32_t *item)
 {
 	constexpr uint32_t TILE = RJ_P1_THREADS * RJ_P1_KEYS;
 	const uint64_t base_pair = tile * (TILE / 2);
-	uint32_t item[RJ_P1_KEYS];
 #pragma unroll
 	for (int j = 0; j < RJ_P1_KEYS / 2; j++) {
 		const uint64_t pi = base_pair + (uint64_t)j * RJ_P1_THREADS + threadIdx.x;
@@ -422,11 +454,10 @@ __device__ static inline uint32_t rj_insert_tile(const RJSide &s, const RJParams
 		item[2 * j] = ok0 ? rj_pack(pr, (uint32_t)d0) : RJ_NONE;
 		item[2 * j + 1] = ok1 ? rj_pack(pr, (uint32_t)d1) : RJ_NONE;
 	}
-	return rj_insert_items<false>(s, sm, pr, item, half, kept_at);
 }
 
-// Pass 1, generic variant (NULLs / tombstones / keys outside the partitioned range): same rounds as the lean
-// kernel, whole keys double-buffered in registers (ping-pong, no copies).
+// Pass 1, generic variant (NULLs / tombstones / keys outside the partitioned range): same rounds as the lean kernel,
+// whole keys; the next tile is requested into the same registers once this tile's keys are in shared memory.
 template <bool HAS_PRESENT>
 __global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition(RJSide s, RJParams pr)
 {
@@ -438,30 +469,23 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition(RJS
 	const uint32_t half = blockIdx.x % RJ_SPLIT, slot = blockIdx.x / RJ_SPLIT, nslots = gridDim.x / RJ_SPLIT;
 	const uint64_t ntiles = (s.n + TILE - 1) / TILE;
 	const uint64_t nfull = s.n / TILE; // tiles [0, nfull) are complete
-	int4 buf_a[RJ_P1_KEYS / 2], buf_b[RJ_P1_KEYS / 2];
+	int4 buf[RJ_P1_KEYS / 2];
 	uint64_t tile = slot;
 	long long rj_t_ = (RJ_LAB & 8) ? clock64() : 0; // (timeline experiments only)
 	if (tile < ntiles)
-		rj_load_tile(s, tile, buf_a);
-	auto round = [&](const int4 *buf, uint64_t t) {
-		uint32_t kept_at = 0;
-		const uint32_t kept = t < nfull ? rj_insert_tile<HAS_PRESENT, true>(s, pr, sm, buf, t, half, kept_at)
-				: rj_insert_tile<HAS_PRESENT, false>(s, pr, sm, buf, t, half, kept_at);
-		rj_round_end(s, pr, sm, kept, kept_at, half, rj_t_);
-	};
+		rj_load_tile(s, tile, buf);
 	while (tile < ntiles) {
-		uint64_t next = tile + nslots;
-		if (next < ntiles)
-			rj_load_tile(s, next, buf_b);
-		round(buf_a, tile);
-		tile = next;
-		if (tile >= ntiles)
-			break;
-		next = tile + nslots;
-		if (next < ntiles)
-			rj_load_tile(s, next, buf_a);
-		round(buf_b, tile);
-		tile = next;
+		uint32_t item[RJ_P1_KEYS];
+		if (tile < nfull)
+			rj_decode_tile<HAS_PRESENT, true>(s, pr, buf, tile, item);
+		else
+			rj_decode_tile<HAS_PRESENT, false>(s, pr, buf, tile, item);
+		uint32_t kept_at = 0;
+		const uint32_t kept = rj_insert_items<false>(s, sm, pr, item, half, kept_at);
+		tile += nslots;
+		if (tile < ntiles)
+			rj_load_tile(s, tile, buf);
+		rj_round_end(s, pr, sm, kept, kept_at, half, rj_t_);
 	}
 	rj_drain(s, pr, sm, half);
 }

@@ -74,4 +74,5 @@ struct RJParams {
 	uint32_t *error_flag;
 	const uint32_t *peer_flags; // multi-GPU: every rank's error flags after the exchange (pass 2 does nothing if any is set)
 	int n_peer_flags;
+	int plain_emit;            // pass 2: always take the compiler-generated emit loop (MDBCU_P2_PLAIN_EMIT=1, A/B measurements)
 };

@@ -9,6 +9,12 @@
 #include <cstdlib>
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e_), __LINE__); exit(1); } } while (0)
+#ifndef P1_ALL_HINTS
+#define P1_ALL_HINTS 0
+#endif
+#ifndef P1_W16
+#define P1_W16 false   // -DP1_W16=true: the variant for partitions of exactly 2^16 key values (the lab uses shift 16)
+#endif
 
 __global__ void k_gen(int64_t *k, uint64_t n, uint64_t domain)
 {
@@ -51,13 +57,13 @@ int main(int argc, char **argv)
 	pr.nparts = 4096;
 	pr.part_end = 4096;
 	pr.error_flag = flag;
-	CK(cudaFuncSetAttribute(k_radix_partition_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
+	CK(cudaFuncSetAttribute(k_radix_partition_fast<P1_W16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 	CK(cudaFuncSetAttribute(k_radix_partition<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RJP1Smem)));
 	cudaEvent_t e0, e1;
 	CK(cudaEventCreate(&e0));
 	CK(cudaEventCreate(&e1));
 	printf("n = 2^%d keys, %d SMs, smem %zu\n", lg, sms, sizeof(RJP1Smem));
-	for (int variant = 0; variant < ((RJ_LAB & 8) ? 1 : 9); variant += (variant == 1 ? 7 : 1)) {
+	for (int variant = 0; variant < ((RJ_LAB & 8) ? 1 : 9); variant += ((variant == 1 && !P1_ALL_HINTS) ? 7 : 1)) {
 		s.hints = variant < 8 ? (uint32_t)variant : 0;
 		float total = 0;
 		const int reps = 5;
@@ -65,7 +71,7 @@ int main(int argc, char **argv)
 			CK(cudaMemsetAsync(s.cursor, 0, (size_t)RJ_MAX_PART * RJ_CUR_STRIDE * 4));
 			CK(cudaEventRecord(e0));
 			if (variant < 8)
-				k_radix_partition_fast<<<sms * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem)>>>(s, pr);
+				k_radix_partition_fast<P1_W16><<<sms * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem)>>>(s, pr);
 			else
 				k_radix_partition<false><<<sms * RJ_SPLIT, RJ_P1_THREADS, sizeof(RJP1Smem)>>>(s, pr);
 			CK(cudaEventRecord(e1));

@@ -631,6 +631,28 @@ def test_radix_joincount_large_against_numpy(be, log2_rows):
     tb.drop()
 
 
+@pytest.mark.parametrize("where", ["across_2p32", "across_zero", "above_2p33", "negative"])
+@pytest.mark.parametrize("layout", ["key_count", "count_key"])
+def test_radix_joincount_key_words_and_layouts(be, where, layout):
+    """pass 2 writes keys as (high word of the partition, low word + offset) and addresses rows with 32-bit arithmetic when
+    the partition allows it: partitions that straddle a multiple of 2^32 (or zero), keys far above 2^32 and negative keys
+    must come out exactly, in both compiled result layouts"""
+    rng = np.random.default_rng(97)
+    n = 1 << 20
+    base = {"across_2p32": (1 << 32) - (1 << 19), "across_zero": -(1 << 19), "above_2p33": (1 << 33) + 12345,
+            "negative": -(1 << 40) - 999}[where]
+    a = base + rng.integers(0, 1 << 20, n)
+    b = base + rng.integers(0, 1 << 20, n + 777)
+    ga, oa = both_tables(be, [I], [a])
+    gb, ob = both_tables(be, [I], [b])
+    out = [(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)] if layout == "key_count" else [(OUT_COUNT_STAR,), (OUT_COLUMN, 1, 0)]
+    grows, orows, _, st = run_both(be, [ga, gb], [oa, ob], joins=[((0, 0), (1, 0))], group=[(0, 0)], out=out)
+    assert st.path == capi.PATH_RADIX_JOINCOUNT
+    assert helpers.canon(grows) == helpers.canon(orows)
+    for t in (ga, gb):
+        t.drop()
+
+
 def _tail_cases():
     from tests.test_oracle import TAIL_CASES
     return TAIL_CASES
