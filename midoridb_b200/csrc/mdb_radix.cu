@@ -193,8 +193,13 @@ int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_res
 		return mdb_result_alloc(ctx, plan, res, 0, false);
 	}
 	unsigned long long range = (unsigned long long)kmax - (unsigned long long)kmin + 1ull;
-	if (range == 0 || range > ((unsigned long long)RJ_MAX_PART << RJ_MAX_SHIFT) || range < 4096)
+	if (range == 0 || range > ((unsigned long long)RJ_MAX_PART << RJ_MAX_SHIFT) || range < 4096) {
+		// a key range beyond 4096 partitions x 2^16 remainders: large inputs go to the direct-count path (one counter per key
+		// value, up to 2^30 values) instead of the general operators, which would build a hash table of every row
+		if (range > ((unsigned long long)RJ_MAX_PART << RJ_MAX_SHIFT))
+			ctx->radix_gave_up = true;
 		return MDBCU_EUNSUPPORTED;
+	}
 	{
 		// when the two columns cover almost the same interval, partition over the UNION of the intervals instead:
 		// every key of both sides is then in range and the hot loop needs no per-key range test

@@ -18,6 +18,9 @@
 #define ST_MAX_AGGS 4
 #define ST_MAX_COLS 3              // fact columns referenced: the foreign key + up to two aggregated columns
 #define ST_THREADS 1024
+#ifndef ST_UNROLL
+#define ST_UNROLL 2                // 32-byte vectors per column a thread has in flight
+#endif
 #define ST_EMPTY 0xffffu
 #define ST_ACC_BYTES (64 * 1024)   // shared memory for the per-group accumulators (table + accumulators stay under 195 KiB)
 
@@ -181,7 +184,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_star_probe(StarSpec sp, const
 
 	const uint64_t nquads = n / 4, stride = (uint64_t)gridDim.x * ST_THREADS;
 	uint64_t quad = (uint64_t)blockIdx.x * ST_THREADS + tid;
-	constexpr int UNROLL = 2, ROWS = 4 * UNROLL;
+	constexpr int UNROLL = ST_UNROLL, ROWS = 4 * UNROLL;
 	for (; quad + (UNROLL - 1) * stride < nquads; quad += UNROLL * stride) {
 		uint32_t raw[NC][UNROLL][8], pbits[NC];
 #pragma unroll

@@ -653,6 +653,27 @@ def test_radix_joincount_key_words_and_layouts(be, where, layout):
         t.drop()
 
 
+def test_join_count_wide_key_range_takes_direct_count(be):
+    """keys spread over more than 2^28 values (4096 partitions x 2^16 remainders): the radix path hands the query to the
+    direct-count path (one 32-bit counter per key value), not to the general operators"""
+    rng = np.random.default_rng(101)
+    n = 1 << 21
+    a = rng.integers(-(1 << 28), 1 << 28, n)
+    b = rng.integers(-(1 << 28), 1 << 28, n + 4321)
+    b[:50000] = a[:50000]  # make sure there are matches
+    a[:3] = [-(1 << 28), (1 << 28) - 1, 0]
+    b[-3:] = [-(1 << 28), (1 << 28) - 1, 0]
+    ga, oa = both_tables(be, [I], [a])
+    gb, ob = both_tables(be, [I], [b])
+    grows, orows, _, st = run_both(be, [ga, gb], [oa, ob], joins=[((0, 0), (1, 0))], group=[(0, 0)],
+                                   out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,)])
+    assert st.path == capi.PATH_DIRECT_COUNT
+    assert len(grows) >= 50000
+    assert helpers.canon(grows) == helpers.canon(orows)
+    for t in (ga, gb):
+        t.drop()
+
+
 def _tail_cases():
     from tests.test_oracle import TAIL_CASES
     return TAIL_CASES
