@@ -181,10 +181,19 @@ struct mdbcu_out {
 	struct mdbcu_colref ref;
 };
 
-#define MDBCU_PLAN_DISTRIBUTED 1u /* tables are this rank's shards; exchange join sides by key (needs mdbcu_comm_init) */
+#define MDBCU_PLAN_DISTRIBUTED 1u /* tables are this rank's shards (needs mdbcu_comm_init).  Distributed plan shapes: join + GROUP BY join
+                                   * key + COUNT(*) (join sides exchanged by key, every rank returns the keys it owns); filter + aggregate
+                                   * scans, small-dimension star joins and GROUP BY / aggregates over one sharded table (partials merged,
+                                   * rank 0 returns the rows).  Anything else: MDBCU_EUNSUPPORTED */
 #define MDBCU_PLAN_NO_FASTPATH 2u /* test hook: force the general operators                                */
 
-/* what executor_run_select_stmt (executor_select.c:1655) receives as an optimised AST, flattened */
+/* what executor_run_select_stmt (executor_select.c:1655) receives as an optimised AST, flattened.
+ * Limits of the device operators - such a plan returns MDBCU_EUNSUPPORTED with the reason in mdbcu_last_error(), there is
+ * no CPU fallback: VARCHAR columns in predicates, join keys, GROUP BY or aggregates (not mirrored on the device); join keys
+ * of different kinds (INT vs DOUBLE); a two-column GROUP BY whose columns are not both integers within the int32 range and
+ * free of NULLs (one-column keys of any kind, NULLs included, are fine); plain non-key columns under GROUP BY when the row
+ * ids of the joined tables do not pack into 64 bits; more than 2^32-1 joined rows in the general operators; WHERE programs
+ * nesting deeper than 24 operands. */
 struct mdbcu_plan {
 	int32_t n_tables;
 	mdbcu_table *tables[MDBCU_MAX_TABLES];

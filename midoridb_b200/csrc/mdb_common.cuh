@@ -334,6 +334,8 @@ int mdb_table_refresh_stats(mdbcu_table *t, int col);
 // physical paths (return MDBCU_EUNSUPPORTED when the plan does not fit so the caller can fall through)
 int mdb_select_general(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res);
 int mdb_select_scan_agg(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res);
+int mdb_select_general_dist(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res);
+int out_result_type(const mdbcu_plan *plan, int o); // MDBCU_CT_INTEGER or MDBCU_CT_DOUBLE of result column o
 int mdb_select_radix_joincount(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res);
 int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res);
 
@@ -353,6 +355,33 @@ int mdb_select_direct_count(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result
 bool mdb_plan_has_tail(const mdbcu_plan *plan);
 int mdb_validate_tail(mdbcu_ctx *ctx, const mdbcu_plan *plan);
 int mdb_apply_tail(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res);
+
+// two events around one kernel (stats.dominant_ms); destroyed on every return path
+struct KernelTimer {
+	cudaEvent_t e0 = nullptr, e1 = nullptr;
+	KernelTimer()
+	{
+		cudaEventCreate(&e0);
+		cudaEventCreate(&e1);
+	}
+	KernelTimer(const KernelTimer&) = delete;
+	KernelTimer &operator=(const KernelTimer&) = delete;
+	void start(cudaStream_t s) { cudaEventRecord(e0, s); }
+	void stop(cudaStream_t s) { cudaEventRecord(e1, s); }
+	float ms() const // (the stream has been synchronised by the caller)
+	{
+		float v = 0.f;
+		cudaEventElapsedTime(&v, e0, e1);
+		return v;
+	}
+	~KernelTimer()
+	{
+		if (e0)
+			cudaEventDestroy(e0);
+		if (e1)
+			cudaEventDestroy(e1);
+	}
+};
 
 // phase clock: events are only recorded while the query runs; one synchronise at the end
 struct PhaseClock {

@@ -600,10 +600,8 @@ int mdb_select_scan_agg(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *re
 	}
 
 	clock.begin(0);
-	cudaEvent_t k0, k1;
-	cudaEventCreate(&k0);
-	cudaEventCreate(&k1);
-	cudaEventRecord(k0, ctx->stream);
+	KernelTimer ktimer;
+	ktimer.start(ctx->stream);
 	for (int a2 = sp.naggs; a2 < SA_MAX_AGGS; a2++) {
 		sp.aggs[a2].kind = MDBCU_OUT_COUNT_STAR; // padding slots (ignored by the final kernel)
 		sp.aggs[a2].col = -1;
@@ -615,7 +613,7 @@ int mdb_select_scan_agg(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *re
 		launch_scan_agg<2>(ctx, grid, sp, t->n_slots, partials);
 	else
 		launch_scan_agg<3>(ctx, grid, sp, t->n_slots, partials);
-	cudaEventRecord(k1, ctx->stream);
+	ktimer.stop(ctx->stream);
 	clock.begin(4);
 	const int W = dist ? ctx->world : 1;
 	if (W > 1) {
@@ -634,10 +632,7 @@ int mdb_select_scan_agg(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *re
 	}
 	cudaError_t e = cudaGetLastError();
 	clock.finish();
-	float kms = 0.f;
-	cudaEventElapsedTime(&kms, k0, k1);
-	cudaEventDestroy(k0);
-	cudaEventDestroy(k1);
+	const float kms = ktimer.ms();
 	if (e != cudaSuccess)
 		return mdb_fail(ctx, MDBCU_ECUDA, "scan+aggregate launch failed: %s", cudaGetErrorString(e));
 

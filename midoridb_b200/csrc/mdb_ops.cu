@@ -1405,7 +1405,7 @@ __global__ void k_gather_out(const DGroupSpec *__restrict__ sp, TuplesDev ts, DR
 	}
 }
 
-static int out_result_type(const mdbcu_plan *plan, int o)
+int out_result_type(const mdbcu_plan *plan, int o)
 {
 	const mdbcu_out &out = plan->out[o];
 	if (out.kind == MDBCU_OUT_COUNT_STAR || out.kind == MDBCU_OUT_COUNT_COL)

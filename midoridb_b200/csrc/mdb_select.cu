@@ -89,8 +89,15 @@ extern "C" int mdbcu_select(mdbcu_ctx *ctx, const struct mdbcu_plan *plan, mdbcu
 	}
 	if (rc == MDBCU_EUNSUPPORTED) {
 		if (plan->flags & MDBCU_PLAN_DISTRIBUTED) {
-			rc = mdb_fail(ctx, MDBCU_EUNSUPPORTED, "this plan shape has no distributed implementation (join + GROUP BY join key + "
-					"COUNT(*), filter + aggregate scans and small-dimension star joins have)");
+			// GROUP BY / aggregates over one sharded table: local aggregate, partials all-gathered, merged by key on rank 0
+			release_result_buffers(res);
+			uint64_t keep_rows = ctx->stats.input_rows;
+			memset(&ctx->stats, 0, sizeof(ctx->stats));
+			ctx->stats.input_rows = keep_rows;
+			rc = mdb_select_general_dist(ctx, plan, res);
+			if (rc == MDBCU_EUNSUPPORTED)
+				rc = mdb_fail(ctx, MDBCU_EUNSUPPORTED, "this plan shape has no distributed implementation (join + GROUP BY join key + "
+						"COUNT(*), filter + aggregate scans, small-dimension star joins and GROUP BY over one sharded table have)");
 		} else {
 			release_result_buffers(res);
 			uint64_t keep_rows = ctx->stats.input_rows;

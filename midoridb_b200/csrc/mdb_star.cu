@@ -583,17 +583,15 @@ int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result 
 	// ---- probe: stream the fact table once
 	clock.begin(3);
 	const size_t smem = (((size_t)range * 2 + 15) & ~(size_t)15) + (size_t)ngroups * (na * 12 + 4);
-	cudaEvent_t k0, k1;
-	cudaEventCreate(&k0);
-	cudaEventCreate(&k1);
-	cudaEventRecord(k0, ctx->stream);
+	KernelTimer ktimer;
+	ktimer.start(ctx->stream);
 	if (sp.ncols == 1)
 		st_launch_probe<1>(ctx, ctx->num_sms, smem, na, sp, d_table, F->n_slots);
 	else if (sp.ncols == 2)
 		st_launch_probe<2>(ctx, ctx->num_sms, smem, na, sp, d_table, F->n_slots);
 	else
 		st_launch_probe<3>(ctx, ctx->num_sms, smem, na, sp, d_table, F->n_slots);
-	cudaEventRecord(k1, ctx->stream);
+	ktimer.stop(ctx->stream);
 	if (W > 1) {
 		unsigned char *all;
 		MDB_TRY(tmp.alloc(&all, block_bytes * W));
@@ -619,10 +617,7 @@ int mdb_select_direct_star(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result 
 	uint64_t nrows = 0;
 	MDB_TRY(mdb_read_u64(ctx, (const uint64_t*)d_nrows, &nrows));
 	clock.finish();
-	float kms = 0.f;
-	cudaEventElapsedTime(&kms, k0, k1);
-	cudaEventDestroy(k0);
-	cudaEventDestroy(k1);
+	const float kms = ktimer.ms();
 	if (e != cudaSuccess)
 		return mdb_fail(ctx, MDBCU_ECUDA, "star join launch failed: %s", cudaGetErrorString(e));
 	res->nrows = (W > 1 && ctx->rank != 0) ? 0 : nrows; // distributed: rank 0 returns the groups

@@ -823,11 +823,11 @@ extern "C" int mdbcu_table_append_columns(mdbcu_table *tt, size_t n_rows, const 
 		uint8_t *d_nulls = nullptr;
 		if (!col_data[c])
 			return mdb_fail(ctx, MDBCU_EERROR, "mdbcu_table_append_columns: column %d has no data", c);
-		CUDA_TRY(ctx, cudaMemcpyAsync(col.data + first, col_data[c], n_rows * sizeof(int64_t), cudaMemcpyHostToDevice,
-				ctx->stream));
+		// (cudaMemcpyDefault: the arrays may be host or device memory - mdb_dist_group.cu appends device-resident partials)
+		CUDA_TRY(ctx, cudaMemcpyAsync(col.data + first, col_data[c], n_rows * sizeof(int64_t), cudaMemcpyDefault, ctx->stream));
 		if (col_nulls && col_nulls[c]) {
 			MDB_TRY(tmp.alloc(&d_nulls, n_rows));
-			CUDA_TRY(ctx, cudaMemcpyAsync(d_nulls, col_nulls[c], n_rows, cudaMemcpyHostToDevice, ctx->stream));
+			CUDA_TRY(ctx, cudaMemcpyAsync(d_nulls, col_nulls[c], n_rows, cudaMemcpyDefault, ctx->stream));
 		}
 		MDB_LAUNCH(ctx, k_finish_column, grid, 256, 0, col.data, col.present, d_nulls, first, (uint64_t)n_rows,
 				type_is_intlike(col.type) ? 1 : 0, c, t->x.d_stats);
