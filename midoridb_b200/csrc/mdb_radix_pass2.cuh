@@ -12,6 +12,9 @@
 //     write to consecutive output rows, so every store instruction covers a contiguous run;
 //   * with 4-bit counters two CTAs share an SM: one emits while the other loads.
 #pragma once
+#ifndef RJ_P2_MLP
+#define RJ_P2_MLP 2
+#endif
 
 struct RJOut {
 	int nout;
@@ -59,7 +62,7 @@ template <int BITS, int THREADS, bool TAIL>
 __device__ __forceinline__ uint32_t rj_histogram_run(const uint16_t *__restrict__ run, uint32_t ne, uint32_t *cnt)
 {
 	uint32_t counted = 0;
-	constexpr int MLP = 2; // 32-byte vectors in flight per thread
+	constexpr int MLP = RJ_P2_MLP; // 32-byte vectors in flight per thread
 	const uint32_t nvec = (ne + 15u) / 16u;
 	for (uint32_t v0 = threadIdx.x; v0 < nvec; v0 += THREADS * MLP) {
 		uint32_t w[MLP][8];
