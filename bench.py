@@ -363,6 +363,54 @@ def run_config2(be, args, peak, log2_rows=30, steps=5, warmup=3):
             "note": "query time includes the 16-byte result fetch and the host round trip"}
 
 
+def run_k1(be, args, peak, log2_rows=28, steps=5, warmup=2):
+    """K1 of the north star on the GENERAL operators: SELECT k, v FROM T WHERE k < lo OR k >= hi (an OR: not the fused scan's
+    shape) - predicate evaluation into a verdict bitmap, ballot compaction into a selection vector, gather of the projected
+    columns.  Algorithmic bytes: 16 B per input row + 16 B per result row."""
+    import torch
+    from midoridb_b200 import capi
+    n = 1 << log2_rows
+    t = be.create_table("T", [capi.CT_INTEGER, capi.CT_INTEGER])
+    t.generate(n, [capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=0, hi=(1 << 31) - 1, seed=5),
+                   capi.GenSpec(kind=capi.GEN_UNIFORM_INT, lo=-(1 << 40), hi=1 << 40, seed=6)])
+    lo, hi = 107374182, 2040109465  # 5 % below, 5 % above: 10 % of the rows qualify
+    plan = capi.make_plan([t], pred=[("col", 0, 0), ("int", lo), ("cmp", 1), ("col", 0, 0), ("int", hi), ("cmp", 6), ("or",)],
+                          out=[(capi.OUT_COLUMN, 0, 0), (capi.OUT_COLUMN, 0, 1)])
+    got = {}
+
+    def step(keep=False):
+        res = be.select(plan)
+        st = be.stats()
+        got["n"] = res.nrows
+        if keep:
+            return st, res
+        res.free()
+        return st
+
+    ms, st = _timed(be, step, steps, warmup)
+    verified = None
+    if not args.no_verify:
+        _, res = step(keep=True)
+        rk = torch.as_tensor(capi.DeviceArray(res.device_ptr(0), res.nrows, "<i8"), device=torch.device("cuda", be.device))
+        rv = torch.as_tensor(capi.DeviceArray(res.device_ptr(1), res.nrows, "<i8"), device=torch.device("cuda", be.device))
+        k, v = _dev_tensor(t, 0), _dev_tensor(t, 1)
+        m = (k < lo) | (k >= hi)
+        verified = bool(int(m.sum()) == res.nrows and int(k[m].sum()) == int(rk.sum()) and int(v[m].sum()) == int(rv.sum())
+                        and int((k[m] ^ v[m]).sum()) == int((rk ^ rv).sum()))  # (the pairing of the two columns survives)
+        del rk, rv, k, v, m
+        res.free()
+        torch.cuda.empty_cache()
+    t.drop()
+    alg = 16 * n + 16 * got["n"]
+    gbs = alg / (ms / 1000.0) / 1e9
+    return {"config": "K1", "workload": "SELECT k, v FROM T WHERE k < lo OR k >= hi, 2^%d rows BIGINT/BIGINT, 10%% selectivity (general "
+                                        "operators: predicate program -> verdict bitmap -> compaction -> gather)" % log2_rows,
+            "path": "general operators (k_eval_pred, bitmap compaction, k_gather_out)", "ms_per_query": ms, "rows_per_s": n / (ms / 1000.0),
+            "result_rows": int(got["n"]), "algorithmic_bytes": alg, "achieved_gbs": gbs, "peak_gbs": peak, "frac": gbs / peak,
+            "kernel_launches": int(st.kernel_launches), "phase_ms": [float(x) for x in st.phase_ms], "verified": verified,
+            "verified_how": "row count, sums of both columns and the sum of k XOR v against torch on the mirrored columns"}
+
+
 def run_config5(be, args, peak, log2_rows=30, steps=5, warmup=3):
     """D(id, g) 65 536 rows JOIN F(fk, m) 2^30 rows ON id = fk GROUP BY g MIN(m), MAX(m): 16 B per fact row read once"""
     import torch
@@ -699,6 +747,7 @@ def main():
         extra = {}
         for c in (2, 4, 5):
             extra["config_%d" % c] = EXTRA[c](be, args, peak)
+        extra["k1_filter_projection"] = run_k1(be, args, peak)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -276,12 +276,20 @@ static int grid_for(mdbcu_ctx *ctx, uint64_t n, int threads)
 }
 
 // FROM <table>: live rows in storage order (proc_from_clause_table, executor_select.c:1295-1306)
-static int scan_live(mdbcu_ctx *ctx, const mdbcu_table *t, Tuples *out)
+// identity_ok: the caller's operators all read row ids through TupleRows / k_gather_out (plans without a join): a table
+// without tombstones then needs no row-id array - tuple i IS row i (rid[0] stays nullptr).  K1 of the north star
+// (predicate scan -> selection vector) ran at 4.2 ms for 2^28 rows with the 1 GiB iota array written, read by the
+// predicate kernel and read again by the compaction; without it the predicate kernel reads the columns coalesced.
+static int scan_live(mdbcu_ctx *ctx, const mdbcu_table *t, Tuples *out, bool identity_ok)
 {
 	out->ntab = 1;
 	out->n = 0;
 	if (t->n_slots == 0)
 		return MDBCU_OK;
+	if (t->all_live && identity_ok) {
+		out->n = t->n_slots;
+		return MDBCU_OK;
+	}
 	if (t->all_live) {
 		MDB_TRY(mdb_alloc(ctx, &out->rid[0], t->n_slots));
 		MDB_LAUNCH(ctx, k_iota, grid_for(ctx, t->n_slots, 256), 256, 0, out->rid[0], t->n_slots);
@@ -303,7 +311,7 @@ struct DPredOp {
 	double dval;
 };
 
-// one `<column> <cmp> <literal>` term of a conjunction (see DPredProgram::n_terms)
+// one `<column> <cmp> <literal>` / `<column> IS [NOT] NULL` term (see DPredProgram::n_terms); cmp 7 = IS NULL, 8 = IS NOT NULL
 struct DPredTerm {
 	int32_t tbl, cmp;
 	int32_t as_dbl;  // compare as doubles (DOUBLE column or DOUBLE literal), else as int64
@@ -318,9 +326,14 @@ struct DPredTerm {
 
 struct DPredProgram {
 	int32_t n;
-	// > 0: the program is a conjunction of n_terms `<column> <cmp> <literal>` terms (the common WHERE shape: BASELINE configs 2
-	// and 4), compiled on the host; the kernels evaluate the terms directly - no operand stack in local memory, no decoding
+	// > 0: the program is a boolean combination (AND / OR / XOR) of n_terms <= 8 terms `<column> <cmp> <literal>` or
+	// `<column> IS [NOT] NULL`, compiled on the host: the kernels evaluate the terms directly and look the verdict up in the
+	// combination's truth table (bit m of `truth` = verdict when the terms' outcomes are the bits of m) - no operand stack in
+	// local memory, no decoding.  conj: the combination is the AND of all terms (the common WHERE shape: BASELINE configs 2
+	// and 4) - the first false term ends the evaluation.
 	int32_t n_terms;
+	int32_t conj;
+	uint32_t truth[8];
 	DPredOp ops[MDBCU_MAX_PRED];
 	DPredTerm terms[PRED_MAX_TERMS];
 };
@@ -364,7 +377,12 @@ __device__ static inline bool pv_cmp(int cmp, PVal a, PVal b)
 struct TupleRows {
 	const TuplesDev *ts;
 	uint64_t i;
-	__device__ uint32_t operator()(int t) const { return ts->rid[t][i]; }
+	// (a missing array = the identity: the rows of a single, fully live table need no row-id array at all)
+	__device__ uint32_t operator()(int t) const
+	{
+		const uint32_t *c = ts->rid[t];
+		return c ? c[i] : (uint32_t)i;
+	}
 };
 // ... the fused multiway aggregate holds them in registers.
 struct StarRows {
@@ -376,24 +394,31 @@ template <typename Rows>
 __device__ static bool eval_program(const DPredProgram *__restrict__ prog, const Rows &rows)
 {
 	if (prog->n_terms > 0) {
+		uint32_t outcome = 0;
 		for (int k = 0; k < prog->n_terms; k++) {
 			const DPredTerm &t = prog->terms[k];
 			const uint32_t r = rows(t.tbl);
-			if (t.present && !mdb_bit(t.present, r))
-				return false; // NULL operand: the comparison is not true (executor_select.c:629-631)
-			const long long v = t.data[r];
+			const bool present = !t.present || mdb_bit(t.present, r);
 			bool ok;
-			if (t.as_dbl) {
-				const double x = t.col_dbl ? __longlong_as_double(v) : (double)v, y = t.dlit;
-				ok = t.cmp == 1 ? x < y : t.cmp == 2 ? x > y : t.cmp == 3 ? x != y : t.cmp == 4 ? x == y : t.cmp == 5 ? x <= y : x >= y;
+			if (t.cmp >= 7) {
+				ok = present == (t.cmp == 8);
+			} else if (!present) {
+				ok = false; // NULL operand: the comparison is not true (executor_select.c:629-631)
 			} else {
-				const long long y = t.ilit;
-				ok = t.cmp == 1 ? v < y : t.cmp == 2 ? v > y : t.cmp == 3 ? v != y : t.cmp == 4 ? v == y : t.cmp == 5 ? v <= y : v >= y;
+				const long long v = t.data[r];
+				if (t.as_dbl) {
+					const double x = t.col_dbl ? __longlong_as_double(v) : (double)v, y = t.dlit;
+					ok = t.cmp == 1 ? x < y : t.cmp == 2 ? x > y : t.cmp == 3 ? x != y : t.cmp == 4 ? x == y : t.cmp == 5 ? x <= y : x >= y;
+				} else {
+					const long long y = t.ilit;
+					ok = t.cmp == 1 ? v < y : t.cmp == 2 ? v > y : t.cmp == 3 ? v != y : t.cmp == 4 ? v == y : t.cmp == 5 ? v <= y : v >= y;
+				}
 			}
-			if (!ok)
+			if (prog->conj && !ok)
 				return false;
+			outcome |= (ok ? 1u : 0u) << k;
 		}
-		return true;
+		return prog->conj || ((prog->truth[outcome >> 5] >> (outcome & 31u)) & 1u) != 0;
 	}
 	PVal st[PRED_STACK];
 	int sp = 0;
@@ -491,24 +516,41 @@ static bool col_all_present(const mdbcu_table *t, int col)
 	return t->all_live && !t->cols[col].has_nulls;
 }
 
-// Is the postfix program `t1 t2 AND t3 AND ...` (any association) with every t = <column> <literal> CMP or <literal> <column> CMP?
-// Then fill h->terms.  (A host-side stack of "what kind of thing is on the operand stack" walks the program once.)
-static void compile_conjunction(DPredProgram *h)
+// Is the postfix program a boolean combination (AND / OR / XOR, any nesting) of at most 8 terms `<column> <literal> CMP`,
+// `<literal> <column> CMP`, `<column> IS NULL`, `<column> IS NOT NULL`?  Then fill h->terms and the combination's truth table.
+// A host-side stack walks the program once; a boolean item carries ITS truth table over the terms seen so far, so AND / OR /
+// XOR of two items is the bitwise operation on their tables.
+static void compile_terms(DPredProgram *h)
 {
-	enum { COL, LIT, CONJ };
+	enum { COL, LIT, BOOL };
 	struct Item {
 		int kind, op;
+		uint32_t tt[8];
 	} st[PRED_STACK + 1];
 	int sp = 0, nt = 0;
 	DPredTerm terms[PRED_MAX_TERMS];
+	auto push_term = [&](int k) {
+		Item it;
+		it.kind = BOOL;
+		it.op = 0;
+		for (uint32_t m = 0; m < 256; m++) {
+			if ((m & 31u) == 0)
+				it.tt[m >> 5] = 0;
+			if ((m >> k) & 1u)
+				it.tt[m >> 5] |= 1u << (m & 31u);
+		}
+		st[sp++] = it;
+	};
 	for (int k = 0; k < h->n; k++) {
 		const DPredOp &o = h->ops[k];
 		switch (o.op) {
 		case MDBCU_P_COL:
-			st[sp++] = {COL, k};
+			st[sp].kind = COL;
+			st[sp++].op = k;
 			break;
 		case MDBCU_P_INT: case MDBCU_P_DBL:
-			st[sp++] = {LIT, k};
+			st[sp].kind = LIT;
+			st[sp++].op = k;
 			break;
 		case MDBCU_P_CMP: {
 			if (sp < 2 || nt == PRED_MAX_TERMS)
@@ -518,7 +560,7 @@ static void compile_conjunction(DPredProgram *h)
 				return;
 			const DPredOp &c = h->ops[a.kind == COL ? a.op : b.op], &l = h->ops[a.kind == COL ? b.op : a.op];
 			static const int flipped[7] = {0, 2, 1, 3, 4, 6, 5}; // literal on the left: a < b  <=>  b > a
-			DPredTerm &t = terms[nt++];
+			DPredTerm &t = terms[nt];
 			t.tbl = c.tbl;
 			t.cmp = a.kind == COL ? o.arg : flipped[o.arg];
 			t.col_dbl = c.is_dbl;
@@ -527,23 +569,48 @@ static void compile_conjunction(DPredProgram *h)
 			t.present = c.present;
 			t.ilit = l.ival;
 			t.dlit = l.op == MDBCU_P_DBL ? l.dval : (double)l.ival;
-			st[sp++] = {CONJ, 0};
+			push_term(nt++);
 			break;
 		}
-		case MDBCU_P_AND: {
-			if (sp < 2 || st[sp - 1].kind != CONJ || st[sp - 2].kind != CONJ)
+		case MDBCU_P_ISNULL: case MDBCU_P_ISNOTNULL: {
+			if (sp < 1 || nt == PRED_MAX_TERMS || st[sp - 1].kind != COL)
 				return;
-			sp--;
+			const DPredOp &c = h->ops[st[--sp].op];
+			DPredTerm &t = terms[nt];
+			memset(&t, 0, sizeof(t));
+			t.tbl = c.tbl;
+			t.cmp = o.op == MDBCU_P_ISNULL ? 7 : 8;
+			t.data = c.data;
+			t.present = c.present;
+			push_term(nt++);
+			break;
+		}
+		case MDBCU_P_AND: case MDBCU_P_OR: case MDBCU_P_XOR: {
+			if (sp < 2 || st[sp - 1].kind != BOOL || st[sp - 2].kind != BOOL)
+				return;
+			const Item b = st[--sp];
+			Item &a = st[sp - 1];
+			for (int w = 0; w < 8; w++)
+				a.tt[w] = o.op == MDBCU_P_AND ? (a.tt[w] & b.tt[w]) : o.op == MDBCU_P_OR ? (a.tt[w] | b.tt[w]) : (a.tt[w] ^ b.tt[w]);
 			break;
 		}
 		default:
 			return;
 		}
 	}
-	if (sp != 1 || st[0].kind != CONJ || nt == 0)
+	if (sp != 1 || st[0].kind != BOOL || nt == 0)
 		return;
 	for (int k = 0; k < nt; k++)
 		h->terms[k] = terms[k];
+	// only the outcomes of the nt terms that exist matter: bit m of the table for m < 2^nt
+	const uint32_t all = (1u << nt) - 1u;
+	bool conj = true;
+	for (uint32_t m = 0; m <= all; m++)
+		if ((((st[0].tt[m >> 5] >> (m & 31u)) & 1u) != 0) != (m == all))
+			conj = false;
+	for (int w = 0; w < 8; w++)
+		h->truth[w] = st[0].tt[w];
+	h->conj = conj ? 1 : 0;
 	h->n_terms = nt;
 }
 
@@ -552,6 +619,7 @@ static int build_pred(mdbcu_ctx *ctx, const mdbcu_plan *plan, DPredProgram *h)
 	int depth = 0;
 	h->n = plan->n_pred;
 	h->n_terms = 0;
+	h->conj = 0;
 	if (plan->n_pred < 0 || plan->n_pred > MDBCU_MAX_PRED)
 		return mdb_fail(ctx, MDBCU_EERROR, "predicate program too long");
 	for (int k = 0; k < plan->n_pred; k++) {
@@ -604,7 +672,7 @@ static int build_pred(mdbcu_ctx *ctx, const mdbcu_plan *plan, DPredProgram *h)
 	}
 	if (plan->n_pred && depth != 1)
 		return mdb_fail(ctx, MDBCU_EERROR, "malformed predicate program");
-	compile_conjunction(h);
+	compile_terms(h);
 	return MDBCU_OK;
 }
 
@@ -879,7 +947,7 @@ static int join_step(mdbcu_ctx *ctx, const mdbcu_plan *plan, int j, Tuples *ts)
 	if (jn.cross) {
 		// comma list / ON 1=1: every pair (wrap_on_join_node, optimiser_select.c:395)
 		Tuples right;
-		MDB_TRY(scan_live(ctx, rt, &right));
+		MDB_TRY(scan_live(ctx, rt, &right, false));
 		uint64_t total = ts->n * right.n;
 		int rc = alloc_out_tuples(ctx, &out, ts->ntab + 1, total, &arr);
 		if (rc == MDBCU_OK && total) {
@@ -1395,7 +1463,8 @@ __global__ void k_gather_out(const DGroupSpec *__restrict__ sp, TuplesDev ts, DR
 	for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < ts.n; i += (uint64_t)gridDim.x * blockDim.x) {
 		for (int o = 0; o < sp->n_out; o++) {
 			const DOut &out = sp->out[o];
-			uint32_t r = ts.rid[out.tbl][i];
+			const uint32_t *c = ts.rid[out.tbl];
+			uint32_t r = c ? c[i] : (uint32_t)i; // (identity tuples: scan_live)
 			bool isnull = out.present && !mdb_bit(out.present, r);
 			res.cells[o][i] = isnull ? 0 : out.data[r];
 			res.nulls[o][i] = isnull;
@@ -1792,7 +1861,7 @@ int mdb_select_general(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result *res
 
 	ctx->stats.path = MDBCU_PATH_GENERAL;
 	clock.begin(0);
-	rc = scan_live(ctx, plan->tables[0], &ts);
+	rc = scan_live(ctx, plan->tables[0], &ts, plan->n_joins == 0);
 	lap("general: scan", ts.n);
 	for (int j = 0; rc == MDBCU_OK && j < plan->n_joins; j++) {
 		clock.begin(j == 0 ? 2 : 3);
