@@ -674,6 +674,47 @@ def test_join_count_wide_key_range_takes_direct_count(be):
         t.drop()
 
 
+@pytest.mark.parametrize("n", [1000, 4097, 300001])
+def test_predicate_scan_term_programs(be, n):
+    """K1 on one fully live table (identity tuples, k_eval_terms_scan): WHERE programs that are AND / OR / XOR combinations of
+    column-vs-literal and IS [NOT] NULL terms are compiled into a truth table on the host; programs outside that shape (IN
+    lists, column vs column, more than eight terms) take the postfix interpreter.  Projection and aggregate consumers, NULL
+    cells, DOUBLE comparisons, literals on the left, ragged sizes (not a multiple of 256 rows): all equal to the oracle, and
+    projections come back in storage order."""
+    rng = np.random.default_rng(500 + n)
+    cols = [rng.integers(-50, 50, n), rng.random(n), rng.integers(0, 1000, n)]
+    nulls = [(rng.random(n) < 0.1).astype(np.uint8), (rng.random(n) < 0.1).astype(np.uint8), np.zeros(n, np.uint8)]
+    g, o = both_tables(be, [I, D, I], cols, nulls)
+    preds = [
+        # (a < 0 OR a >= 40)
+        [("col", 0, 0), ("int", 0), ("cmp", 1), ("col", 0, 0), ("int", 40), ("cmp", 6), ("or",)],
+        # (0.5 > b) XOR (c <> 7)   - literal on the left, DOUBLE compare
+        [("dbl", 0.5), ("col", 0, 1), ("cmp", 2), ("col", 0, 2), ("int", 7), ("cmp", 3), ("xor",)],
+        # a IS NULL OR (b IS NOT NULL AND b <= 0.25 AND c >= 100)
+        [("col", 0, 0), ("isnull",), ("col", 0, 1), ("isnotnull",), ("col", 0, 1), ("dbl", 0.25), ("cmp", 5), ("and",),
+         ("col", 0, 2), ("int", 100), ("cmp", 6), ("and",), ("or",)],
+        # a conjunction of three terms (the early-exit shape), an INT column against a DOUBLE literal
+        [("col", 0, 0), ("dbl", -10.5), ("cmp", 2), ("col", 0, 2), ("int", 900), ("cmp", 1), ("and",), ("col", 0, 1), ("dbl", 0.9), ("cmp", 1), ("and",)],
+        # eight terms: ((t1 OR t2) AND (t3 OR t4)) XOR ((t5 AND t6) OR (t7 AND t8))
+        [("col", 0, 0), ("int", -25), ("cmp", 1), ("col", 0, 0), ("int", 25), ("cmp", 2), ("or",),
+         ("col", 0, 2), ("int", 500), ("cmp", 1), ("col", 0, 1), ("dbl", 0.75), ("cmp", 6), ("or",), ("and",),
+         ("col", 0, 2), ("int", 250), ("cmp", 6), ("col", 0, 2), ("int", 750), ("cmp", 5), ("and",),
+         ("col", 0, 1), ("dbl", 0.1), ("cmp", 1), ("col", 0, 0), ("int", 0), ("cmp", 4), ("and",), ("or",), ("xor",)],
+        # outside the compiled shape: IN list, column vs column, nine terms
+        [("col", 0, 2), ("int", 3), ("int", 5), ("int", 8), ("in", 3), ("col", 0, 0), ("int", 10), ("cmp", 2), ("or",)],
+        [("col", 0, 0), ("col", 0, 2), ("cmp", 1), ("col", 0, 1), ("dbl", 0.5), ("cmp", 2), ("and",)],
+        [("col", 0, 2), ("int", 100), ("cmp", 1)] + sum([[("col", 0, 2), ("int", 100 + 90 * k), ("cmp", 2), ("xor",)] for k in range(1, 9)], []),
+    ]
+    for pred in preds:
+        grows, orows, _, st = run_both(be, [g], [o], pred=pred, out=[(OUT_COLUMN, 0, 2), (OUT_COLUMN, 0, 0), (OUT_COLUMN, 0, 1)])
+        assert st.path == capi.PATH_GENERAL
+        assert grows == [helpers.norm_row(r) for r in orows], pred  # same rows, same (storage) order
+        grows, orows, _, _ = run_both(be, [g], [o], pred=pred, group=[(0, 0)],
+                                      out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,), (OUT_SUM, 0, 2), (OUT_MIN, 0, 1)])
+        assert helpers.canon_close(grows, orows, rel=1e-9), pred
+    g.drop()
+
+
 def _tail_cases():
     from tests.test_oracle import TAIL_CASES
     return TAIL_CASES
