@@ -567,19 +567,33 @@ __global__ void __launch_bounds__(EVT_THREADS) k_eval_terms_scan(const DPredProg
 			if (t.cmp >= 7) {
 				okmask = t.cmp == 8 ? pres : (~pres & 0xffu);
 			} else {
-#pragma unroll
-				for (int j = 0; j < 8; j++) {
-					const long long v = (long long)(((unsigned long long)raw[2 * j + 1] << 32) | raw[2 * j]);
-					bool ok;
-					if (t.as_dbl) {
-						const double x = t.col_dbl ? __longlong_as_double(v) : (double)v, y = t.dlit;
-						ok = t.cmp == 1 ? x < y : t.cmp == 2 ? x > y : t.cmp == 3 ? x != y : t.cmp == 4 ? x == y : t.cmp == 5 ? x <= y : x >= y;
-					} else {
-						const long long y = t.ilit;
-						ok = t.cmp == 1 ? v < y : t.cmp == 2 ? v > y : t.cmp == 3 ? v != y : t.cmp == 4 ? v == y : t.cmp == 5 ? v <= y : v >= y;
-					}
-					okmask |= (ok ? 1u : 0u) << j;
+				// the comparison is chosen ONCE per term and 8 rows (all branches here are uniform): per row one compare and one OR
+#define EVT_ROWS(EXPR)                                                                                                   \
+	_Pragma("unroll") for (int j = 0; j < 8; j++) {                                                                  \
+		const long long v = (long long)(((unsigned long long)raw[2 * j + 1] << 32) | raw[2 * j]);                \
+		okmask |= ((EXPR) ? 1u : 0u) << j;                                                                       \
+	}
+#define EVT_CMPS(X, Y)                                                                                                   \
+	switch (t.cmp) {                                                                                                 \
+	case 1: EVT_ROWS((X) < (Y)) break;                                                                               \
+	case 2: EVT_ROWS((X) > (Y)) break;                                                                               \
+	case 3: EVT_ROWS((X) != (Y)) break;                                                                              \
+	case 4: EVT_ROWS((X) == (Y)) break;                                                                              \
+	case 5: EVT_ROWS((X) <= (Y)) break;                                                                              \
+	default: EVT_ROWS((X) >= (Y)) break;                                                                             \
+	}
+				if (!t.as_dbl) {
+					const long long y = t.ilit;
+					EVT_CMPS(v, y)
+				} else if (t.col_dbl) {
+					const double y = t.dlit;
+					EVT_CMPS(__longlong_as_double(v), y)
+				} else {
+					const double y = t.dlit;
+					EVT_CMPS((double)v, y)
 				}
+#undef EVT_CMPS
+#undef EVT_ROWS
 				okmask &= pres; // NULL operand: the comparison is not true (executor_select.c:629-631)
 			}
 			if (conj) {
