@@ -1,15 +1,9 @@
-// mdb_fast.cu - fused kernels for the benchmark shapes of the hot path (BASELINE.json configs).
+// mdb_fast.cu - the fused filter + aggregate scan (BASELINE.json config 2), single-GPU and distributed.
 //
 //  K2 scan_filter_aggregate  : SELECT <aggregates> FROM T WHERE <range conjunction>   (config 2)
 //       replaces proc_from_clause_table :1282 + proc_where_clause :1435 + handle_countonly_case :1590
 //       of src/engine/executor_select.c with ONE pass over the referenced columns.
-//  K7/K3/K4 radix join+count : SELECT k, COUNT(*) FROM A INNER JOIN B ON A.k = B.k GROUP BY k   (README query,
-//       configs 1 and 3) replaces _join_nested_loop_tbl2tbl :1076 + proc_groupby_clause :1526.
-//       result(k) = cntA[k] * cntB[k]; no pair is ever materialised.
-//       pass 1 (k_radix_partition): stream the 8-byte keys once, write 2-byte remainders into
-//               per-partition chunk lists (partition = high bits of key - kmin);
-//       pass 2 (k_radix_joincount): per partition, two byte-counter histograms in shared memory,
-//               multiply, emit (key, count) groups.
+//  (the radix join+count of the README query lives in mdb_radix.cu, the small-build star join in mdb_star.cu)
 //  HBM-bound integer work throughout: no tensor cores (nothing here is a dense contraction).
 #include "mdb_common.cuh"
 
