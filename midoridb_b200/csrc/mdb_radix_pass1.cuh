@@ -39,9 +39,7 @@ __device__ unsigned long long rj_timeline[4][8];
 #endif
 
 #define RJ_P1_WARPS (RJ_P1_THREADS / 32)
-#ifndef RJ_P1_KEYS
-#define RJ_P1_KEYS 8               // keys per thread per round (a multiple of 4: 256-bit loads)
-#endif
+#define RJ_P1_KEYS 8               // keys per thread per round
 #define RJ_WARP_PARTS (RJ_ROWS / RJ_P1_WARPS) // staging rows one warp flushes
 
 #ifndef RJ_LOAD_AT
@@ -352,9 +350,8 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition_fas
 	uint64_t tile = slot;
 	const char *src = reinterpret_cast<const char*>(s.keys + tile * TILE) + tid * 32u;
 	if (tile < nfull) {
-#pragma unroll
-		for (int q = 0; q < RJ_P1_KEYS / 4; q++)
-			rj_load_keys256(src + q * (RJ_P1_THREADS * 32u), buf + 4 * q, evict_first);
+		rj_load_keys256(src, buf, evict_first);
+		rj_load_keys256(src + RJ_P1_THREADS * 32u, buf + 4, evict_first);
 	}
 	while (tile < nfull) {
 		uint32_t item[RJ_P1_KEYS];
@@ -377,11 +374,8 @@ __global__ void __launch_bounds__(RJ_P1_THREADS, RJ_SPLIT) k_radix_partition_fas
 				rj_load_keys256(src, buf, evict_first);
 		};
 		auto load_hi = [&]() {
-			if (more) {
-#pragma unroll
-				for (int q = 1; q < RJ_P1_KEYS / 4; q++)
-					rj_load_keys256(src + q * (RJ_P1_THREADS * 32u), buf + 4 * q, evict_first);
-			}
+			if (more)
+				rj_load_keys256(src + RJ_P1_THREADS * 32u, buf + 4, evict_first);
 		};
 		if (RJ_LOAD_AT == 1) { // both 256-bit loads when this warp's keys are in shared memory, ahead of the first barrier
 			load_lo();
