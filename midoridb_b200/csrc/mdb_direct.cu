@@ -24,7 +24,8 @@
 #include <string.h>
 #include <algorithm>
 
-#define DC_MAX_RANGE (1ull << 30) // key values per side (4 GiB of counters each)
+#define DC_MAX_RANGE (1ull << 30) // key values per side and window (4 GiB of counters each)
+#define DC_MAX_WINDOWS 16         // single-GPU plans: wider key ranges are counted window by window (every window reads the keys again)
 #define DC_THREADS 256
 
 struct DCSide {
@@ -209,15 +210,22 @@ int mdb_select_direct_count(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result
 	ctx->stats.path = MDBCU_PATH_DIRECT_COUNT;
 	if (ca.imin > ca.imax || cb.imin > cb.imax || kmin > kmax)
 		return mdb_result_alloc(ctx, plan, res, 0, false);
-	const unsigned long long range = (unsigned long long)kmax - (unsigned long long)kmin + 1ull;
-	if (range == 0 || range > DC_MAX_RANGE)
+	const unsigned long long full_range = (unsigned long long)kmax - (unsigned long long)kmin + 1ull;
+	if (full_range == 0 || full_range > DC_MAX_RANGE * (dist ? 1ull : (unsigned long long)DC_MAX_WINDOWS))
 		return MDBCU_EUNSUPPORTED;
+	// Single-GPU plans count key ranges beyond 2^30 values in WINDOWS of 2^30: per window the keys are streamed again (keys
+	// outside the window are skipped by the range test of k_dc_count), the counters are reused and the groups appended to
+	// the same result.  32-bit keys spread over [0, 2^32) - four windows - stay off the general operators, which would
+	// build a hash table over every row.
+	const unsigned long long range = std::min<unsigned long long>(full_range, DC_MAX_RANGE);
+	const int n_windows = (int)((full_range + DC_MAX_RANGE - 1) / DC_MAX_RANGE);
 
 	PhaseClock clock(ctx);
 	DevTemp tmp(ctx);
 	const int W = dist ? ctx->world : 1, me = dist ? ctx->rank : 0;
 	if (mdb_trace_level() >= 1)
-		fprintf(stderr, "[mdbcu] rank %d: direct count over %llu key values (%s)\n", me, range, forced ? "handed over by the radix join" : "distributed plan");
+		fprintf(stderr, "[mdbcu] rank %d: direct count over %llu key values in %d window(s) (%s)\n", me, full_range, n_windows,
+				forced ? "handed over by the radix join" : "distributed plan");
 	uint32_t *cnt; // [side A: range][side B: range]
 	unsigned long long *d_cursor;
 	MDB_TRY(tmp.alloc(&cnt, 2 * (size_t)range));
@@ -228,17 +236,21 @@ int mdb_select_direct_count(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result
 	clock.begin(2);
 	const mdbcu_table *tabs[2] = {ta, tb};
 	const int cols[2] = {jn.left.col, jn.right.col};
-	for (int side = 0; side < 2; side++) {
-		DCSide s;
-		s.keys = tabs[side]->cols[cols[side]].data;
-		s.present = dc_col_all_present(tabs[side], cols[side]) ? nullptr : tabs[side]->cols[cols[side]].present;
-		s.n = tabs[side]->n_slots;
-		if (s.n == 0)
-			continue;
-		const int grid = (int)std::min<uint64_t>(mdb_div_up(s.n, (size_t)DC_THREADS * 4), (uint64_t)ctx->num_sms * 8);
-		MDB_LAUNCH(ctx, k_dc_count, grid, DC_THREADS, 0, s, kmin, range, cnt + (size_t)side * range);
-	}
-	CUDA_CHECK_LAUNCH(ctx);
+	auto count_window = [&](long long wmin, unsigned long long wrange) -> int {
+		for (int side = 0; side < 2; side++) {
+			DCSide s;
+			s.keys = tabs[side]->cols[cols[side]].data;
+			s.present = dc_col_all_present(tabs[side], cols[side]) ? nullptr : tabs[side]->cols[cols[side]].present;
+			s.n = tabs[side]->n_slots;
+			if (s.n == 0)
+				continue;
+			const int grid = (int)std::min<uint64_t>(mdb_div_up(s.n, (size_t)DC_THREADS * 4), (uint64_t)ctx->num_sms * 8);
+			MDB_LAUNCH(ctx, k_dc_count, grid, DC_THREADS, 0, s, wmin, wrange, cnt + (size_t)side * range);
+		}
+		CUDA_CHECK_LAUNCH(ctx);
+		return MDBCU_OK;
+	};
+	MDB_TRY(count_window(kmin, range));
 
 	// this rank's slice of the key range (all of it on one GPU)
 	uint64_t own_first = 0, own_end = range;
@@ -251,7 +263,7 @@ int mdb_select_direct_count(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result
 	}
 
 	clock.begin(3);
-	uint64_t cap_groups = own_end - own_first;
+	uint64_t cap_groups = n_windows > 1 ? full_range : own_end - own_first;
 	if (!dist)
 		cap_groups = std::min<uint64_t>(cap_groups, std::min<uint64_t>(ta->n_slots, tb->n_slots));
 	MDB_TRY(mdb_result_alloc(ctx, plan, res, 0, false));
@@ -272,6 +284,18 @@ int mdb_select_direct_count(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result
 	if (own_end > own_first) {
 		const int grid = (int)std::min<uint64_t>(mdb_div_up(own_end - own_first, (size_t)DC_THREADS * 4), (uint64_t)ctx->num_sms * 8);
 		MDB_LAUNCH(ctx, k_dc_emit, grid, DC_THREADS, 0, cnt, cnt + range, own_first, own_end, kmin, out);
+		CUDA_CHECK_LAUNCH(ctx);
+	}
+	// the further windows of a wide key range (single-GPU plans): same counters, same result columns
+	for (int w = 1; w < n_windows; w++) {
+		const long long wmin = (long long)((unsigned long long)kmin + (unsigned long long)w * DC_MAX_RANGE);
+		const unsigned long long wrange = std::min<unsigned long long>(DC_MAX_RANGE, full_range - (unsigned long long)w * DC_MAX_RANGE);
+		clock.begin(2);
+		CUDA_TRY(ctx, cudaMemsetAsync(cnt, 0, 2 * (size_t)range * sizeof(uint32_t), ctx->stream));
+		MDB_TRY(count_window(wmin, wrange));
+		clock.begin(3);
+		const int grid = (int)std::min<uint64_t>(mdb_div_up(wrange, (size_t)DC_THREADS * 4), (uint64_t)ctx->num_sms * 8);
+		MDB_LAUNCH(ctx, k_dc_emit, grid, DC_THREADS, 0, cnt, cnt + range, (uint64_t)0, (uint64_t)wrange, wmin, out);
 		CUDA_CHECK_LAUNCH(ctx);
 	}
 	uint64_t ngroups = 0;

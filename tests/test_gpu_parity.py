@@ -653,16 +653,19 @@ def test_radix_joincount_key_words_and_layouts(be, where, layout):
         t.drop()
 
 
-def test_join_count_wide_key_range_takes_direct_count(be):
+@pytest.mark.parametrize("log2_half_range", [28, 31])
+def test_join_count_wide_key_range_takes_direct_count(be, log2_half_range):
     """keys spread over more than 2^28 values (4096 partitions x 2^16 remainders): the radix path hands the query to the
-    direct-count path (one 32-bit counter per key value), not to the general operators"""
+    direct-count path (one 32-bit counter per key value), not to the general operators; a range of 2^32 values - ordinary
+    32-bit keys - is counted in four windows of 2^30"""
     rng = np.random.default_rng(101)
     n = 1 << 21
-    a = rng.integers(-(1 << 28), 1 << 28, n)
-    b = rng.integers(-(1 << 28), 1 << 28, n + 4321)
+    h = 1 << log2_half_range
+    a = rng.integers(-h, h, n)
+    b = rng.integers(-h, h, n + 4321)
     b[:50000] = a[:50000]  # make sure there are matches
-    a[:3] = [-(1 << 28), (1 << 28) - 1, 0]
-    b[-3:] = [-(1 << 28), (1 << 28) - 1, 0]
+    a[:3] = [-h, h - 1, 0]
+    b[-3:] = [-h, h - 1, 0]
     ga, oa = both_tables(be, [I], [a])
     gb, ob = both_tables(be, [I], [b])
     grows, orows, _, st = run_both(be, [ga, gb], [oa, ob], joins=[((0, 0), (1, 0))], group=[(0, 0)],
