@@ -210,7 +210,8 @@ struct mdbcu_plan {
 	 * ORDER BY :183-191, LIMIT :193-196) and its semantic phase validates them (semantic_select.c:1895,2004), but its
 	 * executor never runs them (`TODO process distinct`, executor_select.c:1723): there is no reference
 	 * behaviour to match, the semantics are SQL's as sqlite3 implements them (the oracle is anchored on it).  Applied in
-	 * this order: HAVING, DISTINCT, ORDER BY, LIMIT.  All-zero = none.  Not available in MDBCU_PLAN_DISTRIBUTED plans. */
+	 * this order: HAVING, DISTINCT, ORDER BY, LIMIT.  All-zero = none.  In MDBCU_PLAN_DISTRIBUTED plans only over ONE sharded
+	 * table (rank 0 returns the whole result and applies them); a distributed join's result is spread over the ranks. */
 	int32_t distinct;                               /* SELECT DISTINCT: one row per distinct combination of ALL output columns (NULL = NULL) */
 	int32_t n_having;                               /* HAVING: postfix program over the result row, columns pushed with MDBCU_P_OUT */
 	struct mdbcu_pred_op having[MDBCU_MAX_HAVING];

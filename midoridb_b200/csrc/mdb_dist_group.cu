@@ -19,7 +19,8 @@
 // it, no qualifying row anywhere -> no result row (:1590), NULL group keys collate equal (:1476-1482: the NULL group of every
 // shard is one NULL-keyed partial row, and the merge groups NULL keys together again).
 // Plain (non-key) columns under GROUP BY carry "the group's first row" in the reference's row order, which has no
-// meaning across shards: such plans, joins and tail operators are not distributed here (MDBCU_EUNSUPPORTED).
+// meaning across shards: such plans and joins are not distributed here (MDBCU_EUNSUPPORTED).  HAVING / DISTINCT / ORDER BY /
+// LIMIT are applied by mdbcu_select afterwards, on rank 0's complete result (mdb_tail.cu).
 #include "mdb_common.cuh"
 
 #include <string.h>
@@ -53,8 +54,6 @@ int mdb_select_general_dist(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result
 	if (!(plan->flags & MDBCU_PLAN_DISTRIBUTED))
 		return MDBCU_EUNSUPPORTED;
 	if (plan->n_tables != 1 || plan->n_joins != 0 || plan->n_out < 1)
-		return MDBCU_EUNSUPPORTED;
-	if (plan->distinct || plan->n_having || plan->n_order || plan->has_limit)
 		return MDBCU_EUNSUPPORTED;
 	if (!mdb_comm_ready(ctx))
 		return mdb_fail(ctx, MDBCU_EERROR, "MDBCU_PLAN_DISTRIBUTED needs mdbcu_comm_init first");

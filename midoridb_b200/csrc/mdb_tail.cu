@@ -498,8 +498,10 @@ int mdb_validate_tail(mdbcu_ctx *ctx, const mdbcu_plan *plan)
 			return mdb_fail(ctx, MDBCU_EERROR, "mdbcu_select: ORDER BY column %d is not a result column", plan->order[k].out_col);
 	if (plan->has_limit && (plan->limit < 0 || plan->offset < 0))
 		return mdb_fail(ctx, MDBCU_EERROR, "mdbcu_select: negative LIMIT / OFFSET");
-	if (mdb_plan_has_tail(plan) && (plan->flags & MDBCU_PLAN_DISTRIBUTED))
-		return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "HAVING / DISTINCT / ORDER BY / LIMIT are not available in distributed plans "
+	// distributed plans: a plan over ONE sharded table returns all of its rows on rank 0 (mdb_fast.cu, mdb_dist_group.cu), where
+	// the tail operators then see the whole result; a join's result stays spread over the ranks that own its keys
+	if (mdb_plan_has_tail(plan) && (plan->flags & MDBCU_PLAN_DISTRIBUTED) && plan->n_tables != 1)
+		return mdb_fail(ctx, MDBCU_EUNSUPPORTED, "HAVING / DISTINCT / ORDER BY / LIMIT are not available in distributed joins "
 				"(every rank holds a part of the result)");
 	return MDBCU_OK;
 }

@@ -292,7 +292,8 @@ def test_loopback_star_join(world):
     assert helpers.canon_close(parts[0][0], oracle.rows_of(cells, nulls), rel=1e-9)
 
 
-@pytest.mark.parametrize("shape", ["int_key_all_aggs", "null_keys_where", "double_key", "two_keys", "no_group_general_pred", "nothing_qualifies"])
+@pytest.mark.parametrize("shape", ["int_key_all_aggs", "null_keys_where", "double_key", "two_keys", "no_group_general_pred", "nothing_qualifies",
+                                   "having_order_limit"])
 @pytest.mark.parametrize("world", [2, 3])
 def test_loopback_group_by_partials(world, shape):
     """GROUP BY / aggregates over ONE sharded table as a distributed plan (mdb_dist_group.cu): every rank aggregates its shard,
@@ -318,6 +319,10 @@ def test_loopback_group_by_partials(world, shape):
         kw = dict(group=[(0, 3)], out=[(OUT_COLUMN, 0, 3), (OUT_SUM, 0, 1), (OUT_COUNT_STAR,), (OUT_MIN, 0, 0), (capi.OUT_AVG, 0, 2)])
     elif shape == "two_keys":
         kw = dict(group=[(0, 0), (0, 3)], out=[(OUT_COLUMN, 0, 3), (OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,), (OUT_MAX, 0, 2), (capi.OUT_AVG, 0, 1)])
+    elif shape == "having_order_limit":
+        # tail operators run on rank 0's complete result: HAVING COUNT(*) > 100 ORDER BY COUNT(*) DESC, key LIMIT 25 OFFSET 3
+        kw = dict(group=[(0, 0)], out=[(OUT_COLUMN, 0, 0), (OUT_COUNT_STAR,), (capi.OUT_AVG, 0, 1)],
+                  having=[("out", 1), ("int", 100), ("cmp", 2)], order=[(1, True), (0, False)], limit=25, offset=3)
     elif shape == "no_group_general_pred":
         # an OR predicate: not the fused scan's shape, so the aggregate without GROUP BY comes here
         kw = dict(out=aggs, pred=[("col", 0, 0), ("int", 0), ("cmp", 1), ("col", 0, 3), ("int", 3), ("cmp", 3), ("or",)])
@@ -346,6 +351,10 @@ def test_loopback_group_by_partials(world, shape):
         assert want == [] and parts[0][0] == []
         return
     assert len(want) >= 1 and all(p[2] > 0 for p in parts)
+    if shape == "having_order_limit":  # ordered by (COUNT(*) DESC, key): an exact order, compare row by row
+        assert len(want) == 25
+        assert helpers.rows_close([helpers.norm_row(r) for r in parts[0][0]], [helpers.norm_row(r) for r in want], rel=1e-9)
+        return
     assert helpers.canon_close(parts[0][0], want, rel=1e-9)
     # keys, counts and integer aggregates are exact
     int_cols = [i for i, o in enumerate(kw["out"]) if o[0] in (OUT_COUNT_STAR, capi.OUT_COUNT_COL) or
