@@ -92,6 +92,17 @@ int mdb_select_general_dist(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result
 	}
 	if (!any_agg && plan->n_group == 0)
 		return MDBCU_EUNSUPPORTED; // a plain projection: nothing to merge
+	// every group key must be in the select list: the partial rows are merged ON those columns (a decision of the plan's
+	// shape, taken before any collective so that all ranks take it together)
+	for (int g = 0; g < plan->n_group; g++) {
+		bool listed = false;
+		for (int o = 0; o < plan->n_out; o++) {
+			int which;
+			listed = listed || (plan->out[o].kind == MDBCU_OUT_COLUMN && dg_is_key(plan, plan->out[o].ref, &which) && which == g);
+		}
+		if (!listed)
+			return MDBCU_EUNSUPPORTED;
+	}
 	const int W = ctx->world, me = ctx->rank;
 	const int nc = local.n_out;
 
@@ -209,7 +220,7 @@ int mdb_select_general_dist(mdbcu_ctx *ctx, const mdbcu_plan *plan, mdbcu_result
 	}
 	for (int g = 0; g < plan->n_group; g++) {
 		if (key_col[g] < 0)
-			return MDBCU_EUNSUPPORTED; // a group key that is not in the select list cannot be merged on (the partial rows lack it)
+			return mdb_fail(ctx, MDBCU_EINTERNAL, "distributed GROUP BY: group key %d is missing from the partial rows", g);
 		merge.group[g].tbl = 0;
 		merge.group[g].col = key_col[g];
 	}
