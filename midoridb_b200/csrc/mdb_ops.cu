@@ -486,8 +486,9 @@ __device__ static bool eval_program(const DPredProgram *__restrict__ prog, const
 	return sp == 1 && st[0].i != 0;
 }
 
-__global__ void k_eval_pred(const DPredProgram *__restrict__ prog, TuplesDev ts, uint32_t *__restrict__ bits)
+__global__ void k_eval_pred(const __grid_constant__ DPredProgram prog_, const __grid_constant__ TuplesDev ts, uint32_t *__restrict__ bits)
 {
+	const DPredProgram *prog = &prog_; // (a kernel parameter: the program is read from the constant bank, not from global memory)
 	// one aligned group of 32 tuples per warp iteration, so every ballot is exactly one bitmap word
 	uint64_t groups = (ts.n + 31) / 32;
 	uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
@@ -819,7 +820,7 @@ static int eval_pred_bits(mdbcu_ctx *ctx, const mdbcu_plan *plan, const Tuples &
 		MDB_LAUNCH(ctx, k_eval_terms_scan, (int)std::min<uint64_t>(mdb_div_up(ts.n, (uint64_t)EVT_THREADS * 8), (uint64_t)ctx->num_sms * 8),
 				EVT_THREADS, 0, (const DPredProgram*)d_prog, (uint64_t)ts.n, bits);
 	else
-		MDB_LAUNCH(ctx, k_eval_pred, grid_for(ctx, ts.n, 256), 256, 0, (const DPredProgram*)d_prog, to_dev(ts), bits);
+		MDB_LAUNCH(ctx, k_eval_pred, grid_for(ctx, ts.n, 256), 256, 0, h, to_dev(ts), bits);
 	CUDA_CHECK_LAUNCH(ctx);
 	*bits_out = bits;
 	return MDBCU_OK;
