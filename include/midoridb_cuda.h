@@ -93,7 +93,8 @@ int mdbcu_table_reload_pages(mdbcu_table *t, size_t first_page, const void *cons
 int mdbcu_table_tombstone(mdbcu_table *t, const uint64_t *page_idx, const uint32_t *slot_idx, size_t n);
 
 /* bulk columnar load (bench/e2e helper, no reference counterpart): col_data[c] = n_rows 8-byte cells,
- * col_nulls[c] = n_rows byte flags or NULL */
+ * col_nulls[c] = n_rows byte flags or NULL; the arrays may be host or device memory (the library's own distributed GROUP BY
+ * appends device-resident partial rows) */
 int mdbcu_table_append_columns(mdbcu_table *t, size_t n_rows, const void *const *col_data,
 		const uint8_t *const *col_nulls);
 
